@@ -1,0 +1,535 @@
+// fsg_api.cu — the extern "C" boundary of libfsg (include/fsg.h): context lifetime, host<->device
+// movement and the step schedule.  No torch types, no exceptions across the boundary, no CPU path.
+#include "fsg_internal.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+static std::string g_create_err;
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            char b_[512];                                                                               \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            (ctx)->err = b_;                                                                            \
+            return e_ == cudaErrorMemoryAllocation ? FSG_E_NOMEM : FSG_E_CUDA;                          \
+        }                                                                                               \
+    } while (0)
+
+int fsg_scene_plume_device(fsg_ctx *c, double spacing, double jitter, uint64_t seed, int64_t *n_out);
+
+// ---- host-derived fp32 thresholds (see FsgDev) ----
+static float largest_float_le(double v) { float f = (float)v; while ((double)f > v) f = nextafterf(f, -INFINITY); return f; }
+static float largest_float_lt(double v) { float f = (float)v; while ((double)f >= v) f = nextafterf(f, -INFINITY); return f; }
+
+void fsg_derive_constants(const fsg_config &cfg, FsgDev &d)
+{
+    d.G = cfg.grid;
+    d.G2 = cfg.grid * cfg.grid;
+    d.numcells = cfg.grid * cfg.grid * cfg.grid;
+    d.cap = cfg.neighbour_cap;
+    d.bin_cap = cfg.bin_cap;
+    d.origin = cfg.origin;
+    d.cellsize = cfg.cellsize;
+    d.h = cfg.h;
+    d.dt = cfg.dt;
+    d.gravity = cfg.gravity;
+    d.sound = cfg.sound;
+    d.alpha_fluid = cfg.alpha_fluid;
+    d.alpha_boundary = cfg.alpha_boundary;
+    const double h = cfg.h;
+    // gate of FluidGPU.cu:236: (double)ds <= 2*cutoff with ds = sqrtf(d2)  <=>  d2 <= d2_max
+    float ds_max = largest_float_le(2 * h);
+    float d2 = ds_max * ds_max;
+    while (sqrtf(d2) > ds_max) d2 = nextafterf(d2, 0.f);
+    while (sqrtf(nextafterf(d2, INFINITY)) <= ds_max) d2 = nextafterf(d2, INFINITY);
+    d.d2_max = d2;
+    d.h_le = largest_float_le(h);
+    d.h_lt = largest_float_lt(h);
+    d.twoh_lt = largest_float_lt(2 * h);
+    d.hf = (float)h;
+    d.inv_h = (float)(1.0 / h);
+    d.w_c = (float)(1. / 3.14159 / (double)powf((float)h, 3.f));
+    d.dw_c = (float)(-45.0 / 3.14159 / (double)powf((float)h, 6.f));
+    d.w0 = (float)(1. / 3.14159 / (double)powf((float)h, 3.f) * (1 - 3. / 2. * 0.0 + 3. / 4. * 0.0));   // kernel(0)
+    d.eps = (float)(0.01 * (double)powf((float)h, 2.f));
+    d.visc_c = (float)(cfg.alpha_fluid * cfg.sound);
+    d.visc_q = (float)(50 * 1.0 / cfg.sound);
+}
+
+extern "C" int fsg_version(void) { return FSG_VERSION; }
+
+extern "C" int fsg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int fsg_config_default(fsg_config *cfg, int model)
+{
+    if (!cfg) return FSG_E_INVALID;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->model = model;
+    cfg->origin = -1.0f;
+    cfg->h = 0.06;
+    cfg->gravity = -9.8;
+    cfg->sound = 1450.0;
+    cfg->world = 1;
+    if (model == FSG_MODEL_BASE) {            // FluidGPU.cuh:1-31, solver.cu:17-19,187
+        cfg->grid = 40;
+        cfg->cellsize = 0.05;
+        cfg->dt = 0.0005;
+        cfg->alpha_fluid = -0.01e2;
+        cfg->alpha_boundary = 2000e-1;
+        cfg->neighbour_cap = 64;
+        cfg->bin_cap = 64;
+        cfg->capacity = 8000;
+    } else if (model == FSG_MODEL_UNIDYN) {   // FluidGPU-unidyn.cuh:1-36, solver-unidyn.cu:21-23,363
+        cfg->grid = 17;
+        cfg->cellsize = 0.12;
+        cfg->dt = 0.0018;
+        cfg->alpha_fluid = -0.0155e1;
+        cfg->alpha_boundary = 80e0;
+        cfg->neighbour_cap = 1024;
+        cfg->bin_cap = 1024;
+        cfg->capacity = 14040;
+    } else
+        return FSG_E_INVALID;
+    return FSG_OK;
+}
+
+static void free_state(FsgState &s)
+{
+    cudaFree(s.posd); cudaFree(s.velp); cudaFree(s.accf); cudaFree(s.dpi);
+    s.posd = s.velp = s.accf = s.dpi = nullptr;
+}
+
+extern "C" int fsg_destroy(fsg_ctx *c)
+{
+    if (!c) return FSG_E_INVALID;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_state(c->A);
+    free_state(c->B);
+    cudaFree(c->carryA); cudaFree(c->carryB);
+    cudaFree(c->keysA); cudaFree(c->keysB); cudaFree(c->perm); cudaFree(c->iota);
+    cudaFree(c->start); cudaFree(c->end);
+    cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
+    cudaFree(c->counters); cudaFree(c->dstats); cudaFree(c->sort_tmp);
+    cudaFree(c->stage);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return FSG_OK;
+}
+
+static int alloc_state(fsg_ctx *c, FsgState &s, int64_t cap)
+{
+    CU(c, cudaMalloc(&s.posd, sizeof(float4) * cap));
+    CU(c, cudaMalloc(&s.velp, sizeof(float4) * cap));
+    CU(c, cudaMalloc(&s.accf, sizeof(float4) * cap));
+    CU(c, cudaMalloc(&s.dpi, sizeof(float4) * cap));
+    return FSG_OK;
+}
+
+static int create_impl(fsg_ctx *c)
+{
+    const fsg_config &cfg = c->cfg;
+    CU(c, cudaSetDevice(cfg.device));
+    cudaDeviceProp prop;
+    CU(c, cudaGetDeviceProperties(&prop, cfg.device));
+    c->sm_count = prop.multiProcessorCount;
+    CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    const int64_t cap = cfg.capacity > 0 ? cfg.capacity : 1;
+    c->cap = cap;
+    int rc;
+    if ((rc = alloc_state(c, c->A, cap)) != FSG_OK) return rc;
+    if ((rc = alloc_state(c, c->B, cap)) != FSG_OK) return rc;
+    CU(c, cudaMalloc(&c->carryA, sizeof(float4) * cap));
+    CU(c, cudaMalloc(&c->carryB, sizeof(float4) * cap));
+    CU(c, cudaMalloc(&c->keysA, sizeof(int) * cap));
+    CU(c, cudaMalloc(&c->keysB, sizeof(int) * cap));
+    CU(c, cudaMalloc(&c->perm, sizeof(int) * cap));
+    CU(c, cudaMalloc(&c->iota, sizeof(int) * cap));
+    const int64_t nc = c->dev.numcells;
+    CU(c, cudaMalloc(&c->start, sizeof(int) * nc));
+    CU(c, cudaMalloc(&c->end, sizeof(int) * nc));
+    const int64_t nb = cap < nc ? cap : nc;
+    CU(c, cudaMalloc(&c->binlist[0], sizeof(int) * (nb > 0 ? nb : 1)));
+    CU(c, cudaMalloc(&c->binlist[1], sizeof(int) * (nb > 0 ? nb : 1)));
+    CU(c, cudaMalloc(&c->counters, sizeof(int) * 8));
+    CU(c, cudaMalloc(&c->dstats, sizeof(unsigned long long) * 4));
+    CU(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * 8, c->stream));
+    CU(c, cudaMemsetAsync(c->dstats, 0, sizeof(unsigned long long) * 4, c->stream));
+    CU(c, fsg_launch_iota(c->iota, cap, c->stream));
+    CU(c, fsg_launch_fill(c->start, -1, nc, c->stream));    // solver.cu:163-169
+    CU(c, fsg_launch_fill(c->end, -1, nc, c->stream));
+    c->launches += 3;
+    c->sort_bits = 1;
+    while ((1ll << c->sort_bits) <= nc) c->sort_bits++;      // keys are in [0, numcells]
+    c->sort_tmp_bytes = fsg_sort_temp_bytes(cap, c->sort_bits);
+    CU(c, cudaMalloc(&c->sort_tmp, c->sort_tmp_bytes ? c->sort_tmp_bytes : 16));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return FSG_OK;
+}
+
+extern "C" int fsg_create(const fsg_config *cfg, fsg_ctx **out)
+{
+    if (!cfg || !out) return FSG_E_INVALID;
+    *out = nullptr;
+    if (cfg->grid < 1 || cfg->grid > 1290 || cfg->cellsize <= 0 || cfg->h <= 0 || cfg->capacity < 0 ||
+        cfg->capacity > 2000000000ll || (cfg->model != FSG_MODEL_BASE && cfg->model != FSG_MODEL_UNIDYN)) {
+        g_create_err = "fsg_create: invalid configuration";
+        return FSG_E_INVALID;
+    }
+    if (cfg->model == FSG_MODEL_UNIDYN) {
+        g_create_err = "fsg_create: the unidyn model is not available through the context API yet";
+        return FSG_E_UNSUPPORTED;
+    }
+    int ndev = fsg_device_count();
+    if (ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+        g_create_err = "fsg_create: no usable CUDA device (libfsg has no CPU path)";
+        return FSG_E_NO_DEVICE;
+    }
+    fsg_ctx *c = new (std::nothrow) fsg_ctx();
+    if (!c) return FSG_E_NOMEM;
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    fsg_derive_constants(*cfg, c->dev);
+    int rc = create_impl(c);
+    if (rc != FSG_OK) {
+        g_create_err = c->err;
+        fsg_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return FSG_OK;
+}
+
+extern "C" const char *fsg_last_error(const fsg_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int fsg_set_stream(fsg_ctx *c, void *s)
+{
+    if (!c) return FSG_E_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+    return FSG_OK;
+}
+extern "C" void *fsg_get_stream(fsg_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" int fsg_sync(fsg_ctx *c)
+{
+    if (!c) return FSG_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return FSG_OK;
+}
+
+// after new particles have been written to B / carryB
+static int after_upload(fsg_ctx *c, int64_t n)
+{
+    // the bin tables may hold the entries of a previous run
+    if (c->tables_dirty) {
+        CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, c->n, c->stream));
+        c->launches++;
+        c->tables_dirty = false;
+    }
+    c->n = n;
+    CU(c, fsg_launch_keys(c->dev, c->B.posd, c->keysB, n, c->stream));   // solver.cu:119
+    c->launches++;
+    c->carry_live = true;
+    c->steps = 0;
+    return FSG_OK;
+}
+
+static int ensure_stage(fsg_ctx *c, size_t bytes)
+{
+    if (c->stage_bytes >= bytes) return FSG_OK;
+    if (c->stage) { CU(c, cudaStreamSynchronize(c->stream)); cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
+    CU(c, cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return FSG_OK;
+}
+
+extern "C" int fsg_upload_aos(fsg_ctx *c, const void *particles, int64_t n)
+{
+    if (!c || (!particles && n > 0) || n < 0) return FSG_E_INVALID;
+    if (n > c->cap) { c->err = "fsg_upload_aos: n exceeds the context capacity"; return FSG_E_INVALID; }
+    CU(c, cudaSetDevice(c->device));
+    const int64_t chunk = 1 << 20;
+    int rc = ensure_stage(c, (size_t)(n < chunk ? n : chunk) * FSG_AOS_STRIDE + 16);
+    if (rc != FSG_OK) return rc;
+    for (int64_t o = 0; o < n; o += chunk) {
+        int64_t m = n - o < chunk ? n - o : chunk;
+        CU(c, cudaMemcpyAsync(c->stage, (const unsigned char *)particles + o * FSG_AOS_STRIDE, (size_t)m * FSG_AOS_STRIDE,
+                              cudaMemcpyHostToDevice, c->stream));
+        FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o};
+        CU(c, fsg_launch_unpack_aos(c->cfg.model, (const unsigned char *)c->stage, m, st, c->carryB + o, c->stream));
+        c->launches++;
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return after_upload(c, n);
+}
+
+extern "C" int fsg_download_aos(fsg_ctx *c, void *particles, int64_t n)
+{
+    if (!c || (!particles && n > 0) || n < 0 || n > c->n) return FSG_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    const int64_t chunk = 1 << 20;
+    int rc = ensure_stage(c, (size_t)(n < chunk ? n : chunk) * FSG_AOS_STRIDE + 16);
+    if (rc != FSG_OK) return rc;
+    for (int64_t o = 0; o < n; o += chunk) {
+        int64_t m = n - o < chunk ? n - o : chunk;
+        FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o};
+        CU(c, fsg_launch_pack_aos(c->cfg.model, (unsigned char *)c->stage, m, st, c->carry_live ? c->carryB + o : nullptr,
+                                  c->keysB + o, 101325.f, c->stream));
+        c->launches++;
+        CU(c, cudaMemcpyAsync((unsigned char *)particles + o * FSG_AOS_STRIDE, c->stage, (size_t)m * FSG_AOS_STRIDE,
+                              cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return FSG_OK;
+}
+
+// ---- SoA host interface: raw arrays are copied into a staging area and (un)packed on the device ----
+__global__ void k_pack_soa(int64_t n, const float *pos, const float *vel, const float *acc, const float *dens,
+                           const float *press, const float *delp, const float *nd, const float *ndp, const int *index,
+                           const unsigned char *bnd, float gravity, FsgState st, float4 *carry)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool b = bnd ? bnd[i] != 0 : false;
+    float de = dens ? dens[i] : 9550.f;
+    st.posd[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], b ? -de : de);
+    st.velp[i] = make_float4(vel ? vel[3 * i] : 0.f, vel ? vel[3 * i + 1] : 0.f, vel ? vel[3 * i + 2] : 0.f, press ? press[i] : 0.f);
+    st.accf[i] = make_float4(acc ? acc[3 * i] : 0.f, acc ? acc[3 * i + 1] : 0.f, acc ? acc[3 * i + 2] : (b ? 0.f : gravity),
+                             __int_as_float(b ? 1 : 0));
+    st.dpi[i] = make_float4(delp ? delp[3 * i] : 0.f, delp ? delp[3 * i + 1] : 0.f, delp ? delp[3 * i + 2] : 0.f,
+                            __int_as_float(index ? index[i] : (int)i));
+    carry[i] = make_float4(nd ? nd[i] : 9550.f, ndp ? ndp[3 * i] : 0.f, ndp ? ndp[3 * i + 1] : 0.f, ndp ? ndp[3 * i + 2] : 0.f);
+}
+
+__global__ void k_unpack_soa(int64_t n, FsgState st, const float4 *carry, const int *keys, float *pos, float *vel, float *acc,
+                             float *dens, float *press, float *delp, float *nd, float *ndp, int *index, int *cell,
+                             unsigned char *bnd)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 pd = st.posd[i], vp = st.velp[i], af = st.accf[i], dp = st.dpi[i];
+    float4 cy = carry ? carry[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos) { pos[3 * i] = pd.x; pos[3 * i + 1] = pd.y; pos[3 * i + 2] = pd.z; }
+    if (vel) { vel[3 * i] = vp.x; vel[3 * i + 1] = vp.y; vel[3 * i + 2] = vp.z; }
+    if (acc) { acc[3 * i] = af.x; acc[3 * i + 1] = af.y; acc[3 * i + 2] = af.z; }
+    if (dens) dens[i] = fabsf(pd.w);
+    if (press) press[i] = vp.w;
+    if (delp) { delp[3 * i] = dp.x; delp[3 * i + 1] = dp.y; delp[3 * i + 2] = dp.z; }
+    if (nd) nd[i] = cy.x;
+    if (ndp) { ndp[3 * i] = cy.y; ndp[3 * i + 1] = cy.z; ndp[3 * i + 2] = cy.w; }
+    if (index) index[i] = __float_as_int(dp.w);
+    if (cell) cell[i] = keys[i];
+    if (bnd) bnd[i] = pd.w < 0.f ? 1 : 0;
+}
+
+struct SoaStage {
+    float *pos, *vel, *acc, *dens, *press, *delp, *nd, *ndp;
+    int *index, *cell;
+    unsigned char *bnd;
+};
+static size_t soa_stage_layout(char *base, int64_t n, const fsg_soa *h, SoaStage &s)
+{
+    size_t o = 0;
+    auto take = [&](const void *hp, size_t bytes) -> char * {
+        if (!hp) return nullptr;
+        char *p = base ? base + o : (char *)1;
+        o += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    s.pos = (float *)take(h->pos, 12 * n);
+    s.vel = (float *)take(h->vel, 12 * n);
+    s.acc = (float *)take(h->acc, 12 * n);
+    s.dens = (float *)take(h->dens, 4 * n);
+    s.press = (float *)take(h->press, 4 * n);
+    s.delp = (float *)take(h->delpress, 12 * n);
+    s.nd = (float *)take(h->newdens, 4 * n);
+    s.ndp = (float *)take(h->newdelpress, 12 * n);
+    s.index = (int *)take(h->index, 4 * n);
+    s.cell = (int *)take(h->cell, 4 * n);
+    s.bnd = (unsigned char *)take(h->boundary, n);
+    return o + 256;
+}
+
+extern "C" int fsg_upload_soa(fsg_ctx *c, const fsg_soa *h)
+{
+    if (!c || !h || h->n < 0 || (h->n > 0 && !h->pos)) return FSG_E_INVALID;
+    const int64_t n = h->n;
+    if (n > c->cap) { c->err = "fsg_upload_soa: n exceeds the context capacity"; return FSG_E_INVALID; }
+    CU(c, cudaSetDevice(c->device));
+    SoaStage s;
+    fsg_soa hh = *h;
+    hh.cell = nullptr;   // recomputed, solver.cu:119
+    size_t bytes = soa_stage_layout(nullptr, n, &hh, s);
+    int rc = ensure_stage(c, bytes);
+    if (rc != FSG_OK) return rc;
+    soa_stage_layout((char *)c->stage, n, &hh, s);
+#define H2D(dst, src, bytes) if (src) CU(c, cudaMemcpyAsync(dst, src, (size_t)(bytes), cudaMemcpyHostToDevice, c->stream))
+    H2D(s.pos, h->pos, 12 * n); H2D(s.vel, h->vel, 12 * n); H2D(s.acc, h->acc, 12 * n); H2D(s.dens, h->dens, 4 * n);
+    H2D(s.press, h->press, 4 * n); H2D(s.delp, h->delpress, 12 * n); H2D(s.nd, h->newdens, 4 * n);
+    H2D(s.ndp, h->newdelpress, 12 * n); H2D(s.index, h->index, 4 * n); H2D(s.bnd, h->boundary, n);
+#undef H2D
+    if (n > 0) {
+        k_pack_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, s.pos, s.vel, s.acc, s.dens, s.press, s.delp, s.nd,
+                                                                       s.ndp, s.index, s.bnd, (float)c->cfg.gravity, c->B,
+                                                                       c->carryB);
+        CU(c, cudaGetLastError());
+        c->launches++;
+    }
+    return after_upload(c, n);
+}
+
+extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
+{
+    if (!c || !h) return FSG_E_INVALID;
+    const int64_t n = c->n;
+    h->n = n;
+    CU(c, cudaSetDevice(c->device));
+    SoaStage s;
+    size_t bytes = soa_stage_layout(nullptr, n, h, s);
+    int rc = ensure_stage(c, bytes);
+    if (rc != FSG_OK) return rc;
+    soa_stage_layout((char *)c->stage, n, h, s);
+    if (n > 0) {
+        k_unpack_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->B, c->carry_live ? c->carryB : nullptr, c->keysB,
+                                                                         s.pos, s.vel, s.acc, s.dens, s.press, s.delp, s.nd,
+                                                                         s.ndp, s.index, s.cell, s.bnd);
+        CU(c, cudaGetLastError());
+        c->launches++;
+    }
+#define D2H(dst, src, bytes) if (dst) CU(c, cudaMemcpyAsync(dst, src, (size_t)(bytes), cudaMemcpyDeviceToHost, c->stream))
+    D2H(h->pos, s.pos, 12 * n); D2H(h->vel, s.vel, 12 * n); D2H(h->acc, s.acc, 12 * n); D2H(h->dens, s.dens, 4 * n);
+    D2H(h->press, s.press, 4 * n); D2H(h->delpress, s.delp, 12 * n); D2H(h->newdens, s.nd, 4 * n);
+    D2H(h->newdelpress, s.ndp, 12 * n); D2H(h->index, s.index, 4 * n); D2H(h->cell, s.cell, 4 * n); D2H(h->boundary, s.bnd, n);
+#undef D2H
+    CU(c, cudaStreamSynchronize(c->stream));
+    return FSG_OK;
+}
+
+// ---- the step: solver.cu:181-198 ----
+extern "C" int fsg_step(fsg_ctx *c, int nsteps)
+{
+    if (!c || nsteps < 0) return FSG_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    const int64_t n = c->n;
+    if (n <= 0) { c->steps += nsteps; return FSG_OK; }
+    for (int t = 0; t < nsteps; t++) {
+        if (c->tables_dirty) {
+            CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, n, c->stream));
+            c->launches++;
+        }
+        const int nxt = c->cur ^ 1;
+        CU(c, cudaMemsetAsync(c->counters + nxt, 0, sizeof(int), c->stream));
+        CU(c, cudaMemsetAsync(c->counters + 2, 0, 2 * sizeof(int), c->stream));
+        if (c->cfg.collect_stats) CU(c, cudaMemsetAsync(c->dstats, 0, 4 * sizeof(unsigned long long), c->stream));
+        // thrust::sort_by_key, key half (solver.cu:181)
+        CU(c, fsg_sort_pairs(c->sort_tmp, c->sort_tmp_bytes, c->keysB, c->keysA, c->iota, c->perm, n, c->sort_bits, c->stream));
+        // value half + findneighbours (solver.cu:181-182)
+        CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA,
+                                 c->start, c->end, c->binlist[nxt], c->counters + nxt, c->counters + 3, c->stream));
+        c->launches++;
+        // mykernel + mykernel2 (solver.cu:187,198)
+        int l = 0;
+        CU(c, fsg_launch_pair_update(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2,
+                                     c->carry_live ? c->carryA : nullptr, &l, c->stream));
+        c->launches += l;
+        c->carry_live = false;
+        c->cur = nxt;
+        c->tables_dirty = true;
+        c->steps++;
+    }
+    return FSG_OK;
+}
+
+extern "C" int fsg_export_viz(fsg_ctx *c, float *spts, float *a3, float *b3)
+{
+    if (!c) return FSG_E_INVALID;
+    if (c->steps < 1) { c->err = "fsg_export_viz: no step taken since upload"; return FSG_E_STATE; }
+    CU(c, cudaSetDevice(c->device));
+    const int64_t n = c->n;
+    int rc = ensure_stage(c, (size_t)n * 20 + 1024);
+    if (rc != FSG_OK) return rc;
+    float *ds = (float *)c->stage, *da = ds + 3 * n, *db = da + n;
+    CU(c, fsg_launch_export_viz(n, c->A.posd, c->keysA, ds, da, db, c->stream));
+    c->launches++;
+    if (spts) CU(c, cudaMemcpyAsync(spts, ds, 12 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (a3) CU(c, cudaMemcpyAsync(a3, da, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (b3) CU(c, cudaMemcpyAsync(b3, db, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return FSG_OK;
+}
+
+extern "C" int fsg_get_tables(fsg_ctx *c, int32_t *cells, int32_t *start, int32_t *end)
+{
+    if (!c) return FSG_E_INVALID;
+    if (c->steps < 1) { c->err = "fsg_get_tables: no step taken since upload"; return FSG_E_STATE; }
+    CU(c, cudaSetDevice(c->device));
+    if (cells) CU(c, cudaMemcpyAsync(cells, c->keysA, sizeof(int) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    if (start) CU(c, cudaMemcpyAsync(start, c->start, sizeof(int) * (size_t)c->dev.numcells, cudaMemcpyDeviceToHost, c->stream));
+    if (end) CU(c, cudaMemcpyAsync(end, c->end, sizeof(int) * (size_t)c->dev.numcells, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return FSG_OK;
+}
+
+extern "C" int fsg_get_stats(fsg_ctx *c, fsg_stats *out)
+{
+    if (!c || !out) return FSG_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int cnt[4] = {0, 0, 0, 0};
+    unsigned long long ds[4] = {0, 0, 0, 0};
+    CU(c, cudaMemcpyAsync(cnt, c->counters, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(ds, c->dstats, sizeof ds, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof *out);
+    out->n = c->n;
+    out->n_live = c->steps > 0 ? cnt[3] : c->n;
+    out->occupied_bins = c->steps > 0 ? cnt[c->cur] : 0;
+    out->pairs_tested = (int64_t)ds[0];
+    out->pairs_in_range = (int64_t)ds[1];
+    out->dropped = (int64_t)ds[2];
+    out->steps = c->steps;
+    out->kernel_launches = c->launches;
+    return FSG_OK;
+}
+
+extern "C" int fsg_scene_plume(fsg_ctx *c, double spacing, double jitter, uint64_t seed, int64_t *n_out)
+{
+    if (!c || !n_out || spacing <= 0) return FSG_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int64_t n = 0;
+    int rc = fsg_scene_plume_device(c, spacing, jitter, seed, &n);
+    *n_out = n;
+    if (rc != FSG_OK) { c->err = rc == FSG_E_NOMEM ? "fsg_scene_plume: scene exceeds the context capacity" : "fsg_scene_plume: launch failed"; return rc; }
+    return after_upload(c, n);
+}
+
+extern "C" int fsg_device_ptr(fsg_ctx *c, int which, void **ptr)
+{
+    if (!c || !ptr) return FSG_E_INVALID;
+    switch (which) {
+    case 0: *ptr = c->B.posd; break;
+    case 1: *ptr = c->B.velp; break;
+    case 2: *ptr = c->B.accf; break;
+    case 3: *ptr = c->B.dpi; break;
+    case 4: *ptr = c->keysB; break;
+    default: return FSG_E_INVALID;
+    }
+    return FSG_OK;
+}
+
+// ---- stage API (implemented in fsg_stage.cu) ----

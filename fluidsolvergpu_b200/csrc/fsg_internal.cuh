@@ -1,0 +1,101 @@
+// fsg_internal.cuh — shared declarations of libfsg's translation units (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/fsg.h"
+
+// ---------------------------------------------------------------------------------------------
+// Device-side constants of one context.  The double members are the reference's macros
+// (FluidGPU.cuh:1-31); the float members are the thresholds / coefficients the fp32 pair path
+// uses, derived on the host so that every comparison decides exactly like the reference's
+// double comparison of a float operand.
+// ---------------------------------------------------------------------------------------------
+struct FsgDev {
+    int G, G2, numcells;
+    int cap, bin_cap;
+    float origin;
+    double cellsize, h, dt, gravity, sound, alpha_fluid, alpha_boundary;
+    // fp32 pair constants
+    float d2_max;    // largest d2 with sqrtf(d2) <= 2h (as the double compare FluidGPU.cu:236 decides)
+    float h_le;      // largest float r with (double)r <= h        FluidGPU.cu:12
+    float h_lt;      // largest float r with (double)r <  h        FluidGPU.cu:36
+    float twoh_lt;   // largest float r with (double)r <  2h       FluidGPU.cu:15
+    float hf;        // (float)h
+    float inv_h;     // 1/h
+    float w_c;       // 1/3.14159/powf(h,3)                        FluidGPU.cu:13
+    float dw_c;      // -45/3.14159/powf(h,6)                      FluidGPU.cu:37
+    float w0;        // kernel(0)                                  FluidGPU.cuh:166
+    float eps;       // 0.01*powf(h,2)                             FluidGPU.cu:255
+    float visc_c;    // ALPHA_FLUID*SOUND
+    float visc_q;    // 50*1.0/SOUND
+};
+
+// SoA particle state: four float4 streams = 64 B per particle (DESIGN.md "Data layout").
+//   posd = (x, y, z, dens)   — sign bit of dens carries Particle::boundary
+//   velp = (vx, vy, vz, press)
+//   accf = (ax, ay, az, flags bits: bit0 boundary, bit1 solid)
+//   dpi  = (delpressx, delpressy, delpressz, index bits)
+struct FsgState {
+    float4 *posd, *velp, *accf, *dpi;
+};
+
+struct fsg_ctx {
+    fsg_config cfg;
+    FsgDev dev;
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    std::string err;
+
+    int64_t cap;        // particle capacity
+    int64_t n;          // particles held
+    FsgState A, B;      // A: sorted pre-update state of the last step; B: post-update state
+    float4 *carryB, *carryA;   // accumulators carried into the first step after upload (newdens, newdelpress xyz)
+    bool carry_live;
+    int *keysB;         // bin ids belonging to B (order of B)
+    int *keysA;         // sorted bin ids (order of A)
+    int *perm, *iota;
+    int *start, *end;   // dense bin tables, -1 = empty  (FluidGPU.cu:106-117)
+    int *binlist[2];    // first sorted slot of every occupied bin (unordered), ping-pong
+    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live
+    unsigned long long *dstats;   // [0] tested, [1] in range, [2] dropped
+    void *sort_tmp;
+    void *stage;        // device staging area for host<->device conversion
+    size_t stage_bytes;
+    size_t sort_tmp_bytes;
+    int sort_bits;
+    int cur;            // which binlist/nocc slot the last step used
+    bool tables_dirty;  // start/end hold the last step's entries
+    int64_t steps;
+    int64_t launches;
+    int sm_count;
+};
+
+// fsg_sort.cu — stable radix sort of (bin id, slot) pairs; the reference's thrust::sort_by_key (solver.cu:181)
+size_t fsg_sort_temp_bytes(int64_t n, int bits);
+cudaError_t fsg_sort_pairs(void *tmp, size_t tmp_bytes, const int *keys_in, int *keys_out, const int *vals_in,
+                           int *vals_out, int64_t n, int bits, cudaStream_t s);
+
+// fsg_base_kernels.cu
+cudaError_t fsg_launch_iota(int *p, int64_t n, cudaStream_t s);
+cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s);
+cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, cudaStream_t s);
+cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const int *keysA, int *start, int *end,
+                                    int64_t n, cudaStream_t s);
+cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
+                               FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
+                               int *binlist, int *nocc, int *nlive, cudaStream_t s);
+cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work,
+                                   const float4 *carry, int *launches, cudaStream_t s);
+cudaError_t fsg_launch_unpack_aos(int model, const unsigned char *aos, int64_t n, FsgState st, float4 *carry,
+                                  cudaStream_t s);
+cudaError_t fsg_launch_pack_aos(int model, unsigned char *aos, int64_t n, FsgState st, const float4 *carry,
+                                const int *keys, float p0, cudaStream_t s);
+cudaError_t fsg_launch_export_viz(int64_t n, const float4 *posd, const int *keys, float *spts, float *a3, float *b3,
+                                  cudaStream_t s);
+cudaError_t fsg_launch_plume(const FsgDev &d, double spacing, double jitter, uint64_t seed, double gravity,
+                             FsgState st, float4 *carry, int64_t capacity, unsigned long long *count, cudaStream_t s);
+
+void fsg_derive_constants(const fsg_config &cfg, FsgDev &d);

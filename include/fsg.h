@@ -1,0 +1,177 @@
+/*
+ * fsg.h — C ABI of libfsg, the B200-native (sm_100a) implementation of FluidSolverGPU's
+ * per-timestep particle update.
+ *
+ * What it replaces (paths relative to the reference repository root):
+ *   the body of the time loops solver.cu:171-216 and solver-unidyn.cu:313-573, i.e. the launches of
+ *   thrust::sort_by_key (solver.cu:181), findneighbours (FluidGPU.cuh:417 / FluidGPU.cu:106),
+ *   mykernel (FluidGPU.cuh:418 / FluidGPU.cu:119), mykernel2 (FluidGPU.cuh:419 / FluidGPU.cu:404)
+ *   and the unidyn counterparts (FluidGPU-unidyn.cuh:537-544).
+ *
+ * Two faces:
+ *   (1) context API  — fsg_create / fsg_upload_* / fsg_step / fsg_download_* : the library owns SoA
+ *       device state and runs the whole step; this is what drivers, benchmarks and multi-GPU use.
+ *   (2) stage API    — fsg_stage_* : one call per reference kernel, on caller-owned DEVICE buffers
+ *       laid out exactly as the reference's (340-byte `Particle` AoS, int key/start/end arrays), so
+ *       the reference drivers can swap each `<<<>>>` launch for one call.
+ *
+ * Conventions: every function returns FSG_OK (0) or a negative FSG_E_* code and never exits or
+ * throws; fsg_last_error() gives a message.  Plain pointers and sizes only.  One host thread per
+ * context (the reference drives everything from one thread, solver.cu:171).  There is NO CPU
+ * fallback: without a CUDA device every compute entry point returns FSG_E_NO_DEVICE.
+ */
+#ifndef FSG_H
+#define FSG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSG_VERSION 100
+
+#if defined(__GNUC__)
+#define FSG_API __attribute__((visibility("default")))
+#else
+#define FSG_API
+#endif
+
+enum {
+    FSG_OK = 0,
+    FSG_E_INVALID = -1,    /* bad argument */
+    FSG_E_NO_DEVICE = -2,  /* no usable CUDA device (there is no CPU path) */
+    FSG_E_CUDA = -3,       /* a CUDA call failed; see fsg_last_error */
+    FSG_E_NOMEM = -4,
+    FSG_E_STATE = -5,      /* call order (e.g. step before upload) */
+    FSG_E_UNSUPPORTED = -6
+};
+
+enum { FSG_MODEL_BASE = 0 /* FluidGPU.cu */, FSG_MODEL_UNIDYN = 1 /* FluidGPU-unidyn.cu */ };
+
+/* sizeof(Particle) in both reference headers (FluidGPU.cuh:59-305, FluidGPU-unidyn.cuh:68-424). */
+#define FSG_AOS_STRIDE 340
+
+/* Run-time form of the reference's compile-time constants (FluidGPU.cuh:1-31,
+ * FluidGPU-unidyn.cuh:1-36).  fsg_config_default() fills in the reference's values. */
+typedef struct fsg_config {
+    int32_t model;          /* FSG_MODEL_*                                                   */
+    int32_t grid;           /* GRIDSIZE: bins per axis                        FluidGPU.cuh:8  */
+    float   origin;         /* XMIN = YMIN = ZMIN                             FluidGPU.cuh:1  */
+    double  cellsize;       /* CELLSIZE                                       FluidGPU.cuh:7  */
+    double  h;              /* cutoff (smoothing length)                      FluidGPU.cuh:30 */
+    double  dt;             /* DT                                             FluidGPU.cuh:31 */
+    double  gravity;        /* GRAVITY                                        FluidGPU.cuh:10 */
+    double  sound;          /* SOUND                                          FluidGPU.cuh:11 */
+    double  alpha_fluid;    /* ALPHA_FLUID                                    FluidGPU.cuh:16 */
+    double  alpha_boundary; /* ALPHA_BOUNDARY                                 FluidGPU.cuh:17 */
+    int32_t neighbour_cap;  /* threads per bin block in the reference launch = max neighbour
+                               particles visited per bin (64: solver.cu:187; 1024: solver-unidyn.cu:363);
+                               0 = visit every particle of the 27 bins                        */
+    int32_t bin_cap;        /* bins with >= this many particles are left out of the thread
+                               count (64: FluidGPU.cu:174); 0 = off                           */
+    int64_t capacity;       /* particles this context can hold                                */
+    int32_t device;         /* CUDA device ordinal                                            */
+    int32_t pair_fp64;      /* 1: evaluate the pair sub-expressions the reference evaluates in
+                               double in double (Appendix A); 0: fp32 (default)               */
+    int32_t collect_stats;  /* 1: count candidate / in-range pairs each step                   */
+    /* slab decomposition along x, the slowest bin axis (solver-unidyn.cu:187-193) */
+    int32_t rank, world;    /* this context's slab and the number of slabs (1 = no decomposition) */
+    int32_t reserved[5];
+} fsg_config;
+
+/* Host-side structure-of-arrays view used by fsg_upload_soa / fsg_download_soa: the live fields
+ * of `class Particle`.  Any pointer may be NULL on upload (class defaults are used: dens = RHO_0,
+ * press = 0, acc = (0,0,GRAVITY), newdens = RHO_0, FluidGPU.cuh:64-71,132-148) or on download. */
+typedef struct fsg_soa {
+    int64_t n;
+    float  *pos;         /* [n][3] xcoord,ycoord,zcoord   */
+    float  *vel;         /* [n][3]                         */
+    float  *acc;         /* [n][3]                         */
+    float  *dens;        /* [n]                            */
+    float  *press;       /* [n]                            */
+    float  *delpress;    /* [n][3] x,y,z                   */
+    float  *newdens;     /* [n] accumulator carried into the next step */
+    float  *newdelpress; /* [n][3] x,y,z                   */
+    int32_t *index;      /* [n] Particle::index (NULL on upload: 0..n-1) */
+    int32_t *cell;       /* [n] Particle::cellnumber (download only; recomputed on upload, solver.cu:119) */
+    uint8_t *boundary;   /* [n]                            */
+} fsg_soa;
+
+typedef struct fsg_ctx fsg_ctx;
+
+typedef struct fsg_stats {
+    int64_t n;               /* particles held                                   */
+    int64_t n_live;          /* particles inside the bin grid                    */
+    int64_t occupied_bins;   /* bins with at least one particle, last step       */
+    int64_t pairs_tested;    /* candidate pairs distance-tested, last step (collect_stats) */
+    int64_t pairs_in_range;  /* pairs with 0 < ds <= 2h, last step (collect_stats)         */
+    int64_t dropped;         /* neighbour particles left unvisited by neighbour_cap, last step (collect_stats) */
+    int64_t steps;           /* steps taken since upload                         */
+    int64_t kernel_launches; /* launches of libfsg's own kernels since create    */
+} fsg_stats;
+
+/* ---- (1) context API ---- */
+FSG_API int  fsg_version(void);
+FSG_API int  fsg_device_count(void);                       /* 0 when there is no usable device */
+FSG_API int  fsg_config_default(fsg_config *cfg, int model);
+FSG_API int  fsg_create(const fsg_config *cfg, fsg_ctx **out);
+FSG_API int  fsg_destroy(fsg_ctx *ctx);
+FSG_API const char *fsg_last_error(const fsg_ctx *ctx);    /* ctx may be NULL: last create error */
+FSG_API int  fsg_set_stream(fsg_ctx *ctx, void *cuda_stream);   /* cudaStream_t; default: a stream the ctx owns */
+FSG_API void *fsg_get_stream(fsg_ctx *ctx);
+
+/* Host -> device.  `particles` is an array of n reference `Particle` records (FSG_AOS_STRIDE bytes
+ * each), as solver.cu:131 copies to the device.  Bin ids are recomputed from the positions with the
+ * expression of solver.cu:119. */
+FSG_API int  fsg_upload_aos(fsg_ctx *ctx, const void *particles, int64_t n);
+FSG_API int  fsg_upload_soa(fsg_ctx *ctx, const fsg_soa *host);
+/* Device -> host, in the device's current (bin-sorted) order, like copying d_SPptr back
+ * (solver-unidyn.cu:475).  Fields the path never touches get the class defaults. */
+FSG_API int  fsg_download_aos(fsg_ctx *ctx, void *particles, int64_t n);
+FSG_API int  fsg_download_soa(fsg_ctx *ctx, fsg_soa *host);
+
+/* nsteps passes of the loop body solver.cu:181-198: sort by bin -> bin ranges -> pair sums ->
+ * EOS / integrate / re-bin.  Asynchronous on the context's stream; fsg_sync waits. */
+FSG_API int  fsg_step(fsg_ctx *ctx, int nsteps);
+FSG_API int  fsg_sync(fsg_ctx *ctx);
+
+/* mykernel2's visualisation export of the LAST step (FluidGPU.cu:410-414): positions, dens and
+ * float(cellnumber) before update(), in that step's sorted order.  Host pointers, any may be NULL. */
+FSG_API int  fsg_export_viz(fsg_ctx *ctx, float *spts, float *a3, float *b3);
+/* The integer tables of the LAST step as the pair kernel saw them (host pointers, may be NULL):
+ * cells[n] sorted keys, start/end[numcells] (FluidGPU.cu:106-117; -1 = empty bin). */
+FSG_API int  fsg_get_tables(fsg_ctx *ctx, int32_t *cells, int32_t *start, int32_t *end);
+FSG_API int  fsg_get_stats(fsg_ctx *ctx, fsg_stats *out);
+
+/* Device-side scene generation for the throughput configs: a column of fluid
+ * particles about the z axis of a grid^3 bin domain, lattice spacing `spacing`, jitter from
+ * splitmix64(seed + lattice id).  Returns the particle count through *n_out. */
+FSG_API int  fsg_scene_plume(fsg_ctx *ctx, double spacing, double jitter, uint64_t seed, int64_t *n_out);
+/* Same generator on the host into caller arrays (for the end-to-end path and the tests);
+ * pass pos == NULL to get the count only.  Pure host code, no device needed. */
+FSG_API int  fsg_scene_plume_host(const fsg_config *cfg, double spacing, double jitter, uint64_t seed,
+                          float *pos, float *vel, int64_t capacity, int64_t *n_out);
+
+/* Device pointers to the SoA state (float4 arrays, see DESIGN.md "Data layout"), for zero-copy
+ * consumers on the same device (bench, halo exchange).  which: 0 = posd, 1 = velp, 2 = accf, 3 = dpi,
+ * 4 = keys (int32).  Valid until the next fsg_* call that changes state. */
+FSG_API int  fsg_device_ptr(fsg_ctx *ctx, int which, void **ptr);
+
+/* ---- (2) stage API: caller-owned DEVICE buffers in the reference's own layout ---- */
+/* replaces thrust::sort_by_key(t_v, t_v + n, t_a)            solver.cu:181 */
+FSG_API int  fsg_stage_sort(fsg_ctx *ctx, int32_t *d_cells, void *d_particles, int64_t n);
+/* replaces findneighbours<<<NUMCELLS,1024>>>(v_d, d_start, d_end, n)   solver.cu:182 */
+FSG_API int  fsg_stage_findneighbours(fsg_ctx *ctx, const int32_t *d_cells, int32_t *d_start, int32_t *d_end, int64_t n);
+/* replaces mykernel<<<NUMCELLS,64>>>(d_SPptr, v_d, d_start, d_end, n)  solver.cu:187 */
+FSG_API int  fsg_stage_mykernel(fsg_ctx *ctx, void *d_particles, const int32_t *d_cells, const int32_t *d_start,
+                        const int32_t *d_end, int64_t n);
+/* replaces mykernel2<<<NUMCELLS,1024>>>(d_SPptr, v_d, d_start, d_end, n, spts, a3, b3)  solver.cu:198 */
+FSG_API int  fsg_stage_mykernel2(fsg_ctx *ctx, void *d_particles, int32_t *d_cells, int32_t *d_start, int32_t *d_end,
+                         int64_t n, float *spts, float *a3, float *b3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSG_H */

@@ -1,0 +1,103 @@
+"""CPU tests of the boundary: libfsg.so loads, exports every symbol include/fsg.h declares, and —
+with no GPU — refuses to compute instead of falling back."""
+import ctypes as C
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "fsg.h").read_text()
+    return sorted(set(re.findall(r"FSG_API[^;]*?\b(fsg_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree(fsg):
+    names = declared_symbols()
+    assert len(names) >= 24
+    assert sorted(fsg._lib.SIGNATURES) == names
+
+
+def test_library_exports_every_declared_symbol(fsg):
+    lib = fsg._lib.load()
+    for name in declared_symbols():
+        assert getattr(lib, name) is not None
+    assert lib.fsg_version() == 100
+
+
+def test_struct_layouts_match_header(fsg, tmp_path):
+    """ctypes mirrors vs the C compiler's view of include/fsg.h (sizes and a few offsets)."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fsg.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(fsg_config),sizeof(fsg_soa),sizeof(fsg_stats),offsetof(fsg_config,capacity),'
+                   'offsetof(fsg_config,world),offsetof(fsg_soa,boundary));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(fsg.FsgConfig), C.sizeof(fsg.FsgSoa), C.sizeof(fsg.FsgStats), fsg.FsgConfig.capacity.offset,
+                   fsg.FsgConfig.world.offset, fsg.FsgSoa.boundary.offset]
+
+
+def test_config_defaults_are_the_reference_constants(fsg):
+    cfg = fsg.FluidSolver.base_config()
+    # FluidGPU.cuh:1-31, solver.cu:17-19,187
+    assert (cfg.grid, cfg.origin, cfg.cellsize, cfg.h, cfg.dt) == (40, -1.0, 0.05, 0.06, 0.0005)
+    assert (cfg.gravity, cfg.sound, cfg.alpha_fluid, cfg.alpha_boundary) == (-9.8, 1450.0, -1.0, 200.0)
+    assert (cfg.neighbour_cap, cfg.bin_cap, cfg.capacity) == (64, 64, 8000)
+    u = fsg.FsgConfig()
+    assert fsg._lib.load().fsg_config_default(C.byref(u), fsg._lib.FSG_MODEL_UNIDYN) == 0
+    # FluidGPU-unidyn.cuh:1-36
+    assert (u.grid, u.cellsize, u.dt, u.alpha_fluid, u.alpha_boundary) == (17, 0.12, 0.0018, -0.155, 80.0)
+
+
+def test_no_cpu_fallback(fsg):
+    lib = fsg._lib.load()
+    if lib.fsg_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(fsg.FsgError) as e:
+        fsg.FluidSolver(fsg.FluidSolver.base_config())
+    assert e.value.code == fsg._lib.FSG_E_NO_DEVICE
+
+
+def test_invalid_arguments_return_codes(fsg):
+    lib = fsg._lib.load()
+    assert lib.fsg_config_default(None, 0) == fsg._lib.FSG_E_INVALID
+    cfg = fsg.FluidSolver.base_config()
+    assert lib.fsg_config_default(C.byref(cfg), 7) == fsg._lib.FSG_E_INVALID
+    cfg = fsg.FluidSolver.base_config(grid=0)
+    ctx = C.c_void_p()
+    assert lib.fsg_create(C.byref(cfg), C.byref(ctx)) == fsg._lib.FSG_E_INVALID
+    assert lib.fsg_destroy(None) == fsg._lib.FSG_E_INVALID
+    assert lib.fsg_step(None, 1) == fsg._lib.FSG_E_INVALID
+
+
+def test_plume_host_scene(fsg):
+    cfg = fsg.scenes.plume_config(32)
+    a, b = fsg.scenes.plume_scene(cfg), fsg.scenes.plume_scene(cfg)
+    n = a["pos"].shape[0]
+    assert n == fsg.scenes.plume_count(cfg) == 16587
+    assert np.array_equal(a["pos"], b["pos"]) and np.array_equal(a["vel"], b["vel"])
+    L = 32 * 0.12
+    r = np.hypot(a["pos"][:, 0], a["pos"][:, 1])
+    assert r.max() <= L / 8 + 0.01                       # column about the z axis
+    assert a["pos"][:, 2].min() >= cfg.origin and a["pos"][:, 2].max() <= cfg.origin + 0.75 * L + 0.01
+    assert 0.18 <= a["vel"][:, 2].min() and a["vel"][:, 2].max() <= 0.5
+    # ~13.8 particles per occupied bin inside the column
+    import oracle_py
+    ids = oracle_py.cell_ids(oracle_py.params_from_cfg(cfg), a["pos"])
+    assert 11.0 < n / len(np.unique(ids)) < 15.0
+    # different seed, different jitter
+    c = fsg.scenes.plume_scene(cfg, seed=1)
+    assert not np.array_equal(a["pos"], c["pos"])
+
+
+def test_section_files_roundtrip(fsg, tmp_path):
+    s = fsg.scenes.random_base_scene(100, 3, boundary_frac=0.3)
+    fsg.sections.write_sections(tmp_path / "s.bin", s)
+    back = fsg.sections.read_sections(tmp_path / "s.bin")
+    for k in s:
+        assert np.array_equal(back[k], s[k].reshape(-1))

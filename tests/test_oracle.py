@@ -1,0 +1,107 @@
+"""CPU tests of the oracle itself: it must reproduce every known answer we hold from the reference's
+own code — the host-compiled kernel()/kernel_test()/kernel_derivative()/set_dens() values
+(tests/golden/kat_base.json, produced by oracle/ref_kat.cu linked against the unmodified
+FluidGPU.o), the bin ids of SURVEY.md App. D, and the state dumps of the reference's CUDA kernels
+run on a B200 (tests/golden/ref_*.npz, produced by tools/make_golden.py)."""
+import json
+import pathlib
+
+import numpy as np
+import pytest
+
+import oracle_py
+from oracle_py import rel_l2
+
+GOLD = pathlib.Path(__file__).parent / "golden"
+
+
+def test_kernel_known_answers(oracle):
+    g = json.loads((GOLD / "kat_base.json").read_text())
+    assert g["sizeof_particle"] == 340
+    for r, k, kt, kd in g["kernel"]:
+        r = float.fromhex(r)
+        assert oracle.fsgo_kernel(r) == float.fromhex(k)
+        assert oracle.fsgo_kernel_test(r) == float.fromhex(kt)
+        assert oracle.fsgo_kernel_derivative(r) == float.fromhex(kd)
+    for b, x, v in g["set_dens"]:
+        assert oracle.fsgo_set_dens(float.fromhex(x), b) == float.fromhex(v)
+
+
+def test_appendix_d_values(oracle):
+    # SURVEY.md App. D (probed from the reference object)
+    assert oracle.fsgo_kernel(0.0) == float.fromhex("0x1.706a2p+10")
+    assert oracle.fsgo_kernel(np.float32(0.12)) == float.fromhex("0x1.36d98cp-65")     # double compare at the support edge
+    assert oracle.fsgo_kernel(np.float32(0.13)) == 0.0
+    assert oracle.fsgo_kernel_derivative(np.float32(0.06)) == float.fromhex("-0x1.2f9074p-31")
+    assert oracle.fsgo_set_dens(0.0, 0) == float.fromhex("0x1.231094p+13")
+
+
+def test_config1_bin_ids(fsg):
+    s = fsg.scenes.base_default_scene()
+    ids = oracle_py.cell_ids(oracle_py.base_params(), s["pos"])
+    assert [int(ids[j]) for j in (0, 1, 14, 15, 224, 225, 7999)] == [25776, 25776, 25787, 27376, 43387, 25816, 38099]
+    assert ids.min() == 25776 and ids.max() == 44507
+    assert len(np.unique(ids)) == 4176     # occupied bins at t = 0
+
+
+def test_first_step_density_quirk(fsg):
+    """newdens starts at RHO_0 (FluidGPU.cuh:144): step-0 density ~ (9550 + sum W + W0)/23 + 9250."""
+    sim = oracle_py.OracleSim(oracle_py.base_params(), fsg.scenes.base_default_scene()).step(1)
+    st = sim.state()
+    assert 9900 < st["dens"].min() and 10000 < st["dens"].mean() < 10400
+    assert np.all(st["newdens"] == 0) and np.all(st["newdelpress"] == 0)
+    assert sim.stats[2] == 0 and sim.stats[3] == 4176
+
+
+def test_oracle_is_deterministic_and_thread_count_independent(fsg):
+    s = fsg.scenes.random_base_scene(2000, 5, boundary_frac=0.1)
+    a = oracle_py.OracleSim(oracle_py.base_params(threads=1), s).step(5).state()
+    b = oracle_py.OracleSim(oracle_py.base_params(threads=4), s).step(5).state()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_linear_momentum_symmetry(fsg):
+    """Pair forces are antisymmetric when no neighbour is dropped: sum of delpress over a closed
+    fluid blob is ~0 relative to the sum of magnitudes."""
+    s = fsg.scenes.random_base_scene(1500, 9, box=((-0.15, 0.15),) * 3, spacing=0.05)
+    sim = oracle_py.OracleSim(oracle_py.base_params(block_threads=0, bin_cap=0), s).step(1)
+    dp = sim.state()["delpress"].astype(np.float64)
+    assert np.abs(dp.sum(0)).max() <= 1e-4 * np.abs(dp).sum()
+
+
+GOLDEN_CASES = [("config1", (1, 2, 10, 100)), ("random_boundary", (1, 5, 20)), ("dense_overflow", (1, 3))]
+
+
+def _golden_scene(fsg, name):
+    if name == "config1":
+        return fsg.scenes.base_default_scene()
+    if name == "random_boundary":
+        return fsg.scenes.random_base_scene(5000, 2, boundary_frac=0.15)
+    return fsg.scenes.random_base_scene(6000, 7, box=((-0.2, 0.2),) * 3, spacing=0.025, jitter=0.005)
+
+
+@pytest.mark.parametrize("name,steps", GOLDEN_CASES)
+def test_oracle_against_reference_gpu_dumps(fsg, name, steps):
+    """Pins the CPU restatement against the reference's own CUDA kernels (run on a B200)."""
+    files = [GOLD / f"ref_{name}_step{k}.npz" for k in steps]
+    if not all(f.exists() for f in files):
+        pytest.skip("golden dumps not generated yet (tools/make_golden.py on a GPU box)")
+    noise = json.loads((GOLD / "golden_noise.json").read_text())["run_to_run_rel_l2"]
+    sim = oracle_py.OracleSim(oracle_py.base_params(), _golden_scene(fsg, name))
+    done = 0
+    for k, f in zip(steps, files):
+        sim.step(k - done)
+        done = k
+        ref = dict(np.load(f))
+        n = len(ref["index"])
+        if k == 1:   # identical inputs: integer work bit-exact
+            assert np.array_equal(sim.cells_sorted, ref["cells_sorted"])
+            assert np.array_equal(sim.start, ref["start"]) and np.array_equal(sim.end, ref["end"])
+            assert np.array_equal(sim.s["index"], ref["index"]) and np.array_equal(sim.s["cell"], ref["cell"])
+            assert np.array_equal(sim.b3, ref["b3"]) and np.array_equal(sim.spts, ref["spts"])
+        o, r = np.argsort(sim.s["index"], kind="stable"), np.argsort(ref["index"], kind="stable")
+        for fld in ("pos", "vel", "acc", "dens", "press", "delpress"):
+            err = rel_l2(sim.s[fld].reshape(n, -1)[o], ref[fld].reshape(n, -1)[r])
+            floor = noise[f"{name}_step{k}"][fld]
+            assert err <= max(1e-5, 10 * floor), (name, k, fld, err, floor)
