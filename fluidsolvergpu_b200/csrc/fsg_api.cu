@@ -49,6 +49,10 @@ void fsg_derive_constants(const fsg_config &cfg, FsgDev &d)
     while (sqrtf(nextafterf(d2, INFINITY)) <= ds_max) d2 = nextafterf(d2, INFINITY);
     d.d2_max = d2;
     d.h_le = largest_float_le(h);
+    d2 = d.h_le * d.h_le;
+    while (sqrtf(d2) > d.h_le) d2 = nextafterf(d2, 0.f);
+    while (sqrtf(nextafterf(d2, INFINITY)) <= d.h_le) d2 = nextafterf(d2, INFINITY);
+    d.d2_h = d2;
     d.h_lt = largest_float_lt(h);
     d.twoh_lt = largest_float_lt(2 * h);
     d.hf = (float)h;
@@ -122,6 +126,8 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
     cudaFree(c->counters); cudaFree(c->dstats); cudaFree(c->sort_tmp);
     cudaFree(c->stage);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return FSG_OK;
@@ -421,6 +427,57 @@ extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
     return FSG_OK;
 }
 
+// ---- per-phase device timing (fsg_set_profiling / fsg_get_phase_ms) ----
+static cudaEvent_t prof_mark(fsg_ctx *c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    cudaEventRecord(e, c->stream);
+    c->ev_used.push_back(e);
+    return e;
+}
+
+static void prof_collect(fsg_ctx *c)
+{
+    // ev_used holds groups of 5 marks: t0 | sort | reorder | pair+update | end
+    for (size_t g = 0; g + 5 <= c->ev_used.size(); g += 5) {
+        float ms;
+        cudaEvent_t *e = &c->ev_used[g];
+        if (cudaEventElapsedTime(&ms, e[0], e[1]) == cudaSuccess) c->phase_ms[3] += ms;
+        if (cudaEventElapsedTime(&ms, e[1], e[2]) == cudaSuccess) c->phase_ms[0] += ms;
+        if (cudaEventElapsedTime(&ms, e[2], e[3]) == cudaSuccess) c->phase_ms[1] += ms;
+        if (cudaEventElapsedTime(&ms, e[3], e[4]) == cudaSuccess) c->phase_ms[2] += ms;
+        c->phase_steps++;
+    }
+    for (cudaEvent_t e : c->ev_used) c->ev_pool.push_back(e);
+    c->ev_used.clear();
+}
+
+extern "C" int fsg_set_profiling(fsg_ctx *c, int on)
+{
+    if (!c) return FSG_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    c->profiling = on != 0;
+    for (double &m : c->phase_ms) m = 0;
+    c->phase_steps = 0;
+    return FSG_OK;
+}
+
+extern "C" int fsg_get_phase_ms(fsg_ctx *c, double ms[4], int64_t *steps)
+{
+    if (!c || !ms) return FSG_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    for (int i = 0; i < 4; i++) { ms[i] = c->phase_ms[i]; c->phase_ms[i] = 0; }
+    if (steps) *steps = c->phase_steps;
+    c->phase_steps = 0;
+    return FSG_OK;
+}
+
 // ---- the step: solver.cu:181-198 ----
 extern "C" int fsg_step(fsg_ctx *c, int nsteps)
 {
@@ -429,6 +486,8 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
     const int64_t n = c->n;
     if (n <= 0) { c->steps += nsteps; return FSG_OK; }
     for (int t = 0; t < nsteps; t++) {
+        const bool prof = c->profiling && c->ev_used.size() < 5 * 4096;
+        if (prof) prof_mark(c);
         if (c->tables_dirty) {
             CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, n, c->stream));
             c->launches++;
@@ -437,17 +496,21 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         CU(c, cudaMemsetAsync(c->counters + nxt, 0, sizeof(int), c->stream));
         CU(c, cudaMemsetAsync(c->counters + 2, 0, 2 * sizeof(int), c->stream));
         if (c->cfg.collect_stats) CU(c, cudaMemsetAsync(c->dstats, 0, 4 * sizeof(unsigned long long), c->stream));
+        if (prof) prof_mark(c);
         // thrust::sort_by_key, key half (solver.cu:181)
         CU(c, fsg_sort_pairs(c->sort_tmp, c->sort_tmp_bytes, c->keysB, c->keysA, c->iota, c->perm, n, c->sort_bits, c->stream));
+        if (prof) prof_mark(c);
         // value half + findneighbours (solver.cu:181-182)
         CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA,
                                  c->start, c->end, c->binlist[nxt], c->counters + nxt, c->counters + 3, c->stream));
         c->launches++;
+        if (prof) prof_mark(c);
         // mykernel + mykernel2 (solver.cu:187,198)
         int l = 0;
         CU(c, fsg_launch_pair_update(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2,
                                      c->carry_live ? c->carryA : nullptr, &l, c->stream));
         c->launches += l;
+        if (prof) prof_mark(c);
         c->carry_live = false;
         c->cur = nxt;
         c->tables_dirty = true;

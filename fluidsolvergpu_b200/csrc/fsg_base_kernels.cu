@@ -5,11 +5,7 @@
 //                    (the reference's value-carrying sort + findneighbours, solver.cu:181-182).
 //   k_pair_update  : gather-form pair sums over the 27-bin neighbourhood, fused with
 //                    Particle::update and re-binning (the reference's mykernel + mykernel2).
-#include "fsg_internal.cuh"
-
-#include <math.h>
-
-#define FULL 0xffffffffu
+#include "fsg_device.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // small utilities
@@ -35,20 +31,6 @@ cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s)
     if (n <= 0) return cudaSuccess;
     k_fill<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, v, n);
     return cudaGetLastError();
-}
-
-// Bin id of a position — the expression of FluidGPU.cu:419 / solver.cu:119:
-//   int((x - XMIN)/CELLSIZE)*G*G + int((y - YMIN)/CELLSIZE)*G + int((z - ZMIN)/CELLSIZE)
-// (float subtraction, double division, truncation).  Where the reference's linear id would leave
-// [0, numcells) — it then writes start[]/end[] out of bounds, FluidGPU.cu:110 — the particle is
-// parked with id == numcells: it sorts last and is never touched again.
-__device__ __forceinline__ int bin_id(const FsgDev &d, float x, float y, float z)
-{
-    float fx = x - d.origin, fy = y - d.origin, fz = z - d.origin;
-    double qx = (double)fx / d.cellsize, qy = (double)fy / d.cellsize, qz = (double)fz / d.cellsize;
-    if (!(fabs(qx) < 1e6 && fabs(qy) < 1e6 && fabs(qz) < 1e6)) return d.numcells;
-    long long l = (long long)(int)qx * d.G2 + (long long)(int)qy * d.G + (int)qz;
-    return (l < 0 || l >= d.numcells) ? d.numcells : (int)l;
 }
 
 __global__ void k_keys(FsgDev d, const float4 *__restrict__ posd, int *__restrict__ keys, int64_t n)
@@ -148,14 +130,6 @@ cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, cons
 // double for the promotion-faithful path (cfg.pair_fp64).
 // Candidate j is staged in shared memory as  pj = (x, y, z, ±dens)  vj = (vx, vy, vz, press/dens^2).
 // ------------------------------------------------------------------------------------------------
-// Squared distance exactly as Particle::distance forms it (FluidGPU.cuh:193-195): three rounded
-// squares added left to right, no FMA contraction — the in/out decision at ds == 2h must not depend
-// on how the compiler fuses the sum.
-__device__ __forceinline__ float dist2(float rx, float ry, float rz)
-{
-    return __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
-}
-
 template <typename R>
 __device__ __forceinline__ void pair_body(const FsgDev &d, float rabx, float raby, float rabz, float d2in,
                                           const float4 &vi, float densi, bool bi, float pod2i, const float4 &pj,
@@ -211,44 +185,6 @@ __device__ __forceinline__ void pair_body(const FsgDev &d, float rabx, float rab
     }
 }
 
-// Particle::update (FluidGPU.cuh:270-304) + the tail of mykernel2 (FluidGPU.cu:419-425) for one
-// particle.  Follows the reference's promotions expression by expression — it runs once per
-// particle, so the double arithmetic is free next to the pair loop.
-__device__ __forceinline__ void particle_update(const FsgDev &d, float4 &pd, float4 &vp, float4 &af, float4 &dpi,
-                                                float newdens, float ndx, float ndy, float ndz, int &key)
-{
-    bool bnd = pd.w < 0.f;
-    // set_dens  cuh:165-167
-    float dens = (float)((double)(newdens + d.w0) / 23.0 * (double)(1 + (float)bnd * 1.5) + 9250);
-    // calculate_pressure  cuh:256-257
-    float press = (float)((double)(1000 * powf((float)d.sound, 0.f) * 9550) / 7.0 * (double)(powf(dens / 9550, 7.f) - 1));
-    dpi.x = ndx;   // set_delpress  cuh:276
-    dpi.y = ndy;
-    dpi.z = ndz;
-    if (!bnd) {
-        const double DT = d.dt;
-        float x = (float)((double)pd.x + DT * (double)vp.x);   // cuh:286-288 (DIFF == 0)
-        float y = (float)((double)pd.y + DT * (double)vp.y);
-        float z = (float)((double)pd.z + DT * (double)vp.z);
-        double tx = ((double)vp.x + DT * (double)af.x + DT * 0.0);          // cuh:290-295
-        float vx = (float)(tx - (tx > 0) * 0.003 + (tx < 0) * 0.003);
-        vx *= ((double)fabsf(vx) > 0.003);
-        double ty = ((double)vp.y + DT * (double)af.y + DT * 0.0);
-        float vy = (float)(ty - (ty > 0) * 0.003 + (ty < 0) * 0.003);
-        vy *= ((double)fabsf(vy) > 0.003);
-        float vz = (float)((double)vp.z + DT * (double)af.z + DT * 0.0);
-        vz *= ((double)fabsf(vz) > 0.003);
-        af.x = (float)(-(150.0 / (double)dens) * (double)ndx);               // cuh:298-300
-        af.y = (float)(-(150.0 / (double)dens) * (double)ndy);
-        af.z = (float)(d.gravity + (-150.0 / (double)dens) * (double)ndz);
-        pd.x = x; pd.y = y; pd.z = z;
-        vp.x = vx; vp.y = vy; vp.z = vz;
-    }
-    pd.w = bnd ? -dens : dens;
-    vp.w = press;
-    key = bin_id(d, pd.x, pd.y, pd.z);   // FluidGPU.cu:419
-}
-
 // ------------------------------------------------------------------------------------------------
 // k_pair_update — one warp per occupied home bin (dynamic queue over the occupied-bin list).
 //
@@ -267,19 +203,6 @@ __device__ __forceinline__ void particle_update(const FsgDev &d, float4 &pd, flo
 #define PAIR_WARPS 4
 #define PAIR_TILE 512   // staged candidates per warp (32 B each)
 #define PAIR_SMEM ((size_t)PAIR_WARPS * PAIR_TILE * (2 * sizeof(float4) + sizeof(unsigned short)))
-
-struct PairArgs {
-    FsgDev d;
-    int n;
-    const int *keysA;
-    const int *start, *end;
-    const int *binlist, *nocc;
-    int *work;
-    FsgState A, B;
-    int *keysB;
-    const float4 *carry;
-    unsigned long long *stats;
-};
 
 template <typename R, bool STATS>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
@@ -465,7 +388,7 @@ cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binli
     int64_t maxb = (int64_t)c->sm_count * 3;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    const bool stats = c->cfg.collect_stats != 0, f64 = c->cfg.pair_fp64 != 0;
+    const bool stats = c->cfg.collect_stats != 0;
     const size_t smem = PAIR_SMEM;
     static bool attr_done = false;
     if (!attr_done) {
@@ -475,12 +398,17 @@ cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binli
         cudaFuncSetAttribute(k_pair_update<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
-    if (f64) {
+    // pair_fp64: 1 = promotion-faithful double path, 2 = the same queue-everything kernel in fp32
+    // (kept as a cross-check of the fast kernel), 0 = fast fp32 kernel (fsg_pair_fast.cu)
+    if (c->cfg.pair_fp64 == 1) {
         if (stats) k_pair_update<double, true><<<(unsigned)blocks, PAIR_WARPS * 32, smem, s>>>(a);
         else k_pair_update<double, false><<<(unsigned)blocks, PAIR_WARPS * 32, smem, s>>>(a);
-    } else {
+    } else if (c->cfg.pair_fp64 == 2) {
         if (stats) k_pair_update<float, true><<<(unsigned)blocks, PAIR_WARPS * 32, smem, s>>>(a);
         else k_pair_update<float, false><<<(unsigned)blocks, PAIR_WARPS * 32, smem, s>>>(a);
+    } else {
+        cudaError_t e2 = fsg_launch_pair_fast(a, stats, c->sm_count, s);
+        if (e2 != cudaSuccess) return e2;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -1,0 +1,84 @@
+// fsg_device.cuh — device helpers shared by the kernels of the base particle step.
+#pragma once
+#include "fsg_internal.cuh"
+
+#include <math.h>
+
+#define FULL 0xffffffffu
+
+// Bin id of a position — the expression of FluidGPU.cu:419 / solver.cu:119:
+//   int((x - XMIN)/CELLSIZE)*G*G + int((y - YMIN)/CELLSIZE)*G + int((z - ZMIN)/CELLSIZE)
+// (float subtraction, double division, truncation).  Where the reference's linear id would leave
+// [0, numcells) — it then writes start[]/end[] out of bounds, FluidGPU.cu:110 — the particle is
+// parked with id == numcells: it sorts last and is never touched again.
+__device__ __forceinline__ int bin_id(const FsgDev &d, float x, float y, float z)
+{
+    float fx = x - d.origin, fy = y - d.origin, fz = z - d.origin;
+    double qx = (double)fx / d.cellsize, qy = (double)fy / d.cellsize, qz = (double)fz / d.cellsize;
+    if (!(fabs(qx) < 1e6 && fabs(qy) < 1e6 && fabs(qz) < 1e6)) return d.numcells;
+    long long l = (long long)(int)qx * d.G2 + (long long)(int)qy * d.G + (int)qz;
+    return (l < 0 || l >= d.numcells) ? d.numcells : (int)l;
+}
+
+// Squared distance exactly as Particle::distance forms it (FluidGPU.cuh:193-195): three rounded
+// squares added left to right, no FMA contraction — the in/out decision at ds == 2h must not depend
+// on how the compiler fuses the sum.
+__device__ __forceinline__ float dist2(float rx, float ry, float rz)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+}
+
+// Particle::update (FluidGPU.cuh:270-304) + the tail of mykernel2 (FluidGPU.cu:419-425) for one
+// particle.  Follows the reference's promotions expression by expression — it runs once per
+// particle, so the double arithmetic is free next to the pair loop.
+__device__ __forceinline__ void particle_update(const FsgDev &d, float4 &pd, float4 &vp, float4 &af, float4 &dpi,
+                                                float newdens, float ndx, float ndy, float ndz, int &key)
+{
+    bool bnd = pd.w < 0.f;
+    // set_dens  cuh:165-167
+    float dens = (float)((double)(newdens + d.w0) / 23.0 * (double)(1 + (float)bnd * 1.5) + 9250);
+    // calculate_pressure  cuh:256-257
+    float press = (float)((double)(1000 * powf((float)d.sound, 0.f) * 9550) / 7.0 * (double)(powf(dens / 9550, 7.f) - 1));
+    dpi.x = ndx;   // set_delpress  cuh:276
+    dpi.y = ndy;
+    dpi.z = ndz;
+    if (!bnd) {
+        const double DT = d.dt;
+        float x = (float)((double)pd.x + DT * (double)vp.x);   // cuh:286-288 (DIFF == 0)
+        float y = (float)((double)pd.y + DT * (double)vp.y);
+        float z = (float)((double)pd.z + DT * (double)vp.z);
+        double tx = ((double)vp.x + DT * (double)af.x + DT * 0.0);          // cuh:290-295
+        float vx = (float)(tx - (tx > 0) * 0.003 + (tx < 0) * 0.003);
+        vx *= ((double)fabsf(vx) > 0.003);
+        double ty = ((double)vp.y + DT * (double)af.y + DT * 0.0);
+        float vy = (float)(ty - (ty > 0) * 0.003 + (ty < 0) * 0.003);
+        vy *= ((double)fabsf(vy) > 0.003);
+        float vz = (float)((double)vp.z + DT * (double)af.z + DT * 0.0);
+        vz *= ((double)fabsf(vz) > 0.003);
+        af.x = (float)(-(150.0 / (double)dens) * (double)ndx);               // cuh:298-300
+        af.y = (float)(-(150.0 / (double)dens) * (double)ndy);
+        af.z = (float)(d.gravity + (-150.0 / (double)dens) * (double)ndz);
+        pd.x = x; pd.y = y; pd.z = z;
+        vp.x = vx; vp.y = vy; vp.z = vz;
+    }
+    pd.w = bnd ? -dens : dens;
+    vp.w = press;
+    key = bin_id(d, pd.x, pd.y, pd.z);   // FluidGPU.cu:419
+}
+
+struct PairArgs {
+    FsgDev d;
+    int n;
+    const int *keysA;
+    const int *start, *end;
+    const int *binlist, *nocc;
+    int *work;
+    FsgState A, B;
+    int *keysB;
+    const float4 *carry;
+    unsigned long long *stats;
+};
+
+
+// fsg_pair_fast.cu
+cudaError_t fsg_launch_pair_fast(const PairArgs &a, bool stats, int sm_count, cudaStream_t s);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/fsg.h"
 
@@ -19,6 +20,7 @@ struct FsgDev {
     double cellsize, h, dt, gravity, sound, alpha_fluid, alpha_boundary;
     // fp32 pair constants
     float d2_max;    // largest d2 with sqrtf(d2) <= 2h (as the double compare FluidGPU.cu:236 decides)
+    float d2_h;      // largest d2 with sqrtf(d2) <= h_le
     float h_le;      // largest float r with (double)r <= h        FluidGPU.cu:12
     float h_lt;      // largest float r with (double)r <  h        FluidGPU.cu:36
     float twoh_lt;   // largest float r with (double)r <  2h       FluidGPU.cu:15
@@ -71,6 +73,10 @@ struct fsg_ctx {
     int64_t steps;
     int64_t launches;
     int sm_count;
+    bool profiling;     // record events around the phases of every step (fsg_set_profiling)
+    std::vector<cudaEvent_t> ev_pool, ev_used;   // 5 events per profiled step
+    double phase_ms[4];
+    int64_t phase_steps;
 };
 
 // fsg_sort.cu — stable radix sort of (bin id, slot) pairs; the reference's thrust::sort_by_key (solver.cu:181)

@@ -152,6 +152,16 @@ class FluidSolver:
         self._check(self._lib.fsg_get_stats(self._ctx, C.byref(st)), "fsg_get_stats")
         return {k: getattr(st, k) for k, _ in FsgStats._fields_}
 
+    def set_profiling(self, on: bool = True):
+        self._check(self._lib.fsg_set_profiling(self._ctx, int(on)), "fsg_set_profiling")
+
+    def phase_ms(self) -> dict:
+        """Milliseconds per phase accumulated since the last call (CUDA events on the solver's stream)."""
+        ms = (C.c_double * 4)()
+        steps = C.c_int64(0)
+        self._check(self._lib.fsg_get_phase_ms(self._ctx, C.byref(ms), C.byref(steps)), "fsg_get_phase_ms")
+        return dict(sort=ms[0], reorder=ms[1], pair_update=ms[2], other=ms[3], steps=steps.value)
+
     def scene_plume(self, spacing: float = 0.05, jitter: float = 0.005, seed: int = 20261018) -> int:
         n = C.c_int64(0)
         self._check(self._lib.fsg_scene_plume(self._ctx, spacing, jitter, seed, C.byref(n)), "fsg_scene_plume")

@@ -73,8 +73,9 @@ typedef struct fsg_config {
                                count (64: FluidGPU.cu:174); 0 = off                           */
     int64_t capacity;       /* particles this context can hold                                */
     int32_t device;         /* CUDA device ordinal                                            */
-    int32_t pair_fp64;      /* 1: evaluate the pair sub-expressions the reference evaluates in
-                               double in double (Appendix A); 0: fp32 (default)               */
+    int32_t pair_fp64;      /* 0: fp32 production kernel (default); 1: evaluate the pair sub-expressions
+                               the reference evaluates in double in double;
+                               2: the kernel of mode 1 in fp32 (cross-check)                  */
     int32_t collect_stats;  /* 1: count candidate / in-range pairs each step                   */
     /* slab decomposition along x, the slowest bin axis (solver-unidyn.cu:187-193) */
     int32_t rank, world;    /* this context's slab and the number of slabs (1 = no decomposition) */
@@ -144,6 +145,12 @@ FSG_API int  fsg_export_viz(fsg_ctx *ctx, float *spts, float *a3, float *b3);
  * cells[n] sorted keys, start/end[numcells] (FluidGPU.cu:106-117; -1 = empty bin). */
 FSG_API int  fsg_get_tables(fsg_ctx *ctx, int32_t *cells, int32_t *start, int32_t *end);
 FSG_API int  fsg_get_stats(fsg_ctx *ctx, fsg_stats *out);
+/* Device-side phase timing (CUDA events on the context's stream around each phase of every step;
+ * the reference prints the same kind of figure, solver.cu:175-197).  fsg_get_phase_ms synchronises,
+ * returns the milliseconds accumulated since the last call — ms[0] key sort, ms[1] reorder + bin
+ * tables, ms[2] pair sums + update, ms[3] table reset / bookkeeping — and clears them. */
+FSG_API int  fsg_set_profiling(fsg_ctx *ctx, int on);
+FSG_API int  fsg_get_phase_ms(fsg_ctx *ctx, double ms[4], int64_t *steps);
 
 /* Device-side scene generation for the throughput configs: a column of fluid
  * particles about the z axis of a grid^3 bin domain, lattice spacing `spacing`, jitter from

@@ -70,7 +70,7 @@ def test_linear_momentum_symmetry(fsg):
     assert np.abs(dp.sum(0)).max() <= 1e-4 * np.abs(dp).sum()
 
 
-GOLDEN_CASES = [("config1", (1, 2, 10, 100)), ("random_boundary", (1, 5, 20)), ("dense_overflow", (1, 3))]
+GOLDEN_CASES = [("config1", (1, 2, 10, 100)), ("random_boundary", (1, 2, 3)), ("dense_overflow", (1, 3))]
 
 
 def _golden_scene(fsg, name):
@@ -104,4 +104,5 @@ def test_oracle_against_reference_gpu_dumps(fsg, name, steps):
         for fld in ("pos", "vel", "acc", "dens", "press", "delpress"):
             err = rel_l2(sim.s[fld].reshape(n, -1)[o], ref[fld].reshape(n, -1)[r])
             floor = noise[f"{name}_step{k}"][fld]
-            assert err <= max(1e-5, 10 * floor), (name, k, fld, err, floor)
+            bound = 1e-5 if k <= 2 else max(1e-5, 5 * floor)
+            assert err <= bound, (name, k, fld, err, floor)

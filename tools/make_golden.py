@@ -27,7 +27,7 @@ KEEP = ("pos", "vel", "acc", "dens", "press", "delpress", "newdens", "newdelpres
 CASES = {
     # name: (scene factory or None for the built-in scene of solver.cu:115-121, steps to dump)
     "config1": (None, (1, 2, 10, 100)),
-    "random_boundary": (lambda: scenes.random_base_scene(5000, 2, boundary_frac=0.15), (1, 5, 20)),
+    "random_boundary": (lambda: scenes.random_base_scene(5000, 2, boundary_frac=0.15), (1, 2, 3)),
     "dense_overflow": (lambda: scenes.random_base_scene(6000, 7, box=((-0.2, 0.2),) * 3, spacing=0.025, jitter=0.005), (1, 3)),
 }
 
