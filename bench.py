@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the per-timestep particle update (the loop body of solver.cu:181-198) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--grid G] [--impl fsg|reference]
+
+A "step" is one pass of the hot path (key sort -> reorder + bin tables -> pair sums + EOS/integrate/re-bin)
+over the whole synthetic plume scene of SURVEY.md §8d: a column of fluid particles in a G^3 bin grid
+(BASELINE.json configs[3], 512^3; configs[2] and [4] with --grid 256 / 1024).
+
+  value     cell-updates/s = G^3 bins x steps / s, state resident in HBM (device-generated scene),
+            timed with CUDA events on the solver's stream, max over ranks.
+  e2e       the same metric through the C ABI with HOST buffers: every step uploads the full particle
+            state from pinned host memory (fsg_upload_soa), steps once, and downloads it again
+            (fsg_download_soa); copies are inside the timed region.
+  roofline  the dominant kernel (pair sums + update), timed live with CUDA events on the solver's
+            stream inside the timed region (fsg_set_profiling), as algorithmic bytes / time vs the
+            measured HBM peak, plus the FP32 issue-rate view that actually bounds it.
+  cpu_baseline  the CPU oracle (oracle/, test infrastructure) on a bounded sample of the same scene
+            family on this box's host cores — a reported baseline, not a target.
+
+--impl reference times the CPU restatement of the reference path (the reference ships CUDA kernels
+only; its "CPU path" is the host restatement oracle/fsg_oracle.c) with every host thread.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES_STEP = 272      # algorithmic HBM bytes per particle-step (reorder 136 + tables 4 + pair/update 132)
+ALG_BYTES_PAIR = 132      # the fused pair-sum/EOS/integrate/re-bin kernel: read 64 + write 64 + new key 4
+FLOP_IN_RANGE, FLOP_REJECTED = 50, 12   # SURVEY.md §8d algorithmic flop per in-range / rejected candidate
+SPACING, JITTER, SEED = 0.05, 0.005, 20261018
+CPU_SAMPLE_GRID = 128     # bounded sample for the CPU legs: the same plume at 128^3 bins (1.07 M particles)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.path = device, None, f"/tmp/fsg_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle = test infrastructure; this is one of the two places allowed to execute it)
+# ------------------------------------------------------------------------------------------------
+def cpu_run(grid: int, steps: int, warmup: int, threads: int = 0):
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_py
+    import fluidsolvergpu_b200 as fsg
+    cfg = fsg.scenes.plume_config(grid)
+    state = fsg.scenes.plume_scene(cfg, SPACING, JITTER, SEED)
+    n = state["pos"].shape[0]
+    cores = threads or (os.cpu_count() or 1)
+    sim = oracle_py.OracleSim(oracle_py.params_from_cfg(cfg, threads=cores), state)
+    sim.step(warmup)
+    t0 = time.perf_counter()
+    sim.step(steps)
+    dt = time.perf_counter() - t0
+    return dict(n=n, grid=grid, cores=cores, seconds=dt, ms_per_step=dt / steps * 1e3,
+                cell_updates_per_s=grid ** 3 * steps / dt, particle_steps_per_s=n * steps / dt)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_run(CPU_SAMPLE_GRID, args.steps, args.warmup)
+    sample = f"plume {CPU_SAMPLE_GRID}^3 bins, {r['n']} particles per step, {args.steps} steps (bounded sample of the {args.grid}^3 scene family; rate per bin is size-independent)"
+    line = {
+        "impl": "reference", "metric": "cell-updates/s", "value": r["cell_updates_per_s"], "unit": "cell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.grid, None, args.gpus),
+        "particle_steps_per_s": r["particle_steps_per_s"],
+        "cpu_baseline": {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference ships CUDA kernels only; this arm is the host restatement of those kernels (oracle/fsg_oracle.c, OpenMP over bins)",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(grid, n, gpus):
+    return {"workload": f"synthetic plume, {grid}^3 bins (CELLSIZE 0.12 = 2h, lattice spacing {SPACING}, jitter {JITTER}, seed {SEED}), "
+                        f"base SPH step: key sort + reorder/bin tables + pair sums + EOS/integrate/re-bin",
+            "grid": grid, "particles": n, "decomposition": "single device" if gpus == 1 else f"{gpus} x-slabs, ghost exchange per step",
+            "l2_policy": "working set (>= 64 B x particles x 2 buffers) exceeds the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def fsg_arm(args):
+    import torch
+    import torch.distributed as dist
+    import fluidsolvergpu_b200 as fsg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libfsg has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    hbm_peak, peak_src, sm_max = peaks()
+    G = args.grid
+    cfg = fsg.scenes.plume_config(G)
+    cfg.device = local
+    cfg.rank, cfg.world = rank, world
+    n_total = fsg.scenes.plume_count(cfg, SPACING)
+    cfg.capacity = n_total if world == 1 else int(n_total / world * 1.5) + 4096
+    solver = fsg.FluidSolver(cfg) if world == 1 else fsg.SlabSolver(cfg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_local = solver.scene_plume(SPACING, JITTER, SEED)
+    stream = torch.cuda.ExternalStream(solver.stream())
+    solver.step(args.warmup)
+    barrier()
+    l0 = solver.stats()["kernel_launches"]
+    solver.set_profiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    solver.step(args.steps, sync=False)
+    e1.record(stream)
+    solver.sync()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    phase = solver.phase_ms()
+    solver.set_profiling(False)
+    launches = solver.stats()["kernel_launches"] - l0
+    if world > 1:
+        t = torch.tensor([ms_total, phase["pair_update"], float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, pair_ms_max = float(t[0]), float(t[1])
+        t2 = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        launches = int(t2[0])
+    ms_step = ms_total / args.steps
+    value = G ** 3 / (ms_step * 1e-3)
+
+    # pair statistics of one extra step (outside the timed region) for the FP32 view of the roofline
+    st = None
+    if world == 1:
+        st = solver.pair_stats_one_step()
+
+    # ---- roofline of the dominant kernel ----
+    pair_ms = phase["pair_update"] / max(1, phase["steps"])
+    achieved = ALG_BYTES_PAIR * n_local / (pair_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_pair_update_fast (pair sums + EOS/integrate/re-bin)", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": pair_ms, "share_of_step": pair_ms / ms_step,
+                "algorithmic_bytes_per_launch": ALG_BYTES_PAIR * n_local,
+                "note": "this kernel is CUDA-core (FP32 issue) bound, not HBM bound: see roofline_fp32; the HBM-bound phases are in `phases`"}
+    extra = {}
+    if st is not None:
+        flop = FLOP_IN_RANGE * st["pairs_in_range"] + FLOP_REJECTED * (st["pairs_tested"] - st["pairs_in_range"])
+        mhz = (clocks or {}).get("sm_mhz") or sm_max
+        peak_tf = 148 * 128 * 2 * mhz * 1e6 / 1e12
+        extra["roofline_fp32"] = {"bound": "fp32 cuda cores", "achieved": flop / (pair_ms * 1e-3) / 1e12, "peak": peak_tf,
+                                  "unit": "TFLOP/s", "frac": flop / (pair_ms * 1e-3) / 1e12 / peak_tf,
+                                  "peak_source": f"148 SM x 128 lanes x 2 flop x {mhz:.0f} MHz (SM clock sampled during the run)",
+                                  "pairs_tested": st["pairs_tested"], "pairs_in_range": st["pairs_in_range"],
+                                  "pair_tests_per_s": st["pairs_tested"] / (pair_ms * 1e-3)}
+    phases = {k: phase[k] / max(1, phase["steps"]) for k in ("sort", "reorder", "pair_update", "other")}
+    stream_ms = phases["sort"] + phases["reorder"]
+    extra["phases_ms"] = phases
+    extra["streaming_phases"] = {"what": "key sort + reorder/bin tables (HBM-bound)", "algorithmic_GBps": (ALG_BYTES_STEP - ALG_BYTES_PAIR) * n_local / (stream_ms * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": (ALG_BYTES_STEP - ALG_BYTES_PAIR) * n_local / (stream_ms * 1e-3) / 1e9 / hbm_peak}
+    extra["step_hbm"] = {"algorithmic_GBps": ALG_BYTES_STEP * n_local / (ms_step * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": ALG_BYTES_STEP * n_local / (ms_step * 1e-3) / 1e9 / hbm_peak}
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = e2e_leg(solver, torch, stream, args, G, world, barrier, dist)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_run(CPU_SAMPLE_GRID, args.cpu_steps, 1)
+        cpu = {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "port",
+               "sample": f"plume {CPU_SAMPLE_GRID}^3 bins ({r['n']} particles) x {args.cpu_steps} steps = {r['seconds']:.1f} s of the CPU oracle (OpenMP over bins)",
+               "particle_steps_per_s": r["particle_steps_per_s"]}
+
+    if rank == 0:
+        line = {"metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(G, n_total, world),
+                "particle_steps_per_s": n_total / (ms_step * 1e-3), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "cpu_baseline": cpu}
+        line.update(extra)
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e_leg(solver, torch, stream, args, G, world, barrier, dist):
+    """Upload (pinned host -> device) + one step + download (device -> pinned host), every step."""
+    import ctypes as C
+    from fluidsolvergpu_b200 import FsgSoa
+    n = solver.stats()["n"]
+    shapes = {"pos": (n, 3), "vel": (n, 3), "acc": (n, 3), "dens": (n,), "press": (n,), "delpress": (n, 3), "newdens": (n,),
+              "newdelpress": (n, 3)}
+    bufs = {k: torch.empty(s, dtype=torch.float32, pin_memory=True) for k, s in shapes.items()}
+    bufs["index"] = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    bufs["boundary"] = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    soa = FsgSoa()
+    soa.n = n
+    for k, b in bufs.items():
+        setattr(soa, k, b.data_ptr())
+    solver.download_raw(soa)          # the current state now lives in host memory
+    h2d = sum(b.numel() * b.element_size() for b in bufs.values())
+    d2h = h2d
+    steps = args.e2e_steps
+
+    def one():
+        solver.upload_raw(soa)
+        solver.step(1, sync=False)
+        solver.download_raw(soa)      # synchronises
+    if world > 1:
+        return {"value": None, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "end-to-end leg runs at N=1"}
+    one()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    barrier()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": G ** 3 / dt, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": dt * 1e3, "steps": steps,
+            "what": "fsg_upload_soa(pinned host) + fsg_step(1) + fsg_download_soa(pinned host) per step, wall clock around synchronised calls"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--impl", default="fsg", choices=["fsg", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "fsg":
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        fsg_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,7 @@ SIGNATURES = {
     "fsg_export_viz": (C.c_int, [P, P, P, P]),
     "fsg_get_tables": (C.c_int, [P, P, P, P]),
     "fsg_get_stats": (C.c_int, [P, C.POINTER(FsgStats)]),
+    "fsg_set_collect_stats": (C.c_int, [P, C.c_int]),
     "fsg_set_profiling": (C.c_int, [P, C.c_int]),
     "fsg_get_phase_ms": (C.c_int, [P, C.POINTER(C.c_double * 4), C.POINTER(C.c_int64)]),
     "fsg_scene_plume": (C.c_int, [P, C.c_double, C.c_double, C.c_uint64, C.POINTER(C.c_int64)]),

@@ -570,6 +570,13 @@ extern "C" int fsg_get_stats(fsg_ctx *c, fsg_stats *out)
     return FSG_OK;
 }
 
+extern "C" int fsg_set_collect_stats(fsg_ctx *c, int on)
+{
+    if (!c) return FSG_E_INVALID;
+    c->cfg.collect_stats = on != 0;
+    return FSG_OK;
+}
+
 extern "C" int fsg_scene_plume(fsg_ctx *c, double spacing, double jitter, uint64_t seed, int64_t *n_out)
 {
     if (!c || !n_out || spacing <= 0) return FSG_E_INVALID;

@@ -152,6 +152,14 @@ class FluidSolver:
         self._check(self._lib.fsg_get_stats(self._ctx, C.byref(st)), "fsg_get_stats")
         return {k: getattr(st, k) for k, _ in FsgStats._fields_}
 
+    def pair_stats_one_step(self) -> dict:
+        """Takes ONE extra step with the pair counters on and returns that step's statistics."""
+        self._check(self._lib.fsg_set_collect_stats(self._ctx, 1), "fsg_set_collect_stats")
+        self.step(1)
+        st = self.stats()
+        self._check(self._lib.fsg_set_collect_stats(self._ctx, 0), "fsg_set_collect_stats")
+        return st
+
     def set_profiling(self, on: bool = True):
         self._check(self._lib.fsg_set_profiling(self._ctx, int(on)), "fsg_set_profiling")
 

@@ -145,6 +145,8 @@ FSG_API int  fsg_export_viz(fsg_ctx *ctx, float *spts, float *a3, float *b3);
  * cells[n] sorted keys, start/end[numcells] (FluidGPU.cu:106-117; -1 = empty bin). */
 FSG_API int  fsg_get_tables(fsg_ctx *ctx, int32_t *cells, int32_t *start, int32_t *end);
 FSG_API int  fsg_get_stats(fsg_ctx *ctx, fsg_stats *out);
+/* Switches the pair counters (fsg_config.collect_stats) on or off for the following steps. */
+FSG_API int  fsg_set_collect_stats(fsg_ctx *ctx, int on);
 /* Device-side phase timing (CUDA events on the context's stream around each phase of every step;
  * the reference prints the same kind of figure, solver.cu:175-197).  fsg_get_phase_ms synchronises,
  * returns the milliseconds accumulated since the last call — ms[0] key sort, ms[1] reorder + bin

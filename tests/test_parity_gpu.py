@@ -236,8 +236,10 @@ def test_edge_cases(fsg):
         sim.step(4)
         compare(s, sim, fsg, bit_exact_ints=False)
         # a particle that leaves the bin grid is parked, the rest keep going
-        st = fsg.scenes.default_state(np.array([[0.0, 0.0, -0.9999], [0.3, 0.3, 0.3], [0.31, 0.3, 0.3]], np.float32),
-                                      vel=np.array([[0, 0, -50.0], [0, 0, 0], [0, 0, 0]], np.float32))
+        # (it has to leave along x: the linear bin id of FluidGPU.cu:419 only goes out of range there —
+        # leaving along y or z wraps into a neighbouring row)
+        st = fsg.scenes.default_state(np.array([[-0.9999, 0.0, 0.0], [0.3, 0.3, 0.3], [0.31, 0.3, 0.3]], np.float32),
+                                      vel=np.array([[-50.0, 0, 0], [0, 0, 0], [0, 0, 0]], np.float32))
         sim = oracle_py.OracleSim(oracle_py.params_from_cfg(cfg), st)
         s.upload(st)
         s.step(6)

@@ -20,7 +20,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 from fluidsolvergpu_b200 import scenes, sections  # noqa: E402
 
 import os
-HARNESS = ROOT / "oracle" / "_ref" / os.environ.get("FSG_REF_HARNESS", "ref_harness_base")
+HARNESS = ROOT / "oracle" / "_ref" / os.environ.get("FSG_REF_HARNESS", "ref_harness_base_nodivsync")
 KEEP = ("pos", "vel", "acc", "dens", "press", "delpress", "newdens", "newdelpress", "index", "cell", "boundary",
         "cells_sorted", "start", "end", "spts", "a3", "b3")
 
