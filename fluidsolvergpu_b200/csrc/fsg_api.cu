@@ -120,7 +120,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_state(c->A);
     free_state(c->B);
-    cudaFree(c->carryA); cudaFree(c->carryB);
+    cudaFree(c->carryA); cudaFree(c->carryB); cudaFree(c->sums);
     cudaFree(c->keysA); cudaFree(c->keysB); cudaFree(c->perm); cudaFree(c->iota);
     cudaFree(c->start); cudaFree(c->end);
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
@@ -158,6 +158,7 @@ static int create_impl(fsg_ctx *c)
     if ((rc = alloc_state(c, c->B, cap)) != FSG_OK) return rc;
     CU(c, cudaMalloc(&c->carryA, sizeof(float4) * cap));
     CU(c, cudaMalloc(&c->carryB, sizeof(float4) * cap));
+    CU(c, cudaMalloc(&c->sums, sizeof(float4) * cap));
     CU(c, cudaMalloc(&c->keysA, sizeof(int) * cap));
     CU(c, cudaMalloc(&c->keysB, sizeof(int) * cap));
     CU(c, cudaMalloc(&c->perm, sizeof(int) * cap));
@@ -249,8 +250,13 @@ static int after_upload(fsg_ctx *c, int64_t n)
         c->tables_dirty = false;
     }
     c->n = n;
-    CU(c, fsg_launch_keys(c->dev, c->B.posd, c->keysB, n, c->stream));   // solver.cu:119
+    CU(c, cudaMemsetAsync(c->counters + 4, 0, sizeof(int), c->stream));
+    CU(c, fsg_launch_keys(c->dev, c->B.posd, c->keysB, n, c->counters + 4, c->stream));   // solver.cu:119
     c->launches++;
+    int flag = 0;
+    CU(c, cudaMemcpyAsync(&flag, c->counters + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->has_boundary = flag != 0;
     c->carry_live = true;
     c->steps = 0;
     return FSG_OK;

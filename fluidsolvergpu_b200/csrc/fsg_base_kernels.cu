@@ -33,18 +33,21 @@ cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s)
     return cudaGetLastError();
 }
 
-__global__ void k_keys(FsgDev d, const float4 *__restrict__ posd, int *__restrict__ keys, int64_t n)
+__global__ void k_keys(FsgDev d, const float4 *__restrict__ posd, int *__restrict__ keys, int64_t n, int *any_boundary)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool b = false;
     if (i < n) {
         float4 p = posd[i];
         keys[i] = bin_id(d, p.x, p.y, p.z);
+        b = p.w < 0.f;
     }
+    if (__any_sync(FULL, b) && (threadIdx.x & 31) == 0) atomicOr(any_boundary, 1);
 }
-cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, cudaStream_t s)
+cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, int *any_boundary, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, posd, keys, n);
+    k_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, posd, keys, n, any_boundary);
     return cudaGetLastError();
 }
 
@@ -398,8 +401,17 @@ cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binli
         cudaFuncSetAttribute(k_pair_update<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
+    // Uncapped configuration (every particle of the 27 bins is visited): the pipelined pair-sum kernel
+    // + the streaming update kernel (fsg_pair_v2.cu).  pair_fp64 == 3 keeps the fused kernel instead.
+    if (c->cfg.pair_fp64 == 0 && c->dev.cap <= 0 && c->dev.bin_cap <= 0) {
+        cudaError_t e2 = fsg_launch_pair_v2(a, c->sums, stats, c->has_boundary, c->sm_count, s);
+        if (e2 != cudaSuccess) return e2;
+        e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, s);
+        *launches += 2;
+        return e2;
+    }
     // pair_fp64: 1 = promotion-faithful double path, 2 = the same queue-everything kernel in fp32
-    // (kept as a cross-check of the fast kernel), 0 = fast fp32 kernel (fsg_pair_fast.cu)
+    // (kept as a cross-check of the fast kernel), 0 / 3 = fused fp32 kernel (fsg_pair_fast.cu)
     if (c->cfg.pair_fp64 == 1) {
         if (stats) k_pair_update<double, true><<<(unsigned)blocks, PAIR_WARPS * 32, smem, s>>>(a);
         else k_pair_update<double, false><<<(unsigned)blocks, PAIR_WARPS * 32, smem, s>>>(a);

@@ -82,3 +82,7 @@ struct PairArgs {
 
 // fsg_pair_fast.cu
 cudaError_t fsg_launch_pair_fast(const PairArgs &a, bool stats, int sm_count, cudaStream_t s);
+// fsg_pair_v2.cu
+cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool has_boundary, int sm_count, cudaStream_t s);
+cudaError_t fsg_launch_update(const FsgDev &d, int64_t n, const int *keysA, FsgState A, FsgState B, int *keysB,
+                              const float4 *sums, const float4 *carry, cudaStream_t s);

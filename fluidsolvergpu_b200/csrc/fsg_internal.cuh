@@ -56,12 +56,14 @@ struct fsg_ctx {
     FsgState A, B;      // A: sorted pre-update state of the last step; B: post-update state
     float4 *carryB, *carryA;   // accumulators carried into the first step after upload (newdens, newdelpress xyz)
     bool carry_live;
+    float4 *sums;              // pair sums of the current step (newdens, newdelpress xyz), sorted order
+    bool has_boundary;         // any Particle::boundary set in the uploaded scene
     int *keysB;         // bin ids belonging to B (order of B)
     int *keysA;         // sorted bin ids (order of A)
     int *perm, *iota;
     int *start, *end;   // dense bin tables, -1 = empty  (FluidGPU.cu:106-117)
     int *binlist[2];    // first sorted slot of every occupied bin (unordered), ping-pong
-    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live
+    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live, [4] any-boundary flag
     unsigned long long *dstats;   // [0] tested, [1] in range, [2] dropped
     void *sort_tmp;
     void *stage;        // device staging area for host<->device conversion
@@ -87,7 +89,7 @@ cudaError_t fsg_sort_pairs(void *tmp, size_t tmp_bytes, const int *keys_in, int 
 // fsg_base_kernels.cu
 cudaError_t fsg_launch_iota(int *p, int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s);
-cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, cudaStream_t s);
+cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, int *any_boundary, cudaStream_t s);
 cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const int *keysA, int *start, int *end,
                                     int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,

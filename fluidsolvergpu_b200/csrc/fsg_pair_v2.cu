@@ -1,0 +1,439 @@
+// fsg_pair_v2.cu — pair sums of the base particle step for the uncapped configuration
+// (neighbour_cap == 0 && bin_cap == 0: every particle of the 27 linear-offset bins is visited).
+//
+// Reference work it replaces: mykernel (FluidGPU.cu:119-285).  Particle::update / mykernel2
+// (FluidGPU.cuh:270-304, FluidGPU.cu:404-432) run afterwards as the streaming kernel k_update.
+//
+// Structure (DESIGN.md "Kernels"): persistent blocks of 4 consumer warps + 1 producer warp.
+//   * the PRODUCER walks a dynamic queue of occupied home bins.  Because bin id = ix*G^2 + iy*G + iz
+//     (FluidGPU.cu:419) and the particles are sorted by it, the three z-adjacent bins of every
+//     (dx,dy) column of the 27-bin neighbourhood are ONE contiguous particle run: a neighbourhood
+//     is 9 runs.  Each run is moved into shared memory with one 1-D bulk async copy
+//     (cp.async.bulk, the TMA engine) that signals an mbarrier; three stages are in flight, so the
+//     latency of gathering a neighbourhood is hidden behind the sweep of the previous ones.
+//   * the CONSUMER warps split the home particles of the bin (two per pass).  Lanes are
+//     candidates: every 32-candidate chunk is read once from shared memory and tested against both
+//     home particles; the W(r) term of the outer kernel branch (h < r <= 2h, FluidGPU.cu:15-16) is
+//     evaluated branch-free in the sweep, candidates with r <= h (the support of dW,
+//     FluidGPU.cu:35-43) are only marked in a per-lane bit mask.  After the sweep the marked
+//     candidates are compacted into a per-warp queue and processed 32 at a time with all lanes busy
+//     (pressure gradient + viscosity, FluidGPU.cu:238-279); per-particle sums come from a segmented
+//     warp scan, so the result is deterministic (no atomics, fixed order).
+//   * sums (newdens, newdelpress x/y/z) go to a float4 array that k_update consumes.
+#include "fsg_device.cuh"
+
+#define V2_CWARPS 4                     // consumer warps per block
+#define V2_THREADS ((V2_CWARPS + 1) * 32)
+#define V2_TILE 512                     // staged candidates per stage
+#define V2_NST 3                        // pipeline stages
+#define V2_QCAP 160                     // near-pair queue entries per warp (drained at >= 32)
+#define V2_GROUP 32                     // home particles per item
+#define V2_BINS_PER_GRAB 4
+
+struct V2Stage {
+    float4 sp[V2_TILE];                 // candidate (x, y, z, +-dens)
+    int sj[V2_TILE];                    // global slot of the candidate
+    float4 hp[V2_GROUP];                // home particles of the group
+    int hs, gcount, ct, first, last, pad0, pad1, pad2;
+};
+struct V2Warp {
+    unsigned q[V2_QCAP];
+    float4 acc[8];                      // the warp's home particles of the group: dens, delpress x/y/z
+};
+struct V2Smem {
+    V2Stage st[V2_NST];
+    V2Warp w[V2_CWARPS];
+    unsigned long long full[V2_NST], empty[V2_NST];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok = 0;
+    const unsigned addr = smem_u32(bar);
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float rsqrt_fast(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// pressure / viscosity / inner-W terms of one r <= h pair (FluidGPU.cu:238-279)
+__device__ __forceinline__ float4 v2_near_pair(const FsgDev &d, const float4 &pi, const float4 &vi, const float4 &pj,
+                                               const float4 &vj)
+{
+    float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+    float d2 = dist2(rx, ry, rz);
+    float ds = sqrtf(d2);
+    float densi = fabsf(pi.w), densj = fabsf(pj.w);
+    bool bi = pi.w < 0.f, bj = pj.w < 0.f;
+    float q = ds * d.inv_h;
+    float w = d.w_c * (1.f - 1.5f * q * q + 0.75f * q * q * q);                // FluidGPU.cu:13
+    float t = d.hf - ds;
+    float dwv = d.dw_c * t * t;                                                // FluidGPU.cu:37 (0 at r == h)
+    float g = dwv / ds;
+    float vabx = vi.x - vj.x, vaby = vi.y - vj.y, vabz = vi.z - vj.z;
+    float dd = vabx * rx + vaby * ry + vabz * rz;                              // :253
+    float s = 0.f;
+    if (dd < 0.f) {                                                            // :255
+        float mu = dd / (ds * ds + d.eps);
+        float hm = d.hf * mu;
+        float bf = (!bi && bj) ? 1.f + (float)d.alpha_boundary : 1.f;
+        s = d.visc_c * (hm + d.visc_q * hm * hm) / ((densi + densj) * 0.5f) * bf;
+    }
+    float pp = vj.w / (densj * densj) + vi.w / (densi * densi) + s;            // :258-260
+    float pg = pp * g;
+    return make_float4(w * ((!bi && bj) ? 2.5f : 1.f), pg * rx, pg * ry, pg * rz);
+}
+
+struct V2Args {
+    PairArgs a;
+    float4 *sums;       // [n] newdens, newdelpress x, y, z
+};
+
+// one batch of <= 32 queued near pairs: lanes = pairs, segmented scan keyed by the home slot
+__device__ __forceinline__ void v2_drain_batch(const FsgDev &d, const V2Stage &S, V2Warp &W, const float4 *__restrict__ velp,
+                                               int qh, int qn, int lane, int warp)
+{
+    const int e = qh + lane;
+    const bool valid = e < qn;
+    int key = -1 - lane;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        unsigned ent = W.q[e];
+        key = (int)(ent >> 16);                                   // slot within the warp: pass * 2 + which
+        int c = (int)(ent & 0xffffu);
+        int k = 8 * (key >> 1) + 2 * warp + (key & 1);            // home particle within the group
+        int i = S.hs + k, j = S.sj[c];
+        v = v2_near_pair(d, S.hp[k], velp[i], S.sp[c], velp[j]);
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int ku = __shfl_up_sync(FULL, key, o);
+        float x0 = __shfl_up_sync(FULL, v.x, o), x1 = __shfl_up_sync(FULL, v.y, o);
+        float x2 = __shfl_up_sync(FULL, v.z, o), x3 = __shfl_up_sync(FULL, v.w, o);
+        if (lane >= o && ku == key) { v.x += x0; v.y += x1; v.z += x2; v.w += x3; }
+    }
+    int kn = __shfl_down_sync(FULL, key, 1);
+    if (valid && (lane == 31 || kn != key)) {
+        float4 c4 = W.acc[key];
+        c4.x += v.x; c4.y += v.y; c4.z += v.z; c4.w += v.w;
+        W.acc[key] = c4;
+    }
+    __syncwarp();
+}
+
+template <bool STATS, bool HASB>
+__global__ void __launch_bounds__(V2_THREADS, 5)
+k_pair_v2(V2Args va)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    V2Smem &SM = *reinterpret_cast<V2Smem *>(s_raw);
+    const PairArgs &a = va.a;
+    const FsgDev &d = a.d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nocc = *a.nocc;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < V2_NST; s++) {
+            mbar_init(&SM.full[s], 1);
+            mbar_init(&SM.empty[s], V2_CWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == V2_CWARPS) {
+        // =========================== producer ===========================
+        int it = 0;
+        int grab = 0, grab_end = 0;
+        for (;;) {
+            if (grab >= grab_end) {
+                int m = 0;
+                if (lane == 0) m = atomicAdd(a.work, V2_BINS_PER_GRAB);
+                grab = __shfl_sync(FULL, m, 0);
+                grab_end = min(grab + V2_BINS_PER_GRAB, nocc);
+            }
+            if (grab >= nocc) {
+                const int stage = it % V2_NST;
+                mbar_wait(&SM.empty[stage], ((it / V2_NST) & 1) ^ 1);
+                if (lane == 0) {
+                    SM.st[stage].gcount = -1;
+                    mbar_arrive(&SM.full[stage]);
+                }
+                break;
+            }
+            const int first = a.binlist[grab++];
+            const int b = a.keysA[first];
+            // runs: lane r < 9 owns column (dx, dy) = (r / 3 - 1, r % 3 - 1), bins c0 - 1 .. c0 + 1
+            int rs = 0, rp = 0;
+            if (lane < 9) {
+                const int c0 = b + (lane / 3 - 1) * d.G2 + (lane % 3 - 1) * d.G;
+                int s = -1, e = -1;
+#pragma unroll
+                for (int dz = -1; dz <= 1; dz++) {
+                    int c = c0 + dz;
+                    if (c >= 0 && c < d.numcells) {
+                        int s0 = a.start[c];
+                        if (s0 >= 0) {
+                            if (s < 0) s = s0;
+                            e = a.end[c];
+                        }
+                    }
+                }
+                if (s >= 0) { rs = s; rp = e - s + 1; }
+            }
+            int incl = rp;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int excl = incl - rp;
+            const int C = __shfl_sync(FULL, incl, 8);
+            const int hs = a.start[b], hn = a.end[b] - hs + 1;
+            for (int ig = 0; ig < hn; ig += V2_GROUP) {
+                const int gcount = min(V2_GROUP, hn - ig);
+                for (int t0 = 0; t0 < C; t0 += V2_TILE) {
+                    const int ct = min(V2_TILE, C - t0);
+                    const int stage = it % V2_NST;
+                    V2Stage &S = SM.st[stage];
+                    mbar_wait(&SM.empty[stage], ((it / V2_NST) & 1) ^ 1);
+                    // candidate slots + padding + header (generic-proxy writes, published by the arrive below)
+#pragma unroll 1
+                    for (int r = 0; r < 9; r++) {
+                        int pr = __shfl_sync(FULL, rp, r);
+                        if (pr == 0) continue;
+                        int ex = __shfl_sync(FULL, excl, r), sr = __shfl_sync(FULL, rs, r);
+                        int lo = max(ex, t0), hi = min(ex + pr, t0 + ct);
+                        for (int k = lo + lane; k < hi; k += 32) S.sj[k - t0] = sr + (k - ex);
+                    }
+                    const int cpad = (ct + 31) & ~31;
+                    if (ct + lane < cpad) S.sp[ct + lane] = make_float4(1e30f, 1e30f, 1e30f, 0.f);
+                    if (lane == 0) {
+                        S.hs = hs + ig;
+                        S.gcount = gcount;
+                        S.ct = ct;
+                        S.first = (t0 == 0);
+                        S.last = (t0 + V2_TILE >= C);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_expect_tx(&SM.full[stage], (unsigned)(ct + gcount) * 16u);
+                    __syncwarp();
+                    if (lane < 9 && rp > 0) {
+                        int lo = max(excl, t0), hi = min(excl + rp, t0 + ct);
+                        if (hi > lo) bulk_g2s(&S.sp[lo - t0], a.A.posd + rs + (lo - excl), (unsigned)(hi - lo) * 16u, &SM.full[stage]);
+                    }
+                    if (lane == 9) bulk_g2s(&S.hp[0], a.A.posd + hs + ig, (unsigned)gcount * 16u, &SM.full[stage]);
+                    it++;
+                }
+            }
+        }
+        return;
+    }
+
+    // =========================== consumers ===========================
+    V2Warp &W = SM.w[warp];
+    const unsigned d2max_bits = __float_as_uint(d.d2_max), d2h_bits = __float_as_uint(d.d2_h);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float w_outer = d.w_c * 0.25f;
+    const float inv_h = d.inv_h;
+    unsigned long long st_tested = 0, st_in = 0;
+
+    for (int it = 0;; it++) {
+        const int stage = it % V2_NST;
+        V2Stage &S = SM.st[stage];
+        mbar_wait(&SM.full[stage], (it / V2_NST) & 1);
+        const int gcount = S.gcount;
+        if (gcount < 0) break;
+        const int ct = S.ct;
+        const int cpad = (ct + 31) & ~31;
+        if (S.first && lane < 8) W.acc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        int qn = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 4; pass++) {
+            const int k0 = 8 * pass + 2 * warp;
+            if (k0 >= gcount) break;
+            const bool has1 = k0 + 1 < gcount;
+            const float4 pi0 = S.hp[k0];
+            float4 pi1 = S.hp[has1 ? k0 + 1 : k0];
+            if (!has1) pi1.x = -1e30f;                               // nothing is in range of it
+            const float ci0 = pi0.w < 0.f ? 0.f : 1.5f;              // float(!b_i)*BDENSFACTOR, FluidGPU.cu:276
+            const float ci1 = pi1.w < 0.f ? 0.f : 1.5f;
+            float w0 = 0.f, w1 = 0.f;
+            unsigned m0 = 0, m1 = 0, bit = 1;
+            int nin = 0;
+#pragma unroll 2
+            for (int c0 = 0; c0 < cpad; c0 += 32, bit <<= 1) {
+                const float4 pj = S.sp[c0 + lane];
+                float bjf = 0.f;
+                if (HASB) bjf = pj.w < 0.f ? 1.f : 0.f;
+                {
+                    float rx = pi0.x - pj.x, ry = pi0.y - pj.y, rz = pi0.z - pj.z;
+                    float d2 = STATS ? dist2(rx, ry, rz) : fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+                    unsigned u = __float_as_uint(d2) - 1u;       // 0 < d2 <= thr  <=>  bits(d2) - 1 < bits(thr)
+                    bool inr = u < d2max_bits;                   // FluidGPU.cu:236
+                    bool nearp = u < d2h_bits;                   // r <= h
+                    float inv = rsqrt_fast(d2);
+                    float tt = fmaf(-d2 * inv, inv_h, 2.f);      // 2 - r/h
+                    float t3 = tt * tt * tt;
+                    if (HASB) t3 *= fmaf(ci0, bjf, 1.f);
+                    if (inr && !nearp) w0 += t3;
+                    if (nearp) m0 |= bit;
+                    if (STATS) nin += __popc(__ballot_sync(FULL, inr));
+                }
+                {
+                    float rx = pi1.x - pj.x, ry = pi1.y - pj.y, rz = pi1.z - pj.z;
+                    float d2 = STATS ? dist2(rx, ry, rz) : fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+                    unsigned u = __float_as_uint(d2) - 1u;
+                    bool inr = u < d2max_bits;
+                    bool nearp = u < d2h_bits;
+                    float inv = rsqrt_fast(d2);
+                    float tt = fmaf(-d2 * inv, inv_h, 2.f);
+                    float t3 = tt * tt * tt;
+                    if (HASB) t3 *= fmaf(ci1, bjf, 1.f);
+                    if (inr && !nearp) w1 += t3;
+                    if (nearp) m1 |= bit;
+                    if (STATS) nin += __popc(__ballot_sync(FULL, inr));
+                }
+            }
+            if (STATS && lane == 0) { st_tested += (unsigned long long)ct * (has1 ? 2 : 1); st_in += nin; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                w0 += __shfl_xor_sync(FULL, w0, o);
+                w1 += __shfl_xor_sync(FULL, w1, o);
+            }
+            if (lane < 2) W.acc[2 * pass + lane].x += (lane ? w1 : w0) * w_outer;
+            // ---- compact the marked near candidates into the queue ----
+#pragma unroll
+            for (int which = 0; which < 2; which++) {
+                unsigned m = which ? m1 : m0;
+                const unsigned tag = (unsigned)(2 * pass + which) << 16;
+                for (;;) {
+                    unsigned any = __ballot_sync(FULL, m != 0);
+                    if (!any) break;
+                    if (m) {
+                        int c = (__ffs(m) - 1) * 32 + lane;
+                        W.q[qn + __popc(any & lt_mask)] = tag | (unsigned)c;
+                        m &= m - 1;
+                    }
+                    qn += __popc(any);
+                    __syncwarp();
+                    if (qn >= V2_QCAP - 32) {                      // keep room for one more round
+                        int qh = 0;
+                        while (qn - qh >= 32) { v2_drain_batch(d, S, W, a.A.velp, qh, qn, lane, warp); qh += 32; }
+                        int left = qn - qh;
+                        unsigned ent = 0;
+                        if (lane < left) ent = W.q[qh + lane];
+                        __syncwarp();
+                        if (lane < left) W.q[lane] = ent;
+                        qn = left;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        // ---- drain the queue (entries refer to this stage's candidates) ----
+        __syncwarp();
+        for (int qh = 0; qh < qn; qh += 32) v2_drain_batch(d, S, W, a.A.velp, qh, qn, lane, warp);
+        const int last = S.last, hs = S.hs;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&SM.empty[stage]);
+        if (last && lane < 8) {
+            int k = 8 * (lane >> 1) + 2 * warp + (lane & 1);
+            if (k < gcount) va.sums[hs + k] = W.acc[lane];
+        }
+        __syncwarp();
+    }
+    if (STATS && lane == 0) {
+        atomicAdd(a.stats + 0, st_tested);
+        atomicAdd(a.stats + 1, st_in);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_update — Particle::update + the tail of mykernel2 (FluidGPU.cuh:270-304, FluidGPU.cu:419-425)
+// for every sorted slot: sums (+ accumulators carried in from the upload) -> EOS, integration, new
+// bin id.  Streaming: reads 64 + 16 B, writes 64 + 4 B per particle.  Particles parked outside the
+// bin grid (key == numcells) are copied through unchanged.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B, int *__restrict__ keysB,
+         const float4 *__restrict__ sums, const float4 *__restrict__ carry)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 pd = A.posd[i], vp = A.velp[i], af = A.accf[i], dpi = A.dpi[i];
+    int key = keysA[i];
+    if (key < d.numcells) {
+        float4 s = sums[i];
+        if (carry) { float4 cy = carry[i]; s.x += cy.x; s.y += cy.y; s.z += cy.z; s.w += cy.w; }
+        particle_update(d, pd, vp, af, dpi, s.x, s.y, s.z, s.w, key);
+    }
+    B.posd[i] = pd;
+    B.velp[i] = vp;
+    B.accf[i] = af;
+    B.dpi[i] = dpi;
+    keysB[i] = key;
+}
+
+cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool has_boundary, int sm_count, cudaStream_t s)
+{
+    static bool attr_done = false;
+    const int smem = (int)sizeof(V2Smem);
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_pair_v2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_done = true;
+    }
+    V2Args va;
+    va.a = a;
+    va.sums = sums;
+    int64_t blocks = ((int64_t)a.n + 7) / 8;
+    int64_t maxb = (int64_t)sm_count * 5;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    if (stats) {
+        if (has_boundary) k_pair_v2<true, true><<<(unsigned)blocks, V2_THREADS, smem, s>>>(va);
+        else k_pair_v2<true, false><<<(unsigned)blocks, V2_THREADS, smem, s>>>(va);
+    } else {
+        if (has_boundary) k_pair_v2<false, true><<<(unsigned)blocks, V2_THREADS, smem, s>>>(va);
+        else k_pair_v2<false, false><<<(unsigned)blocks, V2_THREADS, smem, s>>>(va);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t fsg_launch_update(const FsgDev &d, int64_t n, const int *keysA, FsgState A, FsgState B, int *keysB,
+                              const float4 *sums, const float4 *carry, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_update<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, (int)n, keysA, A, B, keysB, sums, carry);
+    return cudaGetLastError();
+}

@@ -194,6 +194,24 @@ def test_uncapped_plume_small(fsg):
             print("plume24 step", k + 1, errs)
 
 
+@pytest.mark.parametrize("stats", [0, 1])
+@pytest.mark.parametrize("boundary_frac", [0.0, 0.2])
+def test_uncapped_random_scene(fsg, stats, boundary_frac):
+    """Uncapped configuration (pipelined pair kernel + streaming update) on a jittered lattice with
+    random velocities and boundary particles; with the pair counters (exact distance arithmetic) and
+    without them (production arithmetic)."""
+    state = fsg.scenes.random_base_scene(6000, 21, box=((-0.4, 0.4),) * 3, spacing=0.05, jitter=0.012, boundary_frac=boundary_frac)
+    cfg = fsg.scenes.plume_config(17)
+    cfg.origin = -1.02
+    cfg.capacity = state["pos"].shape[0]
+    cfg.collect_stats = stats
+    with fsg.FluidSolver(cfg) as s:
+        s.upload(state)
+        for k in range(3):
+            errs = resync_step(fsg, s)
+            print("uncapped random", stats, boundary_frac, k + 1, errs)
+
+
 def test_large_bins_and_many_tiles(fsg):
     """Bins far above 32 particles and neighbourhoods above one staging tile (512): exercises the
     home-particle groups and the candidate tiling of the pair kernel."""

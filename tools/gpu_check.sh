@@ -14,6 +14,6 @@ CMD="python bench.py --grid 256 --steps 2 --warmup 3 --no-cpu --e2e-steps 1"
 $CMD > $O/plain_$TAG.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_list_$TAG.log 2>&1
 echo "ncu list rc=$?"
 CMD2="python tools/quick_bench.py 128"
-$CMD2 > $O/plain2_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_pair_update -s 4 -c 2 -f -o $O/prof_pair_$TAG $CMD2 > $O/ncu_full_$TAG.log 2>&1
+$CMD2 > $O/plain2_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_pair_v2 -s 4 -c 2 -f -o $O/prof_pair_$TAG $CMD2 > $O/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
 fi
