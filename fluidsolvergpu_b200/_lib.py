@@ -21,7 +21,8 @@ class FsgConfig(C.Structure):
         ("dt", C.c_double), ("gravity", C.c_double), ("sound", C.c_double), ("alpha_fluid", C.c_double),
         ("alpha_boundary", C.c_double), ("neighbour_cap", C.c_int32), ("bin_cap", C.c_int32), ("capacity", C.c_int64),
         ("device", C.c_int32), ("pair_fp64", C.c_int32), ("collect_stats", C.c_int32), ("rank", C.c_int32),
-        ("world", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("world", C.c_int32), ("slab_x0", C.c_int32), ("slab_x1", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -64,7 +65,11 @@ SIGNATURES = {
     "fsg_scene_plume": (C.c_int, [P, C.c_double, C.c_double, C.c_uint64, C.POINTER(C.c_int64)]),
     "fsg_scene_plume_host": (C.c_int, [C.POINTER(FsgConfig), C.c_double, C.c_double, C.c_uint64, P, P, C.c_int64,
                                        C.POINTER(C.c_int64)]),
+    "fsg_scene_plume_hist": (C.c_int, [C.POINTER(FsgConfig), C.c_double, P]),
     "fsg_device_ptr": (C.c_int, [P, C.c_int, C.POINTER(P)]),
+    "fsg_slab_pack": (C.c_int, [P, P, P, C.c_int64, C.POINTER(C.c_int64 * 5)]),
+    "fsg_slab_unpack": (C.c_int, [P, P, C.c_int64, C.c_int64, P, C.c_int64, C.c_int64]),
+    "fsg_slab_message_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
     "fsg_stage_sort": (C.c_int, [P, P, P, C.c_int64]),
     "fsg_stage_findneighbours": (C.c_int, [P, P, P, P, C.c_int64]),
     "fsg_stage_mykernel": (C.c_int, [P, P, P, P, P, C.c_int64]),

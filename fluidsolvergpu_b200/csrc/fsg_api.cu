@@ -31,6 +31,9 @@ void fsg_derive_constants(const fsg_config &cfg, FsgDev &d)
     d.G = cfg.grid;
     d.G2 = cfg.grid * cfg.grid;
     d.numcells = cfg.grid * cfg.grid * cfg.grid;
+    d.x0 = cfg.world > 1 ? cfg.slab_x0 : 0;
+    d.x1 = cfg.world > 1 ? cfg.slab_x1 : cfg.grid;
+    d.dead = d.numcells + 1;
     d.cap = cfg.neighbour_cap;
     d.bin_cap = cfg.bin_cap;
     d.origin = cfg.origin;
@@ -125,6 +128,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     cudaFree(c->start); cudaFree(c->end);
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
     cudaFree(c->counters); cudaFree(c->dstats); cudaFree(c->sort_tmp);
+    cudaFree(c->slab_cnt); cudaFree(c->scan_tmp);
     cudaFree(c->stage);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
@@ -178,7 +182,7 @@ static int create_impl(fsg_ctx *c)
     CU(c, fsg_launch_fill(c->end, -1, nc, c->stream));
     c->launches += 3;
     c->sort_bits = 1;
-    while ((1ll << c->sort_bits) <= nc) c->sort_bits++;      // keys are in [0, numcells]
+    while ((1ll << c->sort_bits) <= nc + 1) c->sort_bits++;  // keys are in [0, numcells + 1] (parked, dead)
     c->sort_tmp_bytes = fsg_sort_temp_bytes(cap, c->sort_bits);
     CU(c, cudaMalloc(&c->sort_tmp, c->sort_tmp_bytes ? c->sort_tmp_bytes : 16));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -193,6 +197,16 @@ extern "C" int fsg_create(const fsg_config *cfg, fsg_ctx **out)
         cfg->capacity > 2000000000ll || (cfg->model != FSG_MODEL_BASE && cfg->model != FSG_MODEL_UNIDYN)) {
         g_create_err = "fsg_create: invalid configuration";
         return FSG_E_INVALID;
+    }
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world ||
+        (cfg->world > 1 && (cfg->slab_x0 < 0 || cfg->slab_x1 > cfg->grid || cfg->slab_x1 - cfg->slab_x0 < 2))) {
+        g_create_err = "fsg_create: invalid slab configuration (rank/world; a slab needs at least 2 bin layers)";
+        return FSG_E_INVALID;
+    }
+    if (cfg->world > 1 && (cfg->neighbour_cap != 0 || cfg->bin_cap != 0 || cfg->pair_fp64 != 0)) {
+        g_create_err = "fsg_create: slab decomposition needs the uncapped configuration (neighbour_cap = bin_cap = 0) "
+                       "and a one-layer ghost band, i.e. cellsize >= 2h";
+        return FSG_E_UNSUPPORTED;
     }
     if (cfg->model == FSG_MODEL_UNIDYN) {
         g_create_err = "fsg_create: the unidyn model is not available through the context API yet";
@@ -245,13 +259,15 @@ static int after_upload(fsg_ctx *c, int64_t n)
 {
     // the bin tables may hold the entries of a previous run
     if (c->tables_dirty) {
-        CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, c->n, c->stream));
+        if (c->cfg.world > 1) CU(c, fsg_launch_reset_tables_keys(c->dev, c->keysA, c->start, c->end, c->n_sorted, c->stream));
+        else CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, c->n, c->stream));
         c->launches++;
         c->tables_dirty = false;
     }
     c->n = n;
     CU(c, cudaMemsetAsync(c->counters + 4, 0, sizeof(int), c->stream));
-    CU(c, fsg_launch_keys(c->dev, c->B.posd, c->keysB, n, c->counters + 4, c->stream));   // solver.cu:119
+    CU(c, cudaMemsetAsync(c->counters + 6, 0, sizeof(int), c->stream));
+    CU(c, fsg_launch_keys(c->dev, c->B.posd, c->keysB, n, c->counters + 4, c->cfg.world > 1, c->stream));   // solver.cu:119
     c->launches++;
     int flag = 0;
     CU(c, cudaMemcpyAsync(&flag, c->counters + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -489,18 +505,24 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
 {
     if (!c || nsteps < 0) return FSG_E_INVALID;
     CU(c, cudaSetDevice(c->device));
+    if (c->cfg.world > 1 && nsteps > 1) {
+        c->err = "fsg_step: a slab context advances one step per pack / exchange / unpack round";
+        return FSG_E_STATE;
+    }
     const int64_t n = c->n;
     if (n <= 0) { c->steps += nsteps; return FSG_OK; }
     for (int t = 0; t < nsteps; t++) {
         const bool prof = c->profiling && c->ev_used.size() < 5 * 4096;
         if (prof) prof_mark(c);
         if (c->tables_dirty) {
-            CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, n, c->stream));
+            if (c->cfg.world > 1) CU(c, fsg_launch_reset_tables_keys(c->dev, c->keysA, c->start, c->end, c->n_sorted, c->stream));
+            else CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, n, c->stream));
             c->launches++;
         }
         const int nxt = c->cur ^ 1;
         CU(c, cudaMemsetAsync(c->counters + nxt, 0, sizeof(int), c->stream));
         CU(c, cudaMemsetAsync(c->counters + 2, 0, 2 * sizeof(int), c->stream));
+        CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(int), c->stream));
         if (c->cfg.collect_stats) CU(c, cudaMemsetAsync(c->dstats, 0, 4 * sizeof(unsigned long long), c->stream));
         if (prof) prof_mark(c);
         // thrust::sort_by_key, key half (solver.cu:181)
@@ -508,7 +530,8 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         if (prof) prof_mark(c);
         // value half + findneighbours (solver.cu:181-182)
         CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA,
-                                 c->start, c->end, c->binlist[nxt], c->counters + nxt, c->counters + 3, c->stream));
+                                 c->start, c->end, c->binlist[nxt], c->counters + nxt, c->counters + 3, c->counters + 5, c->stream));
+        c->n_sorted = n;
         c->launches++;
         if (prof) prof_mark(c);
         // mykernel + mykernel2 (solver.cu:187,198)

@@ -33,21 +33,50 @@ cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s)
     return cudaGetLastError();
 }
 
-__global__ void k_keys(FsgDev d, const float4 *__restrict__ posd, int *__restrict__ keys, int64_t n, int *any_boundary)
+// slab_filter: a freshly uploaded particle that lies outside this context's slab is not this context's
+// (every rank is handed the same scene): its slot is marked dead and disappears at the next sort.
+__global__ void k_keys(FsgDev d, const float4 *__restrict__ posd, int *__restrict__ keys, int64_t n, int *any_boundary,
+                       bool slab_filter)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool b = false;
     if (i < n) {
         float4 p = posd[i];
-        keys[i] = bin_id(d, p.x, p.y, p.z);
-        b = p.w < 0.f;
+        int key = bin_id(d, p.x, p.y, p.z);
+        if (slab_filter) {
+            int ix = key / d.G2;
+            if (key >= d.numcells) key = (d.x1 == d.G) ? key : d.dead;     // parked particles stay with the last slab
+            else if (ix < d.x0 || ix >= d.x1) key = d.dead;
+        }
+        keys[i] = key;
+        b = p.w < 0.f;      // (slab contexts: any boundary particle of the scene may arrive later as a ghost)
     }
     if (__any_sync(FULL, b) && (threadIdx.x & 31) == 0) atomicOr(any_boundary, 1);
 }
-cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, int *any_boundary, cudaStream_t s)
+cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, int *any_boundary, bool slab_filter,
+                            cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, posd, keys, n, any_boundary);
+    k_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, posd, keys, n, any_boundary, slab_filter);
+    return cudaGetLastError();
+}
+
+// the same reset driven by the sorted key array (slab contexts: ghost bins have table entries but
+// are not in the home-bin list)
+__global__ void k_reset_tables_keys(int numcells, const int *__restrict__ keysA, int *start, int *end, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int key = keysA[i];
+    if (key < numcells && (i == 0 || keysA[i - 1] != key)) {
+        start[key] = -1;
+        end[key] = -1;
+    }
+}
+cudaError_t fsg_launch_reset_tables_keys(const FsgDev &d, const int *keysA, int *start, int *end, int64_t n, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_reset_tables_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d.numcells, keysA, start, end, n);
     return cudaGetLastError();
 }
 
@@ -60,7 +89,7 @@ __global__ void k_reset_tables(const int *__restrict__ binlist, const int *__res
     int stride = gridDim.x * blockDim.x;
     int cnt = *nocc;
     for (; m < cnt; m += stride) {
-        int b = keysA[binlist[m]];
+        int b = binlist[m];
         start[b] = -1;
         end[b] = -1;
     }
@@ -81,10 +110,11 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
 // bins that k_pair_update walks.  Streaming, HBM-bound: 4+4 B keys/perm + 64 B in + 64 B out.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_reorder(int numcells, int64_t n, const int *__restrict__ perm, const int *__restrict__ keysA, FsgState src,
+k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restrict__ keysA, FsgState src,
           FsgState dst, const float4 *__restrict__ carry_src, float4 *__restrict__ carry_dst, int *start, int *end,
-          int *binlist, int *nocc, int *nlive)
+          int *binlist, int *nocc, int *nlive, int *nkeep)
 {
+    const int numcells = d.numcells;
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool head = false;
     if (k < n) {
@@ -96,34 +126,42 @@ k_reorder(int numcells, int64_t n, const int *__restrict__ perm, const int *__re
         dst.accf[k] = c;
         dst.dpi[k] = e;
         if (carry_src) carry_dst[k] = carry_src[sidx];
+        int next = k + 1 < n ? keysA[k + 1] : d.dead;
         if (key < numcells) {
             int prev = k > 0 ? keysA[k - 1] : -1;
-            int next = k + 1 < n ? keysA[k + 1] : numcells;
             if (key != prev) {
                 start[key] = (int)k;
-                head = true;
+                int ix = key / d.G2;
+                head = ix >= d.x0 && ix < d.x1;       // home bins: the ones this slab owns
             }
             if (key != next) end[key] = (int)k;
             if (next >= numcells) *nlive = (int)k + 1;
         }
+        if (key <= numcells && next > numcells) *nkeep = (int)k + 1;   // live + parked; dead slots are trimmed
     }
-    // warp-aggregated append of bin heads
-    unsigned m = __ballot_sync(FULL, head);
-    if (m) {
-        int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(nocc, __popc(m));
-        base = __shfl_sync(FULL, base, __ffs(m) - 1);
-        if (head) binlist[base + __popc(m & ((1u << lane) - 1))] = (int)k;
+    // block-aggregated append of the home-bin heads: ONE atomic per block (a per-warp atomic on the
+    // single counter serialises in L2 and was the bottleneck of this kernel)
+    __shared__ int s_cnt[8], s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(FULL, head);
+    if (lane == 0) s_cnt[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(nocc, tot) : 0;
     }
+    __syncthreads();
+    if (head) binlist[s_base + s_cnt[warp] + __popc(m & ((1u << lane) - 1))] = keysA[k];
 }
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *nlive, cudaStream_t s)
+                               int *binlist, int *nocc, int *nlive, int *nkeep, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_reorder<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d.numcells, n, perm, keysA, src, dst, carry_src, carry_dst,
-                                                          start, end, binlist, nocc, nlive);
+    k_reorder<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst,
+                                                          start, end, binlist, nocc, nlive, nkeep);
     return cudaGetLastError();
 }
 
@@ -224,8 +262,7 @@ k_pair_update(PairArgs a)
         if (lane == 0) m = atomicAdd(a.work, 1);
         m = __shfl_sync(FULL, m, 0);
         if (m >= nocc) break;
-        const int first = a.binlist[m];
-        const int b = a.keysA[first];
+        const int b = a.binlist[m];
 
         // ---- phase 1: neighbour-bin populations ----
         int p = 0, st = 0;

@@ -15,6 +15,8 @@
 // ---------------------------------------------------------------------------------------------
 struct FsgDev {
     int G, G2, numcells;
+    int x0, x1;      // bin layers this context owns (0, G without slab decomposition)
+    int dead;        // key of a slot that no longer holds a particle of this slab (sorts last, is trimmed)
     int cap, bin_cap;
     float origin;
     double cellsize, h, dt, gravity, sound, alpha_fluid, alpha_boundary;
@@ -52,7 +54,8 @@ struct fsg_ctx {
     std::string err;
 
     int64_t cap;        // particle capacity
-    int64_t n;          // particles held
+    int64_t n;          // particle slots in use (slab contexts: may include dead slots until the next sort)
+    int64_t n_sorted;   // length of the key array the bin tables were built from
     FsgState A, B;      // A: sorted pre-update state of the last step; B: post-update state
     float4 *carryB, *carryA;   // accumulators carried into the first step after upload (newdens, newdelpress xyz)
     bool carry_live;
@@ -62,9 +65,13 @@ struct fsg_ctx {
     int *keysA;         // sorted bin ids (order of A)
     int *perm, *iota;
     int *start, *end;   // dense bin tables, -1 = empty  (FluidGPU.cu:106-117)
-    int *binlist[2];    // first sorted slot of every occupied bin (unordered), ping-pong
-    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live, [4] any-boundary flag
+    int *binlist[2];    // ids of the occupied home bins (unordered), ping-pong
+    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live, [4] any-boundary flag, [5] n_keep
     unsigned long long *dstats;   // [0] tested, [1] in range, [2] dropped
+    int *slab_cnt;      // slab pack: per-warp counts of the 4 message categories, then their exclusive scan
+    void *scan_tmp;
+    size_t scan_tmp_bytes;
+    int64_t slab_warps;
     void *sort_tmp;
     void *stage;        // device staging area for host<->device conversion
     size_t stage_bytes;
@@ -89,12 +96,17 @@ cudaError_t fsg_sort_pairs(void *tmp, size_t tmp_bytes, const int *keys_in, int 
 // fsg_base_kernels.cu
 cudaError_t fsg_launch_iota(int *p, int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s);
-cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, int *any_boundary, cudaStream_t s);
+cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, int *any_boundary, bool slab_filter,
+                            cudaStream_t s);
+cudaError_t fsg_launch_reset_tables_keys(const FsgDev &d, const int *keysA, int *start, int *end, int64_t n, cudaStream_t s);
+// fsg_slab.cu
+size_t fsg_scan_temp_bytes(int64_t n);
+cudaError_t fsg_scan_exclusive(void *tmp, size_t tmp_bytes, const int *in, int *out, int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const int *keysA, int *start, int *end,
                                     int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *nlive, cudaStream_t s);
+                               int *binlist, int *nocc, int *nlive, int *nkeep, cudaStream_t s);
 cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work,
                                    const float4 *carry, int *launches, cudaStream_t s);
 cudaError_t fsg_launch_unpack_aos(int model, const unsigned char *aos, int64_t n, FsgState st, float4 *carry,

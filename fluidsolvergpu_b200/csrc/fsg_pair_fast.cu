@@ -79,8 +79,7 @@ k_pair_update_fast(PairArgs a)
         if (lane == 0) m = atomicAdd(a.work, 1);
         m = __shfl_sync(FULL, m, 0);
         if (m >= nocc) break;
-        const int first = a.binlist[m];
-        const int b = a.keysA[first];
+        const int b = a.binlist[m];
 
         // ---- neighbour-bin populations (FluidGPU.cu:150-183) ----
         int p = 0, st = 0;

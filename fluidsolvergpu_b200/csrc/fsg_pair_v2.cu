@@ -28,12 +28,14 @@
 #define V2_NST 3                        // pipeline stages
 #define V2_QCAP 160                     // near-pair queue entries per warp (drained at >= 32)
 #define V2_GROUP 32                     // home particles per item
-#define V2_BINS_PER_GRAB 4
+#define V2_BINS_PER_GRAB 16
+#define V2_BLOCKS_PER_SM 6
 
 struct V2Stage {
     float4 sp[V2_TILE];                 // candidate (x, y, z, +-dens)
-    int sj[V2_TILE];                    // global slot of the candidate
     float4 hp[V2_GROUP];                // home particles of the group
+    int run_lo[12];                     // first tile slot of each staged run (V2_TILE where unused) ...
+    int run_j[12];                      // ... and the global slot that tile slot holds
     int hs, gcount, ct, first, last, pad0, pad1, pad2;
 };
 struct V2Warp {
@@ -43,7 +45,7 @@ struct V2Warp {
 struct V2Smem {
     V2Stage st[V2_NST];
     V2Warp w[V2_CWARPS];
-    unsigned long long full[V2_NST], empty[V2_NST];
+    unsigned long long full[V2_NST];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -59,15 +61,34 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, u
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the hint (ns) elapses, so the
+// loop below is not a busy spin
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
     unsigned ok = 0;
     const unsigned addr = smem_u32(bar);
     do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
     } while (!ok);
 }
+// "stage is free again" goes through hardware named barriers (ids 1..V2_NST): the consumer warps
+// arrive without blocking, the producer warp blocks in bar.sync — no polling, no issue slots taken
+// from the consumers while the producer is stages ahead.
+__device__ __forceinline__ void stage_free_arrive(int stage)
+{
+    // constant barrier ids, so that the kernel reserves V2_NST + 1 barriers and not all 16
+    if (stage == 0) asm volatile("bar.arrive 1, %0;" ::"n"(V2_THREADS) : "memory");
+    else if (stage == 1) asm volatile("bar.arrive 2, %0;" ::"n"(V2_THREADS) : "memory");
+    else asm volatile("bar.arrive 3, %0;" ::"n"(V2_THREADS) : "memory");
+}
+__device__ __forceinline__ void stage_free_wait(int stage)
+{
+    if (stage == 0) asm volatile("bar.sync 1, %0;" ::"n"(V2_THREADS) : "memory");
+    else if (stage == 1) asm volatile("bar.sync 2, %0;" ::"n"(V2_THREADS) : "memory");
+    else asm volatile("bar.sync 3, %0;" ::"n"(V2_THREADS) : "memory");
+}
+static_assert(V2_NST == 3, "stage_free_* name one barrier per stage");
 // 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
 {
@@ -127,7 +148,12 @@ __device__ __forceinline__ void v2_drain_batch(const FsgDev &d, const V2Stage &S
         key = (int)(ent >> 16);                                   // slot within the warp: pass * 2 + which
         int c = (int)(ent & 0xffffu);
         int k = 8 * (key >> 1) + 2 * warp + (key & 1);            // home particle within the group
-        int i = S.hs + k, j = S.sj[c];
+        int i = S.hs + k, j = 0;
+#pragma unroll
+        for (int r = 0; r < 9; r++) {                             // runs are staged in ascending slot order
+            int lo = S.run_lo[r];
+            if (c >= lo) j = S.run_j[r] + (c - lo);
+        }
         v = v2_near_pair(d, S.hp[k], velp[i], S.sp[c], velp[j]);
     }
 #pragma unroll
@@ -147,7 +173,7 @@ __device__ __forceinline__ void v2_drain_batch(const FsgDev &d, const V2Stage &S
 }
 
 template <bool STATS, bool HASB>
-__global__ void __launch_bounds__(V2_THREADS, 5)
+__global__ void __launch_bounds__(V2_THREADS, V2_BLOCKS_PER_SM)
 k_pair_v2(V2Args va)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -161,7 +187,6 @@ k_pair_v2(V2Args va)
 #pragma unroll
         for (int s = 0; s < V2_NST; s++) {
             mbar_init(&SM.full[s], 1);
-            mbar_init(&SM.empty[s], V2_CWARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -170,43 +195,53 @@ k_pair_v2(V2Args va)
     if (warp == V2_CWARPS) {
         // =========================== producer ===========================
         int it = 0;
-        int grab = 0, grab_end = 0;
+        int grab = 0, grab_end = 0, mybin = 0;
+        // table entries of the NEXT bin are requested one item ahead (pf_*), so that the only exposed
+        // global latency is the queue grab every V2_BINS_PER_GRAB bins
+        int pf_s0 = -1, pf_s1 = -1, pf_s2 = -1, pf_e0 = -1, pf_e1 = -1, pf_e2 = -1;
+        bool pf_valid = false;
+        auto prefetch = [&](int b) {
+            pf_s0 = pf_s1 = pf_s2 = pf_e0 = pf_e1 = pf_e2 = -1;
+            if (lane < 9) {
+                const int c0 = b + (lane / 3 - 1) * d.G2 + (lane % 3 - 1) * d.G;
+                if (c0 - 1 >= 0 && c0 - 1 < d.numcells) { pf_s0 = a.start[c0 - 1]; pf_e0 = a.end[c0 - 1]; }
+                if (c0 >= 0 && c0 < d.numcells) { pf_s1 = a.start[c0]; pf_e1 = a.end[c0]; }
+                if (c0 + 1 >= 0 && c0 + 1 < d.numcells) { pf_s2 = a.start[c0 + 1]; pf_e2 = a.end[c0 + 1]; }
+            }
+        };
         for (;;) {
             if (grab >= grab_end) {
                 int m = 0;
                 if (lane == 0) m = atomicAdd(a.work, V2_BINS_PER_GRAB);
                 grab = __shfl_sync(FULL, m, 0);
                 grab_end = min(grab + V2_BINS_PER_GRAB, nocc);
+                if (grab + lane < grab_end) mybin = a.binlist[grab + lane];
+                pf_valid = false;
             }
             if (grab >= nocc) {
                 const int stage = it % V2_NST;
-                mbar_wait(&SM.empty[stage], ((it / V2_NST) & 1) ^ 1);
+                if (it >= V2_NST) stage_free_wait(stage);
                 if (lane == 0) {
                     SM.st[stage].gcount = -1;
                     mbar_arrive(&SM.full[stage]);
                 }
                 break;
             }
-            const int first = a.binlist[grab++];
-            const int b = a.keysA[first];
+            const int slot = grab & (V2_BINS_PER_GRAB - 1);     // grabs are aligned to V2_BINS_PER_GRAB
+            const int b = __shfl_sync(FULL, mybin, slot);
+            if (!pf_valid) prefetch(b);
             // runs: lane r < 9 owns column (dx, dy) = (r / 3 - 1, r % 3 - 1), bins c0 - 1 .. c0 + 1
             int rs = 0, rp = 0;
-            if (lane < 9) {
-                const int c0 = b + (lane / 3 - 1) * d.G2 + (lane % 3 - 1) * d.G;
-                int s = -1, e = -1;
-#pragma unroll
-                for (int dz = -1; dz <= 1; dz++) {
-                    int c = c0 + dz;
-                    if (c >= 0 && c < d.numcells) {
-                        int s0 = a.start[c];
-                        if (s0 >= 0) {
-                            if (s < 0) s = s0;
-                            e = a.end[c];
-                        }
-                    }
-                }
+            {
+                int s = pf_s0 >= 0 ? pf_s0 : (pf_s1 >= 0 ? pf_s1 : pf_s2);
+                int e = pf_s2 >= 0 ? pf_e2 : (pf_s1 >= 0 ? pf_e1 : pf_e0);
                 if (s >= 0) { rs = s; rp = e - s + 1; }
             }
+            const int hs = __shfl_sync(FULL, pf_s1, 4);
+            const int hn = __shfl_sync(FULL, pf_e1, 4) - hs + 1;
+            grab++;
+            pf_valid = grab < grab_end;
+            if (pf_valid) prefetch(__shfl_sync(FULL, mybin, grab & (V2_BINS_PER_GRAB - 1)));
             int incl = rp;
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) {
@@ -215,22 +250,19 @@ k_pair_v2(V2Args va)
             }
             const int excl = incl - rp;
             const int C = __shfl_sync(FULL, incl, 8);
-            const int hs = a.start[b], hn = a.end[b] - hs + 1;
             for (int ig = 0; ig < hn; ig += V2_GROUP) {
                 const int gcount = min(V2_GROUP, hn - ig);
                 for (int t0 = 0; t0 < C; t0 += V2_TILE) {
                     const int ct = min(V2_TILE, C - t0);
                     const int stage = it % V2_NST;
                     V2Stage &S = SM.st[stage];
-                    mbar_wait(&SM.empty[stage], ((it / V2_NST) & 1) ^ 1);
-                    // candidate slots + padding + header (generic-proxy writes, published by the arrive below)
-#pragma unroll 1
-                    for (int r = 0; r < 9; r++) {
-                        int pr = __shfl_sync(FULL, rp, r);
-                        if (pr == 0) continue;
-                        int ex = __shfl_sync(FULL, excl, r), sr = __shfl_sync(FULL, rs, r);
-                        int lo = max(ex, t0), hi = min(ex + pr, t0 + ct);
-                        for (int k = lo + lane; k < hi; k += 32) S.sj[k - t0] = sr + (k - ex);
+                    if (it >= V2_NST) stage_free_wait(stage);
+                    // run table + padding + header (generic-proxy writes, published by the arrive below)
+                    if (lane < 12) {
+                        int lo = max(excl, t0), hi = min(excl + rp, t0 + ct);
+                        bool used = lane < 9 && rp > 0 && hi > lo;
+                        S.run_lo[lane] = used ? lo - t0 : V2_TILE;
+                        S.run_j[lane] = used ? rs + (lo - excl) : 0;
                     }
                     const int cpad = (ct + 31) & ~31;
                     if (ct + lane < cpad) S.sp[ct + lane] = make_float4(1e30f, 1e30f, 1e30f, 0.f);
@@ -288,7 +320,7 @@ k_pair_v2(V2Args va)
             float w0 = 0.f, w1 = 0.f;
             unsigned m0 = 0, m1 = 0, bit = 1;
             int nin = 0;
-#pragma unroll 2
+#pragma unroll 4
             for (int c0 = 0; c0 < cpad; c0 += 32, bit <<= 1) {
                 const float4 pj = S.sp[c0 + lane];
                 float bjf = 0.f;
@@ -363,7 +395,7 @@ k_pair_v2(V2Args va)
         for (int qh = 0; qh < qn; qh += 32) v2_drain_batch(d, S, W, a.A.velp, qh, qn, lane, warp);
         const int last = S.last, hs = S.hs;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&SM.empty[stage]);
+        stage_free_arrive(stage);
         if (last && lane < 8) {
             int k = 8 * (lane >> 1) + 2 * warp + (lane & 1);
             if (k < gcount) va.sums[hs + k] = W.acc[lane];
@@ -380,7 +412,7 @@ k_pair_v2(V2Args va)
 // k_update — Particle::update + the tail of mykernel2 (FluidGPU.cuh:270-304, FluidGPU.cu:419-425)
 // for every sorted slot: sums (+ accumulators carried in from the upload) -> EOS, integration, new
 // bin id.  Streaming: reads 64 + 16 B, writes 64 + 4 B per particle.  Particles parked outside the
-// bin grid (key == numcells) are copied through unchanged.
+// bin grid (key == numcells) are copied through unchanged; ghosts of a slab context are dropped.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B, int *__restrict__ keysB,
@@ -391,6 +423,11 @@ k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B,
     float4 pd = A.posd[i], vp = A.velp[i], af = A.accf[i], dpi = A.dpi[i];
     int key = keysA[i];
     if (key < d.numcells) {
+        const int ix = key / d.G2;
+        if (ix < d.x0 || ix >= d.x1) {      // ghost copy of a neighbour slab's particle: drop it
+            keysB[i] = d.dead;
+            return;
+        }
         float4 s = sums[i];
         if (carry) { float4 cy = carry[i]; s.x += cy.x; s.y += cy.y; s.z += cy.z; s.w += cy.w; }
         particle_update(d, pd, vp, af, dpi, s.x, s.y, s.z, s.w, key);
@@ -417,7 +454,7 @@ cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool
     va.a = a;
     va.sums = sums;
     int64_t blocks = ((int64_t)a.n + 7) / 8;
-    int64_t maxb = (int64_t)sm_count * 5;
+    int64_t maxb = (int64_t)sm_count * V2_BLOCKS_PER_SM;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
     if (stats) {

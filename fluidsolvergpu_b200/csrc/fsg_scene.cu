@@ -79,18 +79,19 @@ __host__ __device__ static inline void plume_particle(const PlumeGeom &g, int co
     vel[2] = (float)(0.5 * e);
 }
 
-__global__ void k_plume(PlumeGeom g, const int *__restrict__ cols, int64_t n, float gravity, FsgState st, float4 *carry)
+__global__ void k_plume(PlumeGeom g, const int *__restrict__ cols, int64_t n, int64_t id0, float gravity, FsgState st, float4 *carry)
 {
-    int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= n) return;
-    int c = (int)(id / g.nz), kz = (int)(id % g.nz);
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int c = (int)(t / g.nz), kz = (int)(t % g.nz);
+    int64_t id = id0 + t;                         // global particle id == Particle::index
     float p[3], v[3];
     plume_particle(g, cols[c], kz, id, p, v);
-    st.posd[id] = make_float4(p[0], p[1], p[2], 9550.f);
-    st.velp[id] = make_float4(v[0], v[1], v[2], 0.f);
-    st.accf[id] = make_float4(0.f, 0.f, gravity, __int_as_float(0));
-    st.dpi[id] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)id));
-    carry[id] = make_float4(9550.f, 0.f, 0.f, 0.f);
+    st.posd[t] = make_float4(p[0], p[1], p[2], 9550.f);
+    st.velp[t] = make_float4(v[0], v[1], v[2], 0.f);
+    st.accf[t] = make_float4(0.f, 0.f, gravity, __int_as_float(0));
+    st.dpi[t] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)id));
+    carry[t] = make_float4(9550.f, 0.f, 0.f, 0.f);
 }
 
 extern "C" int fsg_scene_plume_host(const fsg_config *cfg, double spacing, double jitter, uint64_t seed, float *pos,
@@ -108,20 +109,50 @@ extern "C" int fsg_scene_plume_host(const fsg_config *cfg, double spacing, doubl
     return FSG_OK;
 }
 
-// device variant; returns the particle count or a negative error through *count_out
+// particles per bin layer ix (lattice positions, jitter ignored): what the host uses to cut the domain
+// into slabs of equal particle count
+extern "C" int fsg_scene_plume_hist(const fsg_config *cfg, double spacing, int64_t *hist)
+{
+    if (!cfg || !hist || spacing <= 0) return FSG_E_INVALID;
+    PlumeGeom g = plume_geom(cfg->grid, cfg->origin, cfg->cellsize, spacing, 0.0, 0);
+    std::vector<int> cols;
+    plume_columns(g, cols);
+    for (int i = 0; i < cfg->grid; i++) hist[i] = 0;
+    for (int c : cols) {
+        double x = g.x0 + (c / g.nxy) * g.spacing;
+        int ix = (int)(((float)x - cfg->origin) / cfg->cellsize);
+        if (ix < 0) ix = 0;
+        if (ix >= cfg->grid) ix = cfg->grid - 1;
+        hist[ix] += g.nz;
+    }
+    return FSG_OK;
+}
+
+// device variant; returns the particle count or a negative error through *count_out.
+// Slab contexts generate only the lattice columns that can fall into their slab (ids stay global);
+// strays are dropped by the slab filter of the key kernel.
 int fsg_scene_plume_device(fsg_ctx *c, double spacing, double jitter, uint64_t seed, int64_t *n_out)
 {
     PlumeGeom g = plume_geom(c->cfg.grid, c->cfg.origin, c->cfg.cellsize, spacing, jitter, seed);
     std::vector<int> cols;
     plume_columns(g, cols);
-    int64_t n = (int64_t)cols.size() * g.nz;
+    size_t c_lo = 0, c_hi = cols.size();
+    if (c->cfg.world > 1) {
+        const double xlo = (double)c->cfg.origin + c->cfg.slab_x0 * c->cfg.cellsize - jitter - 1e-3 * spacing;
+        const double xhi = (double)c->cfg.origin + c->cfg.slab_x1 * c->cfg.cellsize + jitter + 1e-3 * spacing;
+        while (c_lo < cols.size() && g.x0 + (cols[c_lo] / g.nxy) * g.spacing < xlo) c_lo++;
+        c_hi = c_lo;
+        while (c_hi < cols.size() && g.x0 + (cols[c_hi] / g.nxy) * g.spacing <= xhi) c_hi++;
+    }
+    const size_t ncols = c_hi - c_lo;
+    int64_t n = (int64_t)ncols * g.nz;
     *n_out = n;
     if (n > c->cap) return FSG_E_NOMEM;
     if (n == 0) return FSG_OK;
     int *dcols = nullptr;
-    if (cudaMalloc(&dcols, sizeof(int) * cols.size()) != cudaSuccess) return FSG_E_NOMEM;
-    cudaMemcpyAsync(dcols, cols.data(), sizeof(int) * cols.size(), cudaMemcpyHostToDevice, c->stream);
-    k_plume<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(g, dcols, n, (float)c->cfg.gravity, c->B, c->carryB);
+    if (cudaMalloc(&dcols, sizeof(int) * ncols) != cudaSuccess) return FSG_E_NOMEM;
+    cudaMemcpyAsync(dcols, cols.data() + c_lo, sizeof(int) * ncols, cudaMemcpyHostToDevice, c->stream);
+    k_plume<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(g, dcols, n, (int64_t)c_lo * g.nz, (float)c->cfg.gravity, c->B, c->carryB);
     cudaError_t e = cudaGetLastError();
     cudaStreamSynchronize(c->stream);
     cudaFree(dcols);

@@ -79,7 +79,8 @@ typedef struct fsg_config {
     int32_t collect_stats;  /* 1: count candidate / in-range pairs each step                   */
     /* slab decomposition along x, the slowest bin axis (solver-unidyn.cu:187-193) */
     int32_t rank, world;    /* this context's slab and the number of slabs (1 = no decomposition) */
-    int32_t reserved[5];
+    int32_t slab_x0, slab_x1; /* world > 1: this slab owns the bin layers slab_x0 <= ix < slab_x1 (ix = bin id / grid^2) */
+    int32_t reserved[3];
 } fsg_config;
 
 /* Host-side structure-of-arrays view used by fsg_upload_soa / fsg_download_soa: the live fields
@@ -163,10 +164,31 @@ FSG_API int  fsg_scene_plume(fsg_ctx *ctx, double spacing, double jitter, uint64
 FSG_API int  fsg_scene_plume_host(const fsg_config *cfg, double spacing, double jitter, uint64_t seed,
                           float *pos, float *vel, int64_t capacity, int64_t *n_out);
 
+/* Particles per bin layer ix of that scene (hist[grid]; lattice positions): the host cuts the domain
+ * into slabs of equal particle count with it.  Pure host code. */
+FSG_API int  fsg_scene_plume_hist(const fsg_config *cfg, double spacing, int64_t *hist);
+
 /* Device pointers to the SoA state (float4 arrays, see DESIGN.md "Data layout"), for zero-copy
  * consumers on the same device (bench, halo exchange).  which: 0 = posd, 1 = velp, 2 = accf, 3 = dpi,
  * 4 = keys (int32).  Valid until the next fsg_* call that changes state. */
 FSG_API int  fsg_device_ptr(fsg_ctx *ctx, int which, void **ptr);
+
+/* ---- slab decomposition along x (world > 1): the multi-device hand-off of solver-unidyn.cu:396-470 ----
+ * Every step of a slab context is   fsg_slab_pack -> (caller moves the two messages to the x-neighbours,
+ * e.g. NCCL send/recv) -> fsg_slab_unpack -> fsg_step(ctx, 1).
+ * fsg_slab_pack classifies the particles by their new bin layer: those that left the slab are moved
+ * out (migrants, full 64-byte state), those in the slab's outermost layers are copied (ghosts, the
+ * 32-byte read state the neighbour's pair sums need; the reference ships a one-layer `buffer` of whole
+ * Particle records instead, solver-unidyn.cu:187,421-462).  Message layout (device memory):
+ *   [posd m][velp m][accf m][dpi m][posd g][velp g]   float4 arrays, m migrants then g ghosts.
+ * counts[5] (host): migrants/ghosts for the left neighbour, migrants/ghosts for the right one, and the
+ * number of particle slots in use.  Order inside the messages is the particles' current order
+ * (deterministic).  d_to_left / d_to_right hold cap_bytes each. */
+FSG_API int  fsg_slab_pack(fsg_ctx *ctx, void *d_to_left, void *d_to_right, int64_t cap_bytes, int64_t counts[5]);
+FSG_API int  fsg_slab_unpack(fsg_ctx *ctx, const void *d_from_left, int64_t mig_left, int64_t ghost_left,
+                             const void *d_from_right, int64_t mig_right, int64_t ghost_right);
+/* bytes of a message holding m migrants and g ghosts */
+FSG_API int64_t fsg_slab_message_bytes(int64_t m, int64_t g);
 
 /* ---- (2) stage API: caller-owned DEVICE buffers in the reference's own layout ---- */
 /* replaces thrust::sort_by_key(t_v, t_v + n, t_a)            solver.cu:181 */

@@ -301,3 +301,89 @@ def test_run_to_run_determinism(fsg):
             outs.append(s.download())
     for f in FIELDS + ("index", "cell"):
         assert np.array_equal(outs[0][f], outs[1][f]), f
+
+
+# ---------------------------------------------------------------------------------------------
+# slab decomposition (W slabs emulated in one process on one device, see fluidsolvergpu_b200/slab.py)
+# ---------------------------------------------------------------------------------------------
+def _slab_scene(fsg, fast: bool):
+    cfg = fsg.scenes.plume_config(17)
+    cfg.origin = -1.02
+    if fast:
+        # a common drift along x carries particles across the slab faces within a few steps (no boundary
+        # particles here: fluid streaming past boundary particles at speed blows up under the reference's
+        # ALPHA_BOUNDARY = 200 viscosity, FluidGPU.cu:255, and would leave the one-layer ghost band)
+        state = fsg.scenes.random_base_scene(5000, 33, box=((-0.45, 0.45),) * 3, spacing=0.05, jitter=0.012, vel_scale=0.3)
+        state["vel"][:, 0] += np.float32(7.0)
+    else:
+        state = fsg.scenes.random_base_scene(5000, 34, box=((-0.45, 0.45),) * 3, spacing=0.05, jitter=0.012, vel_scale=0.2,
+                                             boundary_frac=0.1)
+    return cfg, state
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("fast", [False, True])
+def test_slabs_match_single_device(fsg, world, fast):
+    """W x-slabs with migration + one-layer ghost exchange against ONE context on the same scene,
+    resynchronised every step: positions, velocities and every integer result bit-exact (they do
+    not depend on the summation order), sums within 1e-5."""
+    cfg, state = _slab_scene(fsg, fast)
+    n = state["pos"].shape[0]
+    cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), world)
+    cfg.capacity = n
+    moved = 0
+    with fsg.SlabGroup(cfg, world, cuts, capacity=2 * n + 64) as g, fsg.FluidSolver(cfg) as s:
+        g.upload(state)
+        # (the boundary scene is stiff — ALPHA_BOUNDARY = 200 — and is only followed for a few steps)
+        for k in range(6 if fast else 3):
+            cur = fsg.by_index(g.download())
+            assert cur["index"].shape[0] == n and np.array_equal(cur["index"], np.arange(n)), "particles lost or duplicated"
+            s.upload({f: cur[f] for f in cur if f != "cell"})
+            g.step(1)
+            s.step(1)
+            moved += sum(sl.last_counts[0] + sl.last_counts[2] for sl in g.slabs)
+            a, b = fsg.by_index(g.download()), fsg.by_index(s.download())
+            assert np.array_equal(a["index"], b["index"])
+            for f in ("pos", "vel", "cell", "boundary"):
+                assert np.array_equal(a[f], b[f]), (f, k)
+            for f in ("acc", "dens", "press", "delpress"):
+                err = rel_l2(a[f], b[f])
+                assert err <= TOL, (f, k, err)
+        # each slab holds the particles of its own layers (cells are the NEW bin ids: a particle may have
+        # just crossed a face, it migrates at the next pack)
+        for r, sl in enumerate(g.slabs):
+            own = sl.download()
+            ix = own["cell"][own["cell"] < cfg.grid ** 3] // (cfg.grid ** 2)
+            assert ix.size == 0 or (ix.min() >= cuts[r][0] - 1 and ix.max() <= cuts[r][1])
+    if fast:
+        assert moved > 0, "the scene was meant to exercise migration"
+
+
+def test_slab_plume_device_scene(fsg):
+    """fsg_scene_plume on slab contexts generates exactly the single-device scene, split by slab."""
+    cfg = fsg.scenes.plume_config(24)
+    host = fsg.scenes.plume_scene(cfg)
+    n = host["pos"].shape[0]
+    cuts = fsg.slab_cuts(fsg.slab.plume_layer_hist(cfg), 3)
+    with fsg.SlabGroup(cfg, 3, cuts, capacity=n + 64) as g:
+        g.scene_plume()
+        got = fsg.by_index(g.download())
+    assert got["index"].shape[0] == n
+    for f in ("pos", "vel", "acc", "dens", "index"):
+        assert np.array_equal(got[f], host[f]), f
+
+
+def test_slab_ghost_band_violation_is_reported(fsg):
+    """A particle that jumps more than one bin layer in a step cannot be handed over through a
+    one-layer ghost band: fsg_slab_pack reports it instead of losing the particle."""
+    cfg = fsg.scenes.plume_config(17)
+    cfg.origin = -1.02
+    pos = np.array([[0.25, 0.0, 0.0], [-0.5, 0.0, 0.0], [0.45, 0.0, 0.0], [0.5, 0.0, 0.0]], np.float32)
+    vel = np.array([[900.0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0]], np.float32)       # 0.45 per step = 3.75 bins
+    state = fsg.scenes.default_state(pos, vel)
+    cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, pos), 2)
+    with fsg.SlabGroup(cfg, 2, cuts, capacity=16) as g:
+        g.upload(state)
+        g.step(1)
+        with pytest.raises(fsg.FsgError, match="ghost band"):
+            g.step(1)

@@ -8,11 +8,10 @@ import fluidsolvergpu_b200 as fsg
 for G in [int(a) for a in sys.argv[1:]] or [64, 128, 256]:
     cfg = fsg.scenes.plume_config(G)
     cfg.capacity = fsg.scenes.plume_count(cfg)
-    cfg.collect_stats = 1
     with fsg.FluidSolver(cfg) as s:
         n = s.scene_plume()
-        s.step(3)
-        st = s.stats()
+        s.step(2)
+        st = s.pair_stats_one_step()
         stream = torch.cuda.ExternalStream(s.stream())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         K = 10
