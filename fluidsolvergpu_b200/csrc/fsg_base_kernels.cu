@@ -422,6 +422,7 @@ cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binli
     a.keysB = c->keysB;
     a.carry = carry;
     a.stats = c->dstats;
+    a.sums = nullptr;
     // persistent grid: resident blocks per SM x SM count (static smem 4*(512*32+1024) = 68 KB -> 3 blocks/SM)
     int64_t warps_needed = n;   // upper bound on occupied bins
     int64_t blocks = (warps_needed + PAIR_WARPS - 1) / PAIR_WARPS;

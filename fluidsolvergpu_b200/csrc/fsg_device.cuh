@@ -77,6 +77,7 @@ struct PairArgs {
     int *keysB;
     const float4 *carry;
     unsigned long long *stats;
+    float4 *sums;       // non-null: write the pair sums here instead of updating the particles (stage API)
 };
 
 

@@ -88,6 +88,9 @@ struct fsg_ctx {
     int64_t phase_steps;
 };
 
+cudaError_t fsg_sort_pairs_int(void *tmp, size_t tmp_bytes, const int *keys_in, int *keys_out, const int *vals_in,
+                               int *vals_out, int64_t n, cudaStream_t s);
+size_t fsg_sort_int_temp_bytes(int64_t n);
 // fsg_sort.cu — stable radix sort of (bin id, slot) pairs; the reference's thrust::sort_by_key (solver.cu:181)
 size_t fsg_sort_temp_bytes(int64_t n, int bits);
 cudaError_t fsg_sort_pairs(void *tmp, size_t tmp_bytes, const int *keys_in, int *keys_out, const int *vals_in,

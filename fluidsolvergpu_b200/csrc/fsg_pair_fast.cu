@@ -60,7 +60,7 @@ __device__ __forceinline__ float4 near_pair(const FsgDev &d, const float4 &pi, c
     return make_float4(w * ((!bi && bj) ? 2.5f : 1.f), pg * rx, pg * ry, pg * rz);
 }
 
-template <bool STATS>
+template <bool STATS, bool FUSED>
 __global__ void __launch_bounds__(FAST_WARPS * 32, 4)
 k_pair_update_fast(PairArgs a)
 {
@@ -209,17 +209,21 @@ k_pair_update_fast(PairArgs a)
             __syncwarp();
             if (lane < gcount) {
                 const int i = hs + ig + lane;
-                float4 pd = a.A.posd[i], vp = a.A.velp[i], af = a.A.accf[i], dpi = a.A.dpi[i];
                 float4 q4 = S.acc[lane];
                 float nd = aw + q4.x, nx = q4.y, ny = q4.z, nz = q4.w;
-                if (a.carry) { float4 cy = a.carry[i]; nd += cy.x; nx += cy.y; ny += cy.z; nz += cy.w; }
-                int key;
-                particle_update(d, pd, vp, af, dpi, nd, nx, ny, nz, key);
-                a.B.posd[i] = pd;
-                a.B.velp[i] = vp;
-                a.B.accf[i] = af;
-                a.B.dpi[i] = dpi;
-                a.keysB[i] = key;
+                if (!FUSED) {                     // stage API: the sums only, the caller's mykernel2 stage consumes them
+                    a.sums[i] = make_float4(nd, nx, ny, nz);
+                } else {
+                    float4 pd = a.A.posd[i], vp = a.A.velp[i], af = a.A.accf[i], dpi = a.A.dpi[i];
+                    if (a.carry) { float4 cy = a.carry[i]; nd += cy.x; nx += cy.y; ny += cy.z; nz += cy.w; }
+                    int key;
+                    particle_update(d, pd, vp, af, dpi, nd, nx, ny, nz, key);
+                    a.B.posd[i] = pd;
+                    a.B.velp[i] = vp;
+                    a.B.accf[i] = af;
+                    a.B.dpi[i] = dpi;
+                    a.keysB[i] = key;
+                }
             }
             __syncwarp();
         }
@@ -235,15 +239,17 @@ cudaError_t fsg_launch_pair_fast(const PairArgs &a, bool stats, int sm_count, cu
 {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_pair_update_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM);
-        cudaFuncSetAttribute(k_pair_update_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM);
+        cudaFuncSetAttribute(k_pair_update_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM);
+        cudaFuncSetAttribute(k_pair_update_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM);
+        cudaFuncSetAttribute(k_pair_update_fast<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM);
         attr_done = true;
     }
     int64_t blocks = ((int64_t)a.n + FAST_WARPS - 1) / FAST_WARPS;
     int64_t maxb = (int64_t)sm_count * 4;      // persistent: 4 resident blocks (16 warps) per SM
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    if (stats) k_pair_update_fast<true><<<(unsigned)blocks, FAST_WARPS * 32, FAST_SMEM, s>>>(a);
-    else k_pair_update_fast<false><<<(unsigned)blocks, FAST_WARPS * 32, FAST_SMEM, s>>>(a);
+    if (a.sums) k_pair_update_fast<false, false><<<(unsigned)blocks, FAST_WARPS * 32, FAST_SMEM, s>>>(a);   // sums only
+    else if (stats) k_pair_update_fast<true, true><<<(unsigned)blocks, FAST_WARPS * 32, FAST_SMEM, s>>>(a);
+    else k_pair_update_fast<false, true><<<(unsigned)blocks, FAST_WARPS * 32, FAST_SMEM, s>>>(a);
     return cudaGetLastError();
 }

@@ -21,3 +21,17 @@ cudaError_t fsg_sort_pairs(void *tmp, size_t tmp_bytes, const int *keys_in, int 
     return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const unsigned *)keys_in, (unsigned *)keys_out, vals_in,
                                            vals_out, n, 0, bits, s);
 }
+
+// full-range signed keys (stage API: the caller's key array is sorted exactly as thrust::sort_by_key<int> would)
+size_t fsg_sort_int_temp_bytes(int64_t n)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int *)nullptr, (int *)nullptr, (const int *)nullptr, (int *)nullptr, n);
+    return bytes;
+}
+cudaError_t fsg_sort_pairs_int(void *tmp, size_t tmp_bytes, const int *keys_in, int *keys_out, const int *vals_in,
+                               int *vals_out, int64_t n, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 32, s);
+}

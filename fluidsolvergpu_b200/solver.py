@@ -175,6 +175,20 @@ class FluidSolver:
         self._check(self._lib.fsg_scene_plume(self._ctx, spacing, jitter, seed, C.byref(n)), "fsg_scene_plume")
         return n.value
 
+    # ---- stage API: caller-owned DEVICE buffers in the reference's own layout (device pointers as ints) ----
+    def stage_sort(self, d_cells: int, d_particles: int, n: int):
+        self._check(self._lib.fsg_stage_sort(self._ctx, d_cells, d_particles, n), "fsg_stage_sort")
+
+    def stage_findneighbours(self, d_cells: int, d_start: int, d_end: int, n: int):
+        self._check(self._lib.fsg_stage_findneighbours(self._ctx, d_cells, d_start, d_end, n), "fsg_stage_findneighbours")
+
+    def stage_mykernel(self, d_particles: int, d_cells: int, d_start: int, d_end: int, n: int):
+        self._check(self._lib.fsg_stage_mykernel(self._ctx, d_particles, d_cells, d_start, d_end, n), "fsg_stage_mykernel")
+
+    def stage_mykernel2(self, d_particles: int, d_cells: int, d_start: int, d_end: int, n: int, spts: int = 0, a3: int = 0, b3: int = 0):
+        self._check(self._lib.fsg_stage_mykernel2(self._ctx, d_particles, d_cells, d_start, d_end, n, spts or None, a3 or None,
+                                                  b3 or None), "fsg_stage_mykernel2")
+
     def device_ptr(self, which: int) -> int:
         p = C.c_void_p()
         self._check(self._lib.fsg_device_ptr(self._ctx, which, C.byref(p)), "fsg_device_ptr")

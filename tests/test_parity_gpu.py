@@ -387,3 +387,60 @@ def test_slab_ghost_band_violation_is_reported(fsg):
         g.step(1)
         with pytest.raises(fsg.FsgError, match="ghost band"):
             g.step(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# stage API: the four reference launches one by one on caller-owned device buffers (340-byte AoS)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scene", ["config1", "random_boundary", "uncapped"])
+def test_stage_api_follows_the_reference_launch_sequence(fsg, scene):
+    """sort_by_key -> findneighbours -> mykernel -> mykernel2 through fsg_stage_* on torch-owned
+    device memory, against the oracle: tables and keys bit-exact every step, fields <= 1e-5 per step
+    (the oracle is restarted from the records the stage path holds)."""
+    import torch
+    import aos
+    if scene == "config1":
+        state, cfg = fsg.scenes.base_default_scene(), fsg.FluidSolver.base_config()
+    elif scene == "random_boundary":
+        state = fsg.scenes.random_base_scene(3000, 2, boundary_frac=0.15)
+        cfg = fsg.FluidSolver.base_config(capacity=state["pos"].shape[0])
+    else:
+        cfg = fsg.scenes.plume_config(24)
+        state = fsg.scenes.plume_scene(cfg)
+        cfg.capacity = state["pos"].shape[0]
+    n, nc = state["pos"].shape[0], cfg.grid ** 3
+    p = oracle_py.params_from_cfg(cfg)
+    dev = torch.device("cuda", 0)
+    rec_h = aos.pack_base(state)
+    cells_h = oracle_py.cell_ids(p, state["pos"]).astype(np.int32)
+    rec_h.reshape(-1).view(aos.BASE_DTYPE)["cellnumber"] = cells_h
+    rec = torch.from_numpy(rec_h.copy()).to(dev)
+    cells = torch.from_numpy(cells_h).to(dev)
+    start = torch.full((nc,), -1, dtype=torch.int32, device=dev)     # solver.cu:163-169
+    end = torch.full((nc,), -1, dtype=torch.int32, device=dev)
+    spts, a3, b3 = (torch.zeros(3 * n, device=dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev))
+    torch.cuda.synchronize()
+    with fsg.FluidSolver(cfg) as s:
+        for step in range(3):
+            cur = aos.unpack_base(rec.cpu().numpy())
+            sim = oracle_py.OracleSim(p, {k: v for k, v in cur.items() if k != "cell"})
+            sim.step(1)
+            s.stage_sort(cells.data_ptr(), rec.data_ptr(), n)
+            s.stage_findneighbours(cells.data_ptr(), start.data_ptr(), end.data_ptr(), n)
+            s.sync()
+            assert np.array_equal(cells.cpu().numpy(), sim.cells_sorted)
+            assert np.array_equal(start.cpu().numpy(), sim.start) and np.array_equal(end.cpu().numpy(), sim.end)
+            s.stage_mykernel(rec.data_ptr(), cells.data_ptr(), start.data_ptr(), end.data_ptr(), n)
+            s.stage_mykernel2(rec.data_ptr(), cells.data_ptr(), start.data_ptr(), end.data_ptr(), n, spts.data_ptr(), a3.data_ptr(),
+                              b3.data_ptr())
+            s.sync()
+            got, ref = aos.unpack_base(rec.cpu().numpy()), sim.state()
+            assert np.array_equal(got["index"], ref["index"]), "sort permutation differs"
+            assert np.array_equal(got["cell"], ref["cell"]) and np.array_equal(cells.cpu().numpy(), ref["cell"])
+            assert np.array_equal(spts.cpu().numpy(), sim.spts) and np.array_equal(b3.cpu().numpy(), sim.b3)
+            assert np.array_equal(a3.cpu().numpy(), sim.a3)
+            assert int((start.cpu() != -1).sum()) == 0 and int((end.cpu() != -1).sum()) == 0      # FluidGPU.cu:427-430
+            for f in FIELDS:
+                err = rel_l2(got[f], ref[f])
+                assert err <= TOL, (scene, step, f, err)
+            assert float(np.abs(got["newdens"]).max()) == 0.0 and float(np.abs(got["newdelpress"]).max()) == 0.0
