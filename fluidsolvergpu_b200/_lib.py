@@ -30,7 +30,7 @@ class FsgSoa(C.Structure):
     _fields_ = [
         ("n", C.c_int64), ("pos", C.c_void_p), ("vel", C.c_void_p), ("acc", C.c_void_p), ("dens", C.c_void_p),
         ("press", C.c_void_p), ("delpress", C.c_void_p), ("newdens", C.c_void_p), ("newdelpress", C.c_void_p),
-        ("index", C.c_void_p), ("cell", C.c_void_p), ("boundary", C.c_void_p),
+        ("index", C.c_void_p), ("cell", C.c_void_p), ("boundary", C.c_void_p), ("solid", C.c_void_p), ("fluid", C.c_void_p),
     ]
 
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "fsg_sync": (C.c_int, [P]),
     "fsg_export_viz": (C.c_int, [P, P, P, P]),
     "fsg_get_tables": (C.c_int, [P, P, P, P]),
+    "fsg_get_split": (C.c_int, [P, P]),
     "fsg_get_stats": (C.c_int, [P, C.POINTER(FsgStats)]),
     "fsg_set_collect_stats": (C.c_int, [P, C.c_int]),
     "fsg_set_profiling": (C.c_int, [P, C.c_int]),

@@ -101,9 +101,9 @@ extern "C" int fsg_config_default(fsg_config *cfg, int model)
         cfg->cellsize = 0.12;
         cfg->dt = 0.0018;
         cfg->alpha_fluid = -0.0155e1;
-        cfg->alpha_boundary = 80e0;
+        cfg->alpha_boundary = 100e-1;     // ALPHA__SAND_BOUNDARY: the boundary factor the unidyn pair term uses (FluidGPU-unidyn.cu:307)
         cfg->neighbour_cap = 1024;
-        cfg->bin_cap = 1024;
+        cfg->bin_cap = 0;
         cfg->capacity = 14040;
     } else
         return FSG_E_INVALID;
@@ -112,8 +112,8 @@ extern "C" int fsg_config_default(fsg_config *cfg, int model)
 
 static void free_state(FsgState &s)
 {
-    cudaFree(s.posd); cudaFree(s.velp); cudaFree(s.accf); cudaFree(s.dpi);
-    s.posd = s.velp = s.accf = s.dpi = nullptr;
+    cudaFree(s.posd); cudaFree(s.velp); cudaFree(s.accf); cudaFree(s.dpi); cudaFree(s.mix);
+    s.posd = s.velp = s.accf = s.dpi = s.mix = nullptr;
 }
 
 extern "C" int fsg_destroy(fsg_ctx *c)
@@ -123,7 +123,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_state(c->A);
     free_state(c->B);
-    cudaFree(c->carryA); cudaFree(c->carryB); cudaFree(c->sums);
+    cudaFree(c->carryA); cudaFree(c->carryB); cudaFree(c->sums); cudaFree(c->sums2); cudaFree(c->vizb);
     cudaFree(c->keysA); cudaFree(c->keysB); cudaFree(c->perm); cudaFree(c->iota);
     cudaFree(c->start); cudaFree(c->end);
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
@@ -143,6 +143,7 @@ static int alloc_state(fsg_ctx *c, FsgState &s, int64_t cap)
     CU(c, cudaMalloc(&s.velp, sizeof(float4) * cap));
     CU(c, cudaMalloc(&s.accf, sizeof(float4) * cap));
     CU(c, cudaMalloc(&s.dpi, sizeof(float4) * cap));
+    if (c->cfg.model == FSG_MODEL_UNIDYN) CU(c, cudaMalloc(&s.mix, sizeof(float4) * cap));
     return FSG_OK;
 }
 
@@ -163,6 +164,11 @@ static int create_impl(fsg_ctx *c)
     CU(c, cudaMalloc(&c->carryA, sizeof(float4) * cap));
     CU(c, cudaMalloc(&c->carryB, sizeof(float4) * cap));
     CU(c, cudaMalloc(&c->sums, sizeof(float4) * cap));
+    if (cfg.model == FSG_MODEL_UNIDYN) {
+        CU(c, cudaMalloc(&c->sums2, sizeof(float4) * cap));
+        CU(c, cudaMalloc(&c->vizb, sizeof(float) * cap));
+        CU(c, cudaMemsetAsync(c->vizb, 0, sizeof(float) * cap, c->stream));
+    }
     CU(c, cudaMalloc(&c->keysA, sizeof(int) * cap));
     CU(c, cudaMalloc(&c->keysB, sizeof(int) * cap));
     CU(c, cudaMalloc(&c->perm, sizeof(int) * cap));
@@ -173,9 +179,9 @@ static int create_impl(fsg_ctx *c)
     const int64_t nb = cap < nc ? cap : nc;
     CU(c, cudaMalloc(&c->binlist[0], sizeof(int) * (nb > 0 ? nb : 1)));
     CU(c, cudaMalloc(&c->binlist[1], sizeof(int) * (nb > 0 ? nb : 1)));
-    CU(c, cudaMalloc(&c->counters, sizeof(int) * 8));
+    CU(c, cudaMalloc(&c->counters, sizeof(int) * 16));
     CU(c, cudaMalloc(&c->dstats, sizeof(unsigned long long) * 4));
-    CU(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * 8, c->stream));
+    CU(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * 16, c->stream));
     CU(c, cudaMemsetAsync(c->dstats, 0, sizeof(unsigned long long) * 4, c->stream));
     CU(c, fsg_launch_iota(c->iota, cap, c->stream));
     CU(c, fsg_launch_fill(c->start, -1, nc, c->stream));    // solver.cu:163-169
@@ -203,13 +209,13 @@ extern "C" int fsg_create(const fsg_config *cfg, fsg_ctx **out)
         g_create_err = "fsg_create: invalid slab configuration (rank/world; a slab needs at least 2 bin layers)";
         return FSG_E_INVALID;
     }
-    if (cfg->world > 1 && (cfg->neighbour_cap != 0 || cfg->bin_cap != 0 || cfg->pair_fp64 != 0)) {
+    if (cfg->model == FSG_MODEL_BASE && cfg->world > 1 && (cfg->neighbour_cap != 0 || cfg->bin_cap != 0 || cfg->pair_fp64 != 0)) {
         g_create_err = "fsg_create: slab decomposition needs the uncapped configuration (neighbour_cap = bin_cap = 0) "
                        "and a one-layer ghost band, i.e. cellsize >= 2h";
         return FSG_E_UNSUPPORTED;
     }
-    if (cfg->model == FSG_MODEL_UNIDYN) {
-        g_create_err = "fsg_create: the unidyn model is not available through the context API yet";
+    if (cfg->model == FSG_MODEL_UNIDYN && cfg->world > 1) {
+        g_create_err = "fsg_create: slab decomposition is implemented for the base model only";
         return FSG_E_UNSUPPORTED;
     }
     int ndev = fsg_device_count();
@@ -269,10 +275,17 @@ static int after_upload(fsg_ctx *c, int64_t n)
     CU(c, cudaMemsetAsync(c->counters + 6, 0, sizeof(int), c->stream));
     CU(c, fsg_launch_keys(c->dev, c->B.posd, c->keysB, n, c->counters + 4, c->cfg.world > 1, c->stream));   // solver.cu:119
     c->launches++;
-    int flag = 0;
-    CU(c, cudaMemcpyAsync(&flag, c->counters + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int flag[5] = {0, 0, 0, 0, 0};
+    CU(c, cudaMemcpyAsync(flag, c->counters + 4, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    c->has_boundary = flag != 0;
+    c->has_boundary = flag[0] != 0;
+    CU(c, cudaMemsetAsync(c->counters + 8, 0, sizeof(int), c->stream));
+    if (c->cfg.model == FSG_MODEL_UNIDYN && flag[4]) {
+        c->n = 0;
+        c->err = "upload: the unidyn path covers scenes whose non-boundary particles are pure fluid (solid == 0) with mass 1 "
+                 "(solver-unidyn.cu:127-184); mixed-phase / granular scenes are not built yet";
+        return FSG_E_UNSUPPORTED;
+    }
     c->carry_live = true;
     c->steps = 0;
     return FSG_OK;
@@ -300,7 +313,11 @@ extern "C" int fsg_upload_aos(fsg_ctx *c, const void *particles, int64_t n)
         CU(c, cudaMemcpyAsync(c->stage, (const unsigned char *)particles + o * FSG_AOS_STRIDE, (size_t)m * FSG_AOS_STRIDE,
                               cudaMemcpyHostToDevice, c->stream));
         FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o};
-        CU(c, fsg_launch_unpack_aos(c->cfg.model, (const unsigned char *)c->stage, m, st, c->carryB + o, c->stream));
+        if (c->cfg.model == FSG_MODEL_UNIDYN) {
+            st.mix = c->B.mix + o;
+            CU(c, fsg_launch_unpack_aos_unidyn((const unsigned char *)c->stage, m, st, c->carryB + o, c->counters + 8, c->stream));
+        } else
+            CU(c, fsg_launch_unpack_aos(c->cfg.model, (const unsigned char *)c->stage, m, st, c->carryB + o, c->stream));
         c->launches++;
         CU(c, cudaStreamSynchronize(c->stream));
     }
@@ -317,8 +334,13 @@ extern "C" int fsg_download_aos(fsg_ctx *c, void *particles, int64_t n)
     for (int64_t o = 0; o < n; o += chunk) {
         int64_t m = n - o < chunk ? n - o : chunk;
         FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o};
-        CU(c, fsg_launch_pack_aos(c->cfg.model, (unsigned char *)c->stage, m, st, c->carry_live ? c->carryB + o : nullptr,
-                                  c->keysB + o, 101325.f, c->stream));
+        if (c->cfg.model == FSG_MODEL_UNIDYN) {
+            st.mix = c->B.mix + o;
+            CU(c, fsg_launch_pack_aos_unidyn((unsigned char *)c->stage, m, st, c->carry_live ? c->carryB + o : nullptr, c->keysB + o, c->dev,
+                                             c->stream));
+        } else
+            CU(c, fsg_launch_pack_aos(c->cfg.model, (unsigned char *)c->stage, m, st, c->carry_live ? c->carryB + o : nullptr,
+                                      c->keysB + o, 101325.f, c->stream));
         c->launches++;
         CU(c, cudaMemcpyAsync((unsigned char *)particles + o * FSG_AOS_STRIDE, c->stage, (size_t)m * FSG_AOS_STRIDE,
                               cudaMemcpyDeviceToHost, c->stream));
@@ -330,7 +352,8 @@ extern "C" int fsg_download_aos(fsg_ctx *c, void *particles, int64_t n)
 // ---- SoA host interface: raw arrays are copied into a staging area and (un)packed on the device ----
 __global__ void k_pack_soa(int64_t n, const float *pos, const float *vel, const float *acc, const float *dens,
                            const float *press, const float *delp, const float *nd, const float *ndp, const int *index,
-                           const unsigned char *bnd, float gravity, FsgState st, float4 *carry)
+                           const unsigned char *bnd, const float *solid, const float *fluid, float gravity, FsgState st, float4 *carry,
+                           int *bad)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -343,11 +366,16 @@ __global__ void k_pack_soa(int64_t n, const float *pos, const float *vel, const 
     st.dpi[i] = make_float4(delp ? delp[3 * i] : 0.f, delp ? delp[3 * i + 1] : 0.f, delp ? delp[3 * i + 2] : 0.f,
                             __int_as_float(index ? index[i] : (int)i));
     carry[i] = make_float4(nd ? nd[i] : 9550.f, ndp ? ndp[3 * i] : 0.f, ndp ? ndp[3 * i + 1] : 0.f, ndp ? ndp[3 * i + 2] : 0.f);
+    if (st.mix) {      // unidyn: solid / fluid default to 0/1 for fluid, 1/0 for boundary particles (solver-unidyn.cu:129-143)
+        float so = solid ? solid[i] : (b ? 1.f : 0.f), fl = fluid ? fluid[i] : (b ? 0.f : 1.f);
+        st.mix[i] = make_float4(so, fl, 0.f, 0.f);
+        if (!b && so != 0.f) atomicOr(bad, 1);
+    }
 }
 
 __global__ void k_unpack_soa(int64_t n, FsgState st, const float4 *carry, const int *keys, float *pos, float *vel, float *acc,
                              float *dens, float *press, float *delp, float *nd, float *ndp, int *index, int *cell,
-                             unsigned char *bnd)
+                             unsigned char *bnd, float *solid, float *fluid)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -364,12 +392,18 @@ __global__ void k_unpack_soa(int64_t n, FsgState st, const float4 *carry, const 
     if (index) index[i] = __float_as_int(dp.w);
     if (cell) cell[i] = keys[i];
     if (bnd) bnd[i] = pd.w < 0.f ? 1 : 0;
+    if (st.mix && (solid || fluid)) {
+        float4 mx = st.mix[i];
+        if (solid) solid[i] = mx.x;
+        if (fluid) fluid[i] = mx.y;
+    }
 }
 
 struct SoaStage {
     float *pos, *vel, *acc, *dens, *press, *delp, *nd, *ndp;
     int *index, *cell;
     unsigned char *bnd;
+    float *solid, *fluid;
 };
 static size_t soa_stage_layout(char *base, int64_t n, const fsg_soa *h, SoaStage &s)
 {
@@ -391,6 +425,8 @@ static size_t soa_stage_layout(char *base, int64_t n, const fsg_soa *h, SoaStage
     s.index = (int *)take(h->index, 4 * n);
     s.cell = (int *)take(h->cell, 4 * n);
     s.bnd = (unsigned char *)take(h->boundary, n);
+    s.solid = (float *)take(h->solid, 4 * n);
+    s.fluid = (float *)take(h->fluid, 4 * n);
     return o + 256;
 }
 
@@ -411,11 +447,12 @@ extern "C" int fsg_upload_soa(fsg_ctx *c, const fsg_soa *h)
     H2D(s.pos, h->pos, 12 * n); H2D(s.vel, h->vel, 12 * n); H2D(s.acc, h->acc, 12 * n); H2D(s.dens, h->dens, 4 * n);
     H2D(s.press, h->press, 4 * n); H2D(s.delp, h->delpress, 12 * n); H2D(s.nd, h->newdens, 4 * n);
     H2D(s.ndp, h->newdelpress, 12 * n); H2D(s.index, h->index, 4 * n); H2D(s.bnd, h->boundary, n);
+    H2D(s.solid, h->solid, 4 * n); H2D(s.fluid, h->fluid, 4 * n);
 #undef H2D
     if (n > 0) {
         k_pack_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, s.pos, s.vel, s.acc, s.dens, s.press, s.delp, s.nd,
-                                                                       s.ndp, s.index, s.bnd, (float)c->cfg.gravity, c->B,
-                                                                       c->carryB);
+                                                                       s.ndp, s.index, s.bnd, s.solid, s.fluid, (float)c->cfg.gravity,
+                                                                       c->B, c->carryB, c->counters + 8);
         CU(c, cudaGetLastError());
         c->launches++;
     }
@@ -436,7 +473,7 @@ extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
     if (n > 0) {
         k_unpack_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->B, c->carry_live ? c->carryB : nullptr, c->keysB,
                                                                          s.pos, s.vel, s.acc, s.dens, s.press, s.delp, s.nd,
-                                                                         s.ndp, s.index, s.cell, s.bnd);
+                                                                         s.ndp, s.index, s.cell, s.bnd, s.solid, s.fluid);
         CU(c, cudaGetLastError());
         c->launches++;
     }
@@ -444,6 +481,7 @@ extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
     D2H(h->pos, s.pos, 12 * n); D2H(h->vel, s.vel, 12 * n); D2H(h->acc, s.acc, 12 * n); D2H(h->dens, s.dens, 4 * n);
     D2H(h->press, s.press, 4 * n); D2H(h->delpress, s.delp, 12 * n); D2H(h->newdens, s.nd, 4 * n);
     D2H(h->newdelpress, s.ndp, 12 * n); D2H(h->index, s.index, 4 * n); D2H(h->cell, s.cell, 4 * n); D2H(h->boundary, s.bnd, n);
+    if (c->B.mix) { D2H(h->solid, s.solid, 4 * n); D2H(h->fluid, s.fluid, 4 * n); }
 #undef D2H
     CU(c, cudaStreamSynchronize(c->stream));
     return FSG_OK;
@@ -536,8 +574,12 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         if (prof) prof_mark(c);
         // mykernel + mykernel2 (solver.cu:187,198)
         int l = 0;
-        CU(c, fsg_launch_pair_update(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2,
-                                     c->carry_live ? c->carryA : nullptr, &l, c->stream));
+        if (c->cfg.model == FSG_MODEL_UNIDYN)      // mykernel + mykernel3 + mykernel2 + cell_calc (solver-unidyn.cu:363-548)
+            CU(c, fsg_launch_unidyn(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2, c->carry_live ? c->carryA : nullptr, &l,
+                                    c->stream));
+        else
+            CU(c, fsg_launch_pair_update(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2,
+                                         c->carry_live ? c->carryA : nullptr, &l, c->stream));
         c->launches += l;
         if (prof) prof_mark(c);
         c->carry_live = false;
@@ -559,6 +601,11 @@ extern "C" int fsg_export_viz(fsg_ctx *c, float *spts, float *a3, float *b3)
     float *ds = (float *)c->stage, *da = ds + 3 * n, *db = da + n;
     CU(c, fsg_launch_export_viz(n, c->A.posd, c->keysA, ds, da, db, c->stream));
     c->launches++;
+    if (c->cfg.model == FSG_MODEL_UNIDYN) {        // a3 = mass, b3 = |diffusion|^2 (FluidGPU-unidyn.cu:465-466)
+        CU(c, fsg_launch_fill((int *)da, 0x3f800000, n, c->stream));
+        CU(c, cudaMemcpyAsync(db, c->vizb, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+        c->launches++;
+    }
     if (spts) CU(c, cudaMemcpyAsync(spts, ds, 12 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (a3) CU(c, cudaMemcpyAsync(a3, da, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (b3) CU(c, cudaMemcpyAsync(b3, db, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
@@ -574,6 +621,22 @@ extern "C" int fsg_get_tables(fsg_ctx *c, int32_t *cells, int32_t *start, int32_
     if (cells) CU(c, cudaMemcpyAsync(cells, c->keysA, sizeof(int) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
     if (start) CU(c, cudaMemcpyAsync(start, c->start, sizeof(int) * (size_t)c->dev.numcells, cudaMemcpyDeviceToHost, c->stream));
     if (end) CU(c, cudaMemcpyAsync(end, c->end, sizeof(int) * (size_t)c->dev.numcells, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return FSG_OK;
+}
+
+extern "C" int fsg_get_split(fsg_ctx *c, int32_t *split)
+{
+    if (!c || !split) return FSG_E_INVALID;
+    if (c->cfg.model != FSG_MODEL_UNIDYN) { c->err = "fsg_get_split: unidyn model only"; return FSG_E_STATE; }
+    if (c->steps < 1) { c->err = "fsg_get_split: no step taken since upload"; return FSG_E_STATE; }
+    CU(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(int) * (size_t)c->dev.numcells;
+    int rc = ensure_stage(c, bytes + 256);
+    if (rc != FSG_OK) return rc;
+    CU(c, fsg_launch_split_table(c, (int *)c->stage, c->stream));
+    c->launches++;
+    CU(c, cudaMemcpyAsync(split, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return FSG_OK;
 }

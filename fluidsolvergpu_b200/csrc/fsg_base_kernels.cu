@@ -125,6 +125,7 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
         dst.velp[k] = b;
         dst.accf[k] = c;
         dst.dpi[k] = e;
+        if (src.mix) dst.mix[k] = src.mix[sidx];
         if (carry_src) carry_dst[k] = carry_src[sidx];
         int next = k + 1 < n ? keysA[k + 1] : d.dead;
         if (key < numcells) {

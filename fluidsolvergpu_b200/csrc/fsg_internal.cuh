@@ -43,6 +43,7 @@ struct FsgDev {
 //   dpi  = (delpressx, delpressy, delpressz, index bits)
 struct FsgState {
     float4 *posd, *velp, *accf, *dpi;
+    float4 *mix;     // unidyn model only: (solid, fluid, -, -)   FluidGPU-unidyn.cuh:180-181
 };
 
 struct fsg_ctx {
@@ -60,6 +61,9 @@ struct fsg_ctx {
     float4 *carryB, *carryA;   // accumulators carried into the first step after upload (newdens, newdelpress xyz)
     bool carry_live;
     float4 *sums;              // pair sums of the current step (newdens, newdelpress xyz), sorted order
+    float4 *sums2;             // unidyn: (diffusion xyz, delfluid)
+    float *vizb;               // unidyn: |diffusion|^2 of the last step (mykernel2's b3, FluidGPU-unidyn.cu:466)
+    int upload_flags;          // host copy of the flags the upload kernels raise
     bool has_boundary;         // any Particle::boundary set in the uploaded scene
     int *keysB;         // bin ids belonging to B (order of B)
     int *keysA;         // sorted bin ids (order of A)
@@ -120,5 +124,13 @@ cudaError_t fsg_launch_export_viz(int64_t n, const float4 *posd, const int *keys
                                   cudaStream_t s);
 cudaError_t fsg_launch_plume(const FsgDev &d, double spacing, double jitter, uint64_t seed, double gravity,
                              FsgState st, float4 *carry, int64_t capacity, unsigned long long *count, cudaStream_t s);
+
+// fsg_unidyn.cu
+cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work, const float4 *carry,
+                              int *launches, cudaStream_t s);
+cudaError_t fsg_launch_split_table(const fsg_ctx *c, int *split, cudaStream_t s);
+cudaError_t fsg_launch_unpack_aos_unidyn(const unsigned char *aos, int64_t n, FsgState st, float4 *carry, int *bad, cudaStream_t s);
+cudaError_t fsg_launch_pack_aos_unidyn(unsigned char *aos, int64_t n, FsgState st, const float4 *carry, const int *keys, const FsgDev &d,
+                                       cudaStream_t s);
 
 void fsg_derive_constants(const fsg_config &cfg, FsgDev &d);

@@ -1,0 +1,422 @@
+// fsg_unidyn.cu — the "unidyn" particle step (reference: FluidGPU-unidyn.cu / FluidGPU-unidyn.cuh, driven
+// by solver-unidyn.cu:313-573): coarse-bin pair sums (mykernel, :124-449), octant pair sums of the split
+// bins (mykernel3, :569-870), update (mykernel2 :451-497 + Particle::update(t) cuh:296-423) and re-binning
+// (cell_calc :544-551).
+//
+// Scope (checked at upload, FSG_E_UNSUPPORTED otherwise): every non-boundary particle is pure fluid
+// (solid == 0) with mass 1 — the default scene of solver-unidyn.cu:127-184 and scenes built like it.  For
+// such scenes the mixed-phase block (:317-357), mixfactor / vel_grad / stress_accel / mixture_accel /
+// delsolid (:368-400) and the granular stress update (:410-446) are exactly zero, merging is unreachable
+// (:261) and splitting needs mass > 3 (:278).  Live sums per pair: newdens, newdelpress, diffusion, delfluid.
+//
+// The reference's dynamic bin splitting is reproduced as what it does to the numbers: a home particle in
+// a bin with more than 6 particles (:181) only sees the 8 bins on the side of its octant (:579-583,
+// z polarity inverted as in :184) — here a 27-bit mask over the staged neighbourhood, not a second kernel.
+// Gather form, one warp per home bin, in-range candidates compacted into a queue, no atomics.
+#include "fsg_device.cuh"
+
+#define UNI_WARPS 2
+#define UNI_TILE 1024                   // the reference's threads per block = neighbour particles per bin (solver-unidyn.cu:363)
+
+struct UniWarpSmem {
+    float4 sp[UNI_TILE];                // x, y, z, +-dens (sign = boundary)
+    float4 sv[UNI_TILE];                // vx, vy, vz, press / dens^2
+    float sf[UNI_TILE];                 // fluid
+    unsigned short q[UNI_TILE];
+    unsigned char tag[UNI_TILE];        // neighbour slot 0..26 of the candidate's bin
+};
+#define UNI_SMEM (sizeof(UniWarpSmem) * UNI_WARPS)
+
+struct UniArgs {
+    FsgDev d;
+    int n;
+    const int *start, *end, *binlist, *nocc;
+    int *work;
+    FsgState A;
+    float4 *sums, *sums2;               // (newdens, newdelpress xyz), (diffusion xyz, delfluid)
+    unsigned long long *stats;
+};
+
+// octant of a particle inside its bin, FluidGPU-unidyn.cu:182-184
+__device__ __forceinline__ int uni_subindex(const FsgDev &d, float x, float y, float z)
+{
+    float fx = x - d.origin, fy = y - d.origin, fz = z - d.origin;
+    const double cs = d.cellsize;
+    int sx = (int)((double)fx / cs) == (int)(((double)fx + cs / 2) / cs);
+    int sy = (int)((double)fy / cs) == (int)(((double)fy + cs / 2) / cs);
+    int sz = (int)((double)fz / cs) == (int)(((double)fz + cs / 2) / cs);
+    return 1 - sx + 2 - 2 * sy + 4 * sz;
+}
+// the 8 neighbour slots (of the 27) mykernel3 visits for an octant, :579-583
+__device__ __forceinline__ unsigned uni_octant_mask(int oct)
+{
+    const int ax = (oct & 1) ? 1 : -1, ay = (oct & 2) ? 1 : -1, az = (oct & 4) ? -1 : 1;
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int a = (k & 1) ? ax : 0, b = (k & 2) ? ay : 0, c = (k & 4) ? az : 0;
+        m |= 1u << ((a + 1) * 9 + (b + 1) * 3 + (c + 1));
+    }
+    return m;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(UNI_WARPS * 32)
+k_pair_unidyn(UniArgs a)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    UniWarpSmem &S = reinterpret_cast<UniWarpSmem *>(s_raw)[warp];
+    const FsgDev &d = a.d;
+    const int nocc = *a.nocc;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float alpha_sb = (float)d.alpha_boundary;     // ALPHA__SAND_BOUNDARY for this model
+    unsigned long long st_tested = 0, st_in = 0, st_drop = 0;
+
+    for (;;) {
+        int m = 0;
+        if (lane == 0) m = atomicAdd(a.work, 1);
+        m = __shfl_sync(FULL, m, 0);
+        if (m >= nocc) break;
+        const int b = a.binlist[m];
+        int p = 0, st = 0;
+        if (lane < 27) {
+            int off = (lane / 9 - 1) * d.G2 + ((lane / 3) % 3 - 1) * d.G + (lane % 3 - 1);   // cu:130-132
+            int c = b + off;
+            if (c >= 0 && c < d.numcells) {
+                int s0 = a.start[c], e0 = a.end[c];
+                if (s0 >= 0 && e0 >= 0 && s0 < a.n && 1 + e0 - s0 > 0) { p = 1 + e0 - s0; st = s0; }
+            }
+        }
+        int incl = p;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - p;
+        int C = __shfl_sync(FULL, incl, 31);
+        if (C > UNI_TILE) {                         // beyond the reference's 1024 threads per block: not reproduced, reported
+            if (lane == 0) st_drop += C - UNI_TILE;
+            C = UNI_TILE;
+        }
+        const int hs = __shfl_sync(FULL, st, 13), hn = __shfl_sync(FULL, p, 13);
+        const bool split = hn > 6;                  // cu:181
+
+        // ---- stage the neighbourhood ----
+        __syncwarp();
+#pragma unroll 1
+        for (int t = 0; t < 27; t++) {
+            int pt = __shfl_sync(FULL, p, t);
+            if (pt == 0) continue;
+            int ex = __shfl_sync(FULL, excl, t), stt = __shfl_sync(FULL, st, t);
+            int hi = min(ex + pt, C);
+            for (int k = ex + lane; k < hi; k += 32) {
+                int j = stt + (k - ex);
+                float4 pj = a.A.posd[j], vj = a.A.velp[j];
+                float dj = fabsf(pj.w);
+                vj.w = vj.w / (dj * dj);              // press / powf(dens, 2), cu:310
+                S.sp[k] = pj;
+                S.sv[k] = vj;
+                S.sf[k] = a.A.mix[j].y;
+                S.tag[k] = (unsigned char)t;
+            }
+        }
+        __syncwarp();
+
+        for (int ig = 0; ig < hn; ig += 32) {
+            const int gcount = min(32, hn - ig);
+            float s_nd = 0.f, s_x = 0.f, s_y = 0.f, s_z = 0.f, s_dx = 0.f, s_dy = 0.f, s_dz = 0.f, s_df = 0.f;
+#pragma unroll 1
+            for (int il = 0; il < gcount; il++) {
+                const int i = hs + ig + il;
+                const float4 pi = a.A.posd[i], vi = a.A.velp[i];
+                const float4 mi = a.A.mix[i];
+                const float densi = fabsf(pi.w);
+                const bool bi = pi.w < 0.f;
+                const float pod2i = vi.w / (densi * densi);
+                const float solid_i = mi.x, fluid_i = mi.y;
+                const unsigned allow = split ? uni_octant_mask(uni_subindex(d, pi.x, pi.y, pi.z)) : 0x7ffffffu;
+                int qn = 0, ntest = 0;
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    int c = c0 + lane;
+                    bool ok = false, in = false;
+                    if (c < C) {
+                        ok = (allow >> S.tag[c]) & 1u;
+                        float4 pj = S.sp[c];
+                        float d2 = dist2(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+                        in = ok && (d2 <= d.d2_max) && (d2 > 0.f);       // cu:287
+                    }
+                    unsigned mk = __ballot_sync(FULL, in);
+                    if (in) S.q[qn + __popc(mk & lt_mask)] = (unsigned short)c;
+                    qn += __popc(mk);
+                    if (STATS) ntest += __popc(__ballot_sync(FULL, ok));
+                }
+                if (STATS && lane == 0) { st_tested += ntest; st_in += qn; }
+                __syncwarp();
+                float t_nd = 0.f, t_x = 0.f, t_y = 0.f, t_z = 0.f, t_dx = 0.f, t_dy = 0.f, t_dz = 0.f, t_df = 0.f;
+                for (int q = lane; q < qn; q += 32) {
+                    const int c = S.q[q];
+                    const float4 pj = S.sp[c], vj = S.sv[c];
+                    const float fluid_j = S.sf[c];
+                    const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+                    const float ds = sqrtf(dist2(rx, ry, rz));
+                    const float densj = fabsf(pj.w);
+                    const bool bj = pj.w < 0.f;
+                    // W(ds), FluidGPU-unidyn.cu:11-21
+                    float w;
+                    const float qq = ds * d.inv_h;
+                    if (ds <= d.h_le) w = d.w_c * (1.f - 1.5f * qq * qq + 0.75f * qq * qq * qq);
+                    else if (ds <= d.twoh_lt) { float tt = 2.f - qq; w = d.w_c * 0.25f * tt * tt * tt; }
+                    else w = 0.f;
+                    t_nd += w * ((!bi && bj) ? 2.5f : 1.f);                         // cu:362 (mass == 1)
+                    if (ds <= d.h_lt) {                                             // support of dW, cu:35-43
+                        const float tt = d.hf - ds;
+                        const float g = d.dw_c * tt * tt / ds;
+                        const float dkx = g * rx, dky = g * ry, dkz = g * rz;       // cu:296-298
+                        const float vabx = vi.x - vj.x, vaby = vi.y - vj.y, vabz = vi.z - vj.z;
+                        const float dd = vabx * rx + vaby * ry + vabz * rz;         // cu:304
+                        float s = 0.f;
+                        if (dd < 0.f) {                                             // cu:307
+                            const float mu = dd / (ds * ds + d.eps);
+                            const float hm = d.hf * mu;
+                            const float bf = (!bi && bj) ? 1.f + (1.f + 3.f * fluid_i * fluid_i) * alpha_sb : 1.f;
+                            s = ((solid_i * 9.f + 1.f) * (float)d.alpha_fluid) * (float)d.sound * (hm + d.visc_q * hm * hm) /
+                                ((densi + densj) * 0.5f) * bf;
+                        }
+                        const float pp = vj.w + pod2i + s;                          // cu:310-312
+                        t_x += pp * dkx;
+                        t_y += pp * dky;
+                        t_z += pp * dkz;
+                        if (!bi && !bj) {
+                            const float inv = 1.f / densj;
+                            t_dx += inv * dkx;                                      // cu:364-366
+                            t_dy += inv * dky;
+                            t_dz += inv * dkz;
+                            t_df += -0.5f * inv * (fluid_i + fluid_j) * (dkx * vabx + dky * vaby + dkz * vabz);   // cu:401
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    t_nd += __shfl_xor_sync(FULL, t_nd, o);
+                    t_x += __shfl_xor_sync(FULL, t_x, o);
+                    t_y += __shfl_xor_sync(FULL, t_y, o);
+                    t_z += __shfl_xor_sync(FULL, t_z, o);
+                    t_dx += __shfl_xor_sync(FULL, t_dx, o);
+                    t_dy += __shfl_xor_sync(FULL, t_dy, o);
+                    t_dz += __shfl_xor_sync(FULL, t_dz, o);
+                    t_df += __shfl_xor_sync(FULL, t_df, o);
+                }
+                if (lane == il) { s_nd = t_nd; s_x = t_x; s_y = t_y; s_z = t_z; s_dx = t_dx; s_dy = t_dy; s_dz = t_dz; s_df = t_df; }
+                __syncwarp();
+            }
+            if (lane < gcount) {
+                a.sums[hs + ig + lane] = make_float4(s_nd, s_x, s_y, s_z);
+                a.sums2[hs + ig + lane] = make_float4(s_dx, s_dy, s_dz, s_df);
+            }
+        }
+        __syncwarp();
+    }
+    if (STATS && lane == 0) {
+        atomicAdd(a.stats + 0, st_tested);
+        atomicAdd(a.stats + 1, st_in);
+    }
+    if (lane == 0 && st_drop) atomicAdd(a.stats + 2, st_drop);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mykernel2 (cu:451-497) + Particle::update(t) (cuh:296-423) + cell_calc (cu:544-551), per sorted slot.
+// Follows the reference's float / double promotions expression by expression.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_update_unidyn(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B, int *__restrict__ keysB,
+                const float4 *__restrict__ sums, const float4 *__restrict__ sums2, const float4 *__restrict__ carry, float *__restrict__ vizb)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 pd = A.posd[i], vp = A.velp[i], af = A.accf[i], dpi = A.dpi[i], mx = A.mix[i];
+    int key = keysA[i];
+    float b3 = 0.f;
+    if (key < d.numcells) {
+        float4 s = sums[i], s2 = sums2[i];
+        if (carry) { float4 cy = carry[i]; s.x += cy.x; s.y += cy.y; s.z += cy.z; s.w += cy.w; }
+        const float diffx = s2.x, diffy = s2.y, diffz = s2.z;
+        float delfluid = s2.w;
+        const float delsolid = 0.f;
+        b3 = diffx * diffx + diffy * diffy + diffz * diffz;                  // cu:466
+        const bool bnd = pd.w < 0.f;
+        float solid = mx.x, fluid = mx.y;
+        const double DT = d.dt;
+        // set_dens cuh:183-185, calculate_pressure cuh:282-284 (double pow; RHO_0_SAND == RHO_0)
+        const float dens = (float)((double)(s.x + d.w0) / 23.0 * (double)(1 + (float)bnd * 1.5) + 9250);
+        const double eos = pow((double)(dens / 9550), 7.0) - 1;
+        const float press = (float)((double)((1 - solid) * 1000) * 1.0 * 9550 / 7.0 * eos + (double)(solid * 1000) * 1.0 * 9550 / 7.0 * eos);
+        dpi.x = s.y; dpi.y = s.z; dpi.z = s.w;                                // set_delpress cuh:302
+        if (!bnd) {
+            const float friction = fabsf(diffx) + fabsf(diffy) + fabsf(diffz);   // cuh:311
+            solid = (float)((double)solid + DT * (double)delsolid);           // :312-313
+            solid *= (solid >= 0.0);
+            if ((double)(fluid + delfluid) < 0.2) delfluid = 0;               // :315
+            fluid = (float)((double)fluid + DT * (double)delfluid);           // :316-317
+            fluid *= (fluid >= 0);
+            fluid *= 1 / (fluid + solid);                                     // :319-320
+            solid *= 1 / (fluid + solid);
+            float x = (float)((double)pd.x + DT * (double)vp.x + 0.5 * DT * DT * (double)af.x + (double)(0 * diffx));   // :328-330
+            float y = (float)((double)pd.y + DT * (double)vp.y + 0.5 * DT * DT * (double)af.y + (double)(0 * diffy));
+            float z = (float)((double)pd.z + DT * (double)vp.z + 0.5 * DT * DT * (double)af.z + (double)(0 * diffz));
+            float vx = vp.x, vy = vp.y, vz = vp.z;
+            if ((double)z < -0.89) { vx = 0; vy = 0; }                        // :332-341
+            // :351-353 — stress_accel == mixture_accel == 0 in scope; the y and z lines test the NEW xvel (sic)
+            const double fr = (double)friction * 0.0000002 * (double)solid;
+            double tx = (double)vx + DT * (double)af.x;
+            vx = (float)(((double)vx + 0.5 * DT * (double)af.x) - (tx > 0) * fr + (tx < 0) * fr);
+            tx = (double)vx + DT * (double)af.x;
+            vy = (float)(((double)vy + 0.5 * DT * (double)af.y) - (tx > 0) * fr + (tx < 0) * fr);
+            vz = (float)(((double)vz + 0.5 * DT * (double)af.z) - (tx > 0) * fr + (tx < 0) * fr);
+            af.x = (float)(-((220.0 - 70.0 * (double)solid) / (double)dens) * (double)dpi.x);     // :357-359
+            af.y = (float)(-((220.0 - 70.0 * (double)solid) / (double)dens) * (double)dpi.y);
+            af.z = (float)(d.gravity + ((-220.0 + 70.0 * (double)solid) / (double)dens) * (double)dpi.z);
+            vx = (float)((double)vx + 0.5 * (double)af.x * DT);                // :390-392
+            vy = (float)((double)vy + 0.5 * (double)af.y * DT);
+            vz = (float)((double)vz + 0.5 * (double)af.z * DT);
+            if ((double)fabsf(z) > 0.98) { z = (float)(0.97 / (double)z); vz = 0; }               // :404-413
+            if ((double)fabsf(y) > 0.98) vy = -vy;
+            if ((double)fabsf(x) > 0.98) vx = -vx;
+            pd.x = x; pd.y = y; pd.z = z;
+            vp.x = vx; vp.y = vy; vp.z = vz;
+            mx.x = solid; mx.y = fluid;
+        }
+        pd.w = bnd ? -dens : dens;
+        vp.w = press;
+        key = bin_id(d, pd.x, pd.y, pd.z);                                    // cell_calc, cu:547
+    }
+    B.posd[i] = pd;
+    B.velp[i] = vp;
+    B.accf[i] = af;
+    B.dpi[i] = dpi;
+    B.mix[i] = mx;
+    keysB[i] = key;
+    vizb[i] = b3;
+}
+
+// split[] as mykernel leaves it (cu:181-190): bin id for bins with more than 6 particles, else -1
+__global__ void k_split_table(int numcells, const int *__restrict__ start, const int *__restrict__ end, int *split)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= numcells) return;
+    int s0 = start[c];
+    split[c] = (s0 >= 0 && end[c] - s0 + 1 > 6) ? c : -1;
+}
+
+cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work, const float4 *carry,
+                              int *launches, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_pair_unidyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
+        cudaFuncSetAttribute(k_pair_unidyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
+        attr_done = true;
+    }
+    UniArgs a;
+    a.d = c->dev;
+    a.n = (int)n;
+    a.start = c->start;
+    a.end = c->end;
+    a.binlist = binlist;
+    a.nocc = nocc;
+    a.work = work;
+    a.A = c->A;
+    a.sums = c->sums;
+    a.sums2 = c->sums2;
+    a.stats = c->dstats;
+    int64_t blocks = (n + UNI_WARPS - 1) / UNI_WARPS;
+    int64_t maxb = (int64_t)c->sm_count * 2;
+    if (blocks > maxb) blocks = maxb;
+    if (c->cfg.collect_stats) k_pair_unidyn<true><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, s>>>(a);
+    else k_pair_unidyn<false><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_update_unidyn<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->dev, (int)n, c->keysA, c->A, c->B, c->keysB, c->sums, c->sums2, carry,
+                                                              c->vizb);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t fsg_launch_split_table(const fsg_ctx *c, int *split, cudaStream_t s)
+{
+    const int nc = c->dev.numcells;
+    k_split_table<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(nc, c->start, c->end, split);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// AoS <-> SoA for the unidyn Particle record (offsets: FluidGPU-unidyn.cuh:119-181 as laid out by nvcc,
+// sizeof == 340)
+// ------------------------------------------------------------------------------------------------
+namespace aos_uni {
+enum { POS = 0, VEL = 12, ACC = 36, INDEX = 60, CELL = 64, SUBINDEX = 68, MASS = 72, DENS = 76, PRESS = 80, DELP_Z = 84, DELP_Y = 88,
+       DELP_X = 92, DIFFUSION = 96, NEWDENS = 108, NDELP_Z = 112, NDELP_Y = 116, NDELP_X = 120, BOUNDARY = 316, SOLID = 320, FLUID = 324,
+       DELSOLID = 328, DELFLUID = 332, FLAG = 336, SPLIT = 337 };
+}
+__device__ __forceinline__ float uldf(const unsigned char *r, int off) { return *reinterpret_cast<const float *>(r + off); }
+__device__ __forceinline__ void ustf(unsigned char *r, int off, float v) { *reinterpret_cast<float *>(r + off) = v; }
+
+__global__ void k_unpack_aos_unidyn(const unsigned char *__restrict__ aos, int64_t n, FsgState st, float4 *carry, int *bad)
+{
+    using namespace aos_uni;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char *r = aos + i * FSG_AOS_STRIDE;
+    bool bnd = r[BOUNDARY] != 0;
+    float dens = uldf(r, DENS), solid = uldf(r, SOLID);
+    st.posd[i] = make_float4(uldf(r, POS), uldf(r, POS + 4), uldf(r, POS + 8), bnd ? -dens : dens);
+    st.velp[i] = make_float4(uldf(r, VEL), uldf(r, VEL + 4), uldf(r, VEL + 8), uldf(r, PRESS));
+    st.accf[i] = make_float4(uldf(r, ACC), uldf(r, ACC + 4), uldf(r, ACC + 8), __int_as_float(bnd ? 1 : 0));
+    st.dpi[i] = make_float4(uldf(r, DELP_X), uldf(r, DELP_Y), uldf(r, DELP_Z), __int_as_float(*reinterpret_cast<const int *>(r + INDEX)));
+    st.mix[i] = make_float4(solid, uldf(r, FLUID), 0.f, 0.f);
+    carry[i] = make_float4(uldf(r, NEWDENS), uldf(r, NDELP_X), uldf(r, NDELP_Y), uldf(r, NDELP_Z));
+    if ((!bnd && solid != 0.f) || uldf(r, MASS) != 1.f) atomicOr(bad, 1);
+}
+
+__global__ void k_pack_aos_unidyn(unsigned char *__restrict__ aos, int64_t n, FsgState st, const float4 *carry, const int *keys, FsgDev d)
+{
+    using namespace aos_uni;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned char *r = aos + i * FSG_AOS_STRIDE;
+    for (int o = 0; o < FSG_AOS_STRIDE; o += 4) *reinterpret_cast<int *>(r + o) = 0;
+    float4 pd = st.posd[i], vp = st.velp[i], af = st.accf[i], dpi = st.dpi[i], mx = st.mix[i];
+    ustf(r, POS, pd.x); ustf(r, POS + 4, pd.y); ustf(r, POS + 8, pd.z);
+    ustf(r, VEL, vp.x); ustf(r, VEL + 4, vp.y); ustf(r, VEL + 8, vp.z);
+    ustf(r, ACC, af.x); ustf(r, ACC + 4, af.y); ustf(r, ACC + 8, af.z);
+    *reinterpret_cast<int *>(r + INDEX) = __float_as_int(dpi.w);
+    *reinterpret_cast<int *>(r + CELL) = keys[i];
+    *reinterpret_cast<int *>(r + SUBINDEX) = uni_subindex(d, pd.x, pd.y, pd.z);
+    ustf(r, MASS, 1.f);
+    ustf(r, DENS, fabsf(pd.w));
+    ustf(r, PRESS, vp.w);
+    ustf(r, DELP_X, dpi.x); ustf(r, DELP_Y, dpi.y); ustf(r, DELP_Z, dpi.z);
+    float4 cy = carry ? carry[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    ustf(r, NEWDENS, cy.x);
+    ustf(r, NDELP_X, cy.y); ustf(r, NDELP_Y, cy.z); ustf(r, NDELP_Z, cy.w);
+    r[BOUNDARY] = pd.w < 0.f ? 1 : 0;
+    ustf(r, SOLID, mx.x);
+    ustf(r, FLUID, mx.y);
+    r[FLAG] = 1;                                     // update() leaves flag = true, cuh:422
+}
+
+cudaError_t fsg_launch_unpack_aos_unidyn(const unsigned char *aos, int64_t n, FsgState st, float4 *carry, int *bad, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_unpack_aos_unidyn<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(aos, n, st, carry, bad);
+    return cudaGetLastError();
+}
+cudaError_t fsg_launch_pack_aos_unidyn(unsigned char *aos, int64_t n, FsgState st, const float4 *carry, const int *keys, const FsgDev &d,
+                                       cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_pack_aos_unidyn<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(aos, n, st, carry, keys, d);
+    return cudaGetLastError();
+}

@@ -94,3 +94,34 @@ def plume_scene(cfg, spacing: float = 0.05, jitter: float = 0.005, seed: int = 2
     if rc != 0:
         raise _lib.FsgError(rc, "fsg_scene_plume_host")
     return default_state(pos, vel)
+
+
+def unidyn_default_scene() -> dict:
+    """solver-unidyn.cu:124-185 — 10 000 fluid particles (30 x 30 x 12 lattice, spacing 0.05) over a floor
+    (2 020) and four walls (4 x 505) of boundary particles; solid/fluid = 0/1 for fluid, 1/0 for boundary."""
+    nspts, nbpts = 10000, 4040
+    j = np.arange(nspts)
+    fx = -.76 + 0.05 * ((j // 30) % 30)
+    fy = -0.76 + 0.05 * (j % 30)
+    fz = -0.40 + (j // 30 // 30) * 0.05
+    i = np.arange(nbpts // 2)
+    floor = np.stack([-0.96 + 0.04 * (i % 45), -0.96 + 0.04 * (i // 45), np.full(i.shape, -0.7)], 1)
+    i = np.arange(nbpts // 8)
+    a, b = -0.96 + 0.04 * (i % 45), -0.74 + 0.04 * (i // 45)
+    walls = [np.stack([a, np.full(i.shape, -0.96), b], 1), np.stack([a, np.full(i.shape, 0.84), b], 1),
+             np.stack([np.full(i.shape, -0.96), a, b], 1), np.stack([np.full(i.shape, 0.76), a, b], 1)]
+    pos = np.concatenate([np.stack([fx, fy, fz], 1), floor] + walls).astype(np.float32)
+    bnd = np.r_[np.zeros(nspts, np.uint8), np.ones(nbpts, np.uint8)]
+    st = default_state(pos, boundary=bnd)
+    st["solid"] = bnd.astype(np.float32)
+    st["fluid"] = (1 - bnd).astype(np.float32)
+    return st
+
+
+def random_unidyn_scene(n: int, seed: int, boundary_frac: float = 0.1, vel_scale: float = 0.2) -> dict:
+    """Seeded jittered lattice in the unidyn domain (CELLSIZE 0.12): fluid particles + boundary particles."""
+    st = random_base_scene(n, seed, box=((-0.5, 0.5),) * 3, spacing=0.05, jitter=0.012, vel_scale=vel_scale, boundary_frac=boundary_frac)
+    st["solid"] = st["boundary"].astype(np.float32)
+    st["fluid"] = (1 - st["boundary"]).astype(np.float32)
+    st["vel"][st["boundary"] != 0] = 0
+    return st

@@ -18,6 +18,7 @@ from ._lib import FsgConfig, FsgError, FsgSoa, FsgStats
 
 _F3 = ("pos", "vel", "acc", "delpress", "newdelpress")
 _F1 = ("dens", "press", "newdens")
+_FU = ("solid", "fluid")      # unidyn model only
 
 
 class FluidSolver:
@@ -41,6 +42,21 @@ class FluidSolver:
         for k, v in kw.items():
             setattr(cfg, k, v)
         return cfg
+
+    @staticmethod
+    def unidyn_config(capacity: int = 14040, device: int = 0, **kw) -> FsgConfig:
+        """FluidGPU-unidyn.cuh:1-36 constants (GRIDSIZE 17, CELLSIZE 0.12, DT 0.0018, ...)."""
+        cfg = FsgConfig()
+        _lib.load().fsg_config_default(C.byref(cfg), _lib.FSG_MODEL_UNIDYN)
+        cfg.capacity = capacity
+        cfg.device = device
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        return cfg
+
+    @property
+    def is_unidyn(self) -> bool:
+        return self.cfg.model == _lib.FSG_MODEL_UNIDYN
 
     @property
     def numcells(self) -> int:
@@ -74,7 +90,7 @@ class FluidSolver:
         soa = FsgSoa()
         soa.n = n
         keep = []
-        for k in _F3 + _F1:
+        for k in _F3 + _F1 + (_FU if self.is_unidyn else ()):
             if state.get(k) is not None:
                 a = np.ascontiguousarray(state[k], np.float32)
                 keep.append(a)
@@ -97,11 +113,11 @@ class FluidSolver:
         n = st["n"]
         out = {}
         soa = FsgSoa()
-        fields = fields or (_F3 + _F1 + ("index", "cell", "boundary"))
+        fields = fields or (_F3 + _F1 + ("index", "cell", "boundary") + (_FU if self.is_unidyn else ()))
         for k in fields:
             if k in _F3:
                 out[k] = np.empty((n, 3), np.float32)
-            elif k in _F1:
+            elif k in _F1 or k in _FU:
                 out[k] = np.empty(n, np.float32)
             elif k in ("index", "cell"):
                 out[k] = np.empty(n, np.int32)
@@ -146,6 +162,12 @@ class FluidSolver:
         end = np.empty(self.numcells, np.int32)
         self._check(self._lib.fsg_get_tables(self._ctx, cells.ctypes.data, start.ctypes.data, end.ctypes.data), "fsg_get_tables")
         return cells, start, end
+
+    def split(self) -> np.ndarray:
+        """unidyn: split[] of the last step (FluidGPU-unidyn.cu:181-190)."""
+        out = np.empty(self.numcells, np.int32)
+        self._check(self._lib.fsg_get_split(self._ctx, out.ctypes.data), "fsg_get_split")
+        return out
 
     def stats(self) -> dict:
         st = FsgStats()

@@ -99,6 +99,9 @@ typedef struct fsg_soa {
     int32_t *index;      /* [n] Particle::index (NULL on upload: 0..n-1) */
     int32_t *cell;       /* [n] Particle::cellnumber (download only; recomputed on upload, solver.cu:119) */
     uint8_t *boundary;   /* [n]                            */
+    /* unidyn model only (FluidGPU-unidyn.cuh:180-181); NULL on upload: 0/1 for fluid, 1/0 for boundary particles */
+    float  *solid;       /* [n] */
+    float  *fluid;       /* [n] */
 } fsg_soa;
 
 typedef struct fsg_ctx fsg_ctx;
@@ -145,6 +148,9 @@ FSG_API int  fsg_export_viz(fsg_ctx *ctx, float *spts, float *a3, float *b3);
 /* The integer tables of the LAST step as the pair kernel saw them (host pointers, may be NULL):
  * cells[n] sorted keys, start/end[numcells] (FluidGPU.cu:106-117; -1 = empty bin). */
 FSG_API int  fsg_get_tables(fsg_ctx *ctx, int32_t *cells, int32_t *start, int32_t *end);
+/* unidyn: split[numcells] as mykernel leaves it (FluidGPU-unidyn.cu:181-190) — the bin id for bins with more
+ * than 6 particles in the LAST step (their particles only see the 8 bins of their octant), else -1. */
+FSG_API int  fsg_get_split(fsg_ctx *ctx, int32_t *split);
 FSG_API int  fsg_get_stats(fsg_ctx *ctx, fsg_stats *out);
 /* Switches the pair counters (fsg_config.collect_stats) on or off for the following steps. */
 FSG_API int  fsg_set_collect_stats(fsg_ctx *ctx, int on);

@@ -85,6 +85,27 @@ int fsgo_base_step(const fsgo_params *p, fsgo_state *s,
                    int *cells_sorted, int *start, int *end,
                    float *spts, float *a3, float *b3, long long *stats);
 
+/* ---- unidyn model (FluidGPU-unidyn.cu / .cuh), see fsg_oracle_unidyn.c ---- */
+void fsgo_params_unidyn(fsgo_params *p);   /* FluidGPU-unidyn.cuh:1-36; alpha_boundary = ALPHA__SAND_BOUNDARY */
+
+typedef struct fsgo_ustate {
+    int    n;
+    float *pos, *vel, *acc, *dens, *press, *delpress, *newdens, *newdelpress;   /* as fsgo_state */
+    int   *index, *cell;
+    unsigned char *boundary;
+    float *solid;      /* [n] FluidGPU-unidyn.cuh:180 */
+    float *fluid;      /* [n] :181 */
+    int   *subindex;   /* [n] octant of the particle inside a split bin (:119, FluidGPU-unidyn.cu:182-184) */
+} fsgo_ustate;
+
+/* One pass of the solver-unidyn.cu:313-573 loop body on one device: sort (:331) -> count_after_merge (:341)
+ * -> findneighbours (:354) -> mykernel (:363) -> mykernel3 (:379) -> mykernel2 (:389) -> cell_calc (:548).
+ * split_out[numcells]: split[] as mykernel leaves it (bin id for bins with more than 6 particles, else -1).
+ * viz: spts = pre-update positions, a3 = mass, b3 = |diffusion|^2 (FluidGPU-unidyn.cu:462-466).
+ * Returns 0; -1 allocation failure; -2 scene outside the restated scope (see fsg_oracle_unidyn.c). */
+int fsgo_unidyn_step(const fsgo_params *p, fsgo_ustate *s, int t, int *cells_sorted, int *start, int *end, int *split,
+                     float *spts, float *a3, float *b3, long long *stats);
+
 #ifdef __cplusplus
 }
 #endif

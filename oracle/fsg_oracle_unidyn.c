@@ -1,0 +1,391 @@
+/*
+ * fsg_oracle_unidyn.c — CPU restatement of FluidSolverGPU's "unidyn" per-timestep particle update
+ * (FluidGPU-unidyn.cu / FluidGPU-unidyn.cuh, driven by solver-unidyn.cu:313-573).
+ *
+ * TEST INFRASTRUCTURE ONLY (see fsg_oracle.h).  Every function cites the reference file:line it follows.
+ *
+ * Scope of the restatement: scenes in which every non-boundary particle is pure fluid (solid == 0)
+ * and mass == 1 — the default scene of solver-unidyn.cu:127-184 and anything built like it.  For such
+ * scenes the mixed-phase block (FluidGPU-unidyn.cu:317-357), mixfactor (:368), vel_grad (:369-377),
+ * stress_accel (:379-381), mixture_accel (:391-398), delsolid (:400) and the granular stress update
+ * (:410-446) contribute exactly zero, merging is unreachable (`ds <= -10 && ds > 0`, :261) and
+ * splitting needs mass > 3 (:278); the live sums are newdens, newdelpress, diffusion and delfluid.
+ * fsgo_unidyn_step returns -2 for a scene outside that scope.
+ */
+#include "fsg_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+void fsgo_params_unidyn(fsgo_params *p)
+{
+    p->grid = 17;               /* GRIDSIZE   FluidGPU-unidyn.cuh:8  */
+    p->origin = -1.0f;          /* XMIN       :1 */
+    p->cellsize = 0.12;         /* CELLSIZE   :7 */
+    p->h = 0.06;                /* cutoff     :35 */
+    p->dt = 0.0018;             /* DT         :36 */
+    p->alpha_fluid = -0.0155e1; /* :17 */
+    p->alpha_boundary = 100e-1; /* ALPHA__SAND_BOUNDARY :21 — the factor the unidyn pair term uses (FluidGPU-unidyn.cu:307) */
+    p->sound = 1450.0;          /* :11 */
+    p->gravity = -9.8;          /* :10 */
+    p->block_threads = 1024;    /* solver-unidyn.cu:363 */
+    p->bin_cap = 0;
+    p->threads = 0;
+}
+
+/* FluidGPU-unidyn.cuh:183-185 */
+static float u_set_dens(float x, int boundary, double h)
+{
+    return (x + fsgo_kernel_h(0, h)) / 23.0 * (1 + (float)(boundary != 0) * 1.5) + 9250;
+}
+/* FluidGPU-unidyn.cuh:282-284: double pow, blended by `solid` (RHO_0_SAND == RHO_0) */
+static float u_pressure(float dens, float solid, double sound)
+{
+    return (1 - solid) * 1000 * pow(sound, 0) * 9550 / 7.0 * (pow(dens / 9550, 7) - 1) +
+           (solid) * 1000 * pow(sound, 0) * 9550 / 7.0 * (pow(dens / 9550, 7) - 1);
+}
+
+typedef struct { float dens, px, py, pz, dx, dy, dz, delfluid; } upair_acc;
+
+/* pair body, FluidGPU-unidyn.cu:258-401 (== :679-821 of mykernel3), live terms only */
+static inline void upair_body(const fsgo_params *P, const fsgo_ustate *s, int i, int j, upair_acc *a, long long *st)
+{
+    const double cutoff = P->h;
+    const float *pi = s->pos + 3 * (size_t)i, *pj = s->pos + 3 * (size_t)j;
+    float rabx = pi[0] - pj[0], raby = pi[1] - pj[1], rabz = pi[2] - pj[2];
+    float ds = sqrt(powf(rabx, 2) + powf(raby, 2) + powf(rabz, 2));   /* cuh:211-213: double sqrt of a float sum, narrowed */
+    st[0]++;
+    if (ds <= (2 * cutoff) && ds > 0) {                                /* cu:287 */
+        st[1]++;
+        float k = fsgo_kernel_h(ds, cutoff);
+        const float *vi = s->vel + 3 * (size_t)i, *vj = s->vel + 3 * (size_t)j;
+        float vabx = vi[0] - vj[0], vaby = vi[1] - vj[1], vabz = vi[2] - vj[2];
+        float dkx = fsgo_kernel_derivative_h(ds, cutoff) * rabx / ds;  /* cu:296-298 */
+        float dky = fsgo_kernel_derivative_h(ds, cutoff) * raby / ds;
+        float dkz = fsgo_kernel_derivative_h(ds, cutoff) * rabz / ds;
+        float d = vabx * rabx + vaby * raby + vabz * rabz;             /* cu:304 */
+        float d2 = powf(ds, 2);                                        /* cu:305 */
+        int bi = s->boundary[i] != 0, bj = s->boundary[j] != 0;
+        float di = s->dens[i], dj = s->dens[j];
+        float solid_i = s->solid[i], fluid_i = s->fluid[i];
+        const float mass = 1.0f;
+        /* cu:307 */
+        float sv = (((solid_i * 9 + 1) * P->alpha_fluid) * P->sound *
+                    (powf(mass, 1) * cutoff * (d / (d2 + 0.01 * powf(cutoff, 2))) +
+                     50 * 1.0 / P->sound * powf(cutoff * (d / (d2 + 0.01 * powf(cutoff, 2))), 2)) /
+                    ((di + dj) / 2.0)) *
+                   (d < 0) * (1 + (!bi) * (bj) * ((1 + 3 * fluid_i * fluid_i) * P->alpha_boundary));
+        float pp = s->press[j] / powf(dj, 2) + s->press[i] / powf(di, 2) + sv;   /* cu:310-312 */
+        float dpx = pp * dkx, dpy = pp * dky, dpz = pp * dkz;
+        a->px += dpx * mass;                                           /* cu:358-360 */
+        a->py += dpy * mass;
+        a->pz += dpz * mass;
+        a->dens += (float)(k * (1 + (float)(!bi) * (float)(bj) * 1.5) * mass);   /* cu:362 */
+        a->dx += mass / dj * dkx * !bj * !bi;                          /* cu:364-366 */
+        a->dy += mass / dj * dky * !bj * !bi;
+        a->dz += mass / dj * dkz * !bj * !bi;
+        /* cu:401 with zero drift velocities: (!bj)(!bi) * -0.5/dens_j * (fluid_i+fluid_j) * (dk . vab) + (-0...)/dens_j */
+        a->delfluid += (float)((!bj) * (!bi) * -0.5 / dj * (fluid_i + s->fluid[j]) * (dkx * vabx + dky * vaby + dkz * vabz) +
+                               (-(fluid_i * 0.0f + s->fluid[j] * 0.0f) * dkx - (fluid_i * 0.0f + s->fluid[j] * 0.0f) * dky -
+                                (fluid_i * 0.0f + s->fluid[j] * 0.0f) * dkz) / dj);
+    }
+}
+
+/* thread -> neighbour particle map of mykernel / mykernel3 (cu:196-241, :606-666) over `nn` bin offsets */
+static int ucandidates(const fsgo_params *P, int bidx, const int *nb, int nn, const int *start, const int *end, int n,
+                       int *cand, int cand_max, long long *dropped)
+{
+    const int G = P->grid, numcells = G * G * G;
+    int p[27], pidx[27];
+    long long all = 0;
+    int total = 0;
+    for (int t = 0; t < nn; t++) {
+        p[t] = 0;
+        pidx[t] = 0;
+        int c = bidx + nb[t];
+        if (c >= 0 && c < numcells && start[c] >= 0 && end[c] >= 0 && start[c] < n && 1 + end[c] - start[c] > 0) {
+            p[t] = 1 + end[c] - start[c];
+            pidx[t] = t;
+            all += p[t];
+            total += p[t];
+        }
+    }
+    int count = 0;
+    for (int t = 0; t < nn; t++)
+        if (p[t] != 0) {
+            p[count] = p[t];
+            pidx[count] = pidx[t];
+            count++;
+        }
+    for (int t = count; t < nn; t++) p[t] = pidx[t] = 0;
+    int nthreads = total;
+    if (P->block_threads > 0 && nthreads > P->block_threads) nthreads = P->block_threads;
+    if (nthreads > cand_max) nthreads = cand_max;
+    int used = 0;
+    for (int tidx = 0; tidx < nthreads; tidx++) {
+        int sum = 0, jj = 0;
+        while (tidx + 1 > sum && jj < nn) {
+            sum += p[jj];
+            jj++;
+        }
+        int c = bidx + nb[pidx[jj - 1]];
+        int j = -1;
+        if (c >= 0 && c < numcells) {
+            j = start[c] + sum - (tidx + 1);
+            if (!(start[c] >= 0 && j < n && j >= 0)) j = -1;
+        }
+        cand[used++] = j;
+    }
+    if (dropped) *dropped += all - used;
+    return used;
+}
+
+static void permute_f(float *a, const int *perm, int n, int w, float *tmp)
+{
+    for (int i = 0; i < n; i++)
+        for (int c = 0; c < w; c++) tmp[(size_t)i * w + c] = a[(size_t)perm[i] * w + c];
+    memcpy(a, tmp, sizeof(float) * (size_t)n * w);
+}
+
+int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sorted, int *start_out, int *end_out,
+                     int *split_out, float *spts, float *a3, float *b3, long long *stats)
+{
+    (void)t;
+    const int n = s->n, G = P->grid, numcells = G * G * G;
+    int rc = -1;
+    /* scope check */
+    for (int i = 0; i < n; i++)
+        if (!s->boundary[i] && s->solid[i] != 0.0f) return -2;
+
+    int *perm = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    float *tmp = (float *)malloc(sizeof(float) * 3 * (size_t)(n > 0 ? n : 1));
+    int *start = (int *)malloc(sizeof(int) * (size_t)numcells);
+    int *end = (int *)malloc(sizeof(int) * (size_t)numcells);
+    int *split = (int *)malloc(sizeof(int) * (size_t)numcells);
+    int *cnt = (int *)calloc((size_t)numcells + 2, sizeof(int));
+    upair_acc *acc = (upair_acc *)calloc((size_t)(n > 0 ? n : 1), sizeof(upair_acc));
+    int *occ = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    long long st[4] = {0, 0, 0, 0};
+    if (!perm || !tmp || !start || !end || !split || !cnt || !acc || !occ) goto done;
+
+    /* ---- solver-unidyn.cu:331 stable sort by cell id (out-of-grid ids last) ---- */
+    for (int i = 0; i < n; i++) {
+        int k = s->cell[i];
+        if (k < 0 || k >= numcells) k = numcells;
+        cnt[k + 1]++;
+    }
+    for (int c = 0; c <= numcells; c++) cnt[c + 1] += cnt[c];
+    for (int i = 0; i < n; i++) {
+        int k = s->cell[i];
+        if (k < 0 || k >= numcells) k = numcells;
+        perm[cnt[k]++] = i;
+    }
+    permute_f(s->pos, perm, n, 3, tmp);
+    permute_f(s->vel, perm, n, 3, tmp);
+    permute_f(s->acc, perm, n, 3, tmp);
+    permute_f(s->dens, perm, n, 1, tmp);
+    permute_f(s->press, perm, n, 1, tmp);
+    permute_f(s->delpress, perm, n, 3, tmp);
+    permute_f(s->newdens, perm, n, 1, tmp);
+    permute_f(s->newdelpress, perm, n, 3, tmp);
+    permute_f(s->solid, perm, n, 1, tmp);
+    permute_f(s->fluid, perm, n, 1, tmp);
+    {
+        int *ti = (int *)tmp;
+        for (int i = 0; i < n; i++) ti[i] = s->index[perm[i]];
+        memcpy(s->index, ti, sizeof(int) * (size_t)n);
+        for (int i = 0; i < n; i++) ti[i] = s->cell[perm[i]];
+        memcpy(s->cell, ti, sizeof(int) * (size_t)n);
+        for (int i = 0; i < n; i++) ti[i] = s->subindex[perm[i]];
+        memcpy(s->subindex, ti, sizeof(int) * (size_t)n);
+        unsigned char *tb = (unsigned char *)tmp;
+        for (int i = 0; i < n; i++) tb[i] = s->boundary[perm[i]];
+        memcpy(s->boundary, tb, (size_t)n);
+    }
+    /* count_after_merge, FluidGPU-unidyn.cu:554-562: particles with cell >= NUMCELLS drop out */
+    int nlive = n;
+    while (nlive > 0 && (s->cell[nlive - 1] < 0 || s->cell[nlive - 1] >= numcells)) nlive--;
+
+    /* ---- findneighbours, FluidGPU-unidyn.cu:104-122 ---- */
+    for (int c = 0; c < numcells; c++) start[c] = end[c] = split[c] = -1;
+    int nocc = 0;
+    for (int i = 0; i < nlive; i++) {
+        if (i == 0 || s->cell[i] != s->cell[i - 1]) {
+            start[s->cell[i]] = i;
+            occ[nocc++] = s->cell[i];
+        }
+        if (i == nlive - 1 || s->cell[i] != s->cell[i + 1]) end[s->cell[i]] = i;
+    }
+    st[3] = nocc;
+    /* ---- split marking + octant subindex, FluidGPU-unidyn.cu:181-192 ---- */
+    for (int o = 0; o < nocc; o++) {
+        int b = occ[o];
+        int pop = 1 + end[b] - start[b];
+        if (pop > 6) {
+            split[b] = b;
+            for (int i = start[b]; i <= end[b]; i++) {
+                const float *x = s->pos + 3 * (size_t)i;
+                float fx = x[0] - P->origin, fy = x[1] - P->origin, fz = x[2] - P->origin;
+                /* int((x-XMIN)/CELLSIZE) == int((x-XMIN+CELLSIZE/2)/CELLSIZE): (x - XMIN) float, + 0.06 double */
+                int sx = (int)(fx / P->cellsize) == (int)((fx + P->cellsize / 2) / P->cellsize);
+                int sy = (int)(fy / P->cellsize) == (int)((fy + P->cellsize / 2) / P->cellsize);
+                int sz = (int)(fz / P->cellsize) == (int)((fz + P->cellsize / 2) / P->cellsize);
+                s->subindex[i] = 1 - sx + 2 - 2 * sy + 4 * sz;
+            }
+        }
+    }
+    if (cells_sorted) memcpy(cells_sorted, s->cell, sizeof(int) * (size_t)n);
+    if (start_out) memcpy(start_out, start, sizeof(int) * (size_t)numcells);
+    if (end_out) memcpy(end_out, end, sizeof(int) * (size_t)numcells);
+    if (split_out) memcpy(split_out, split, sizeof(int) * (size_t)numcells);
+
+    /* ---- mykernel (coarse bins) + mykernel3 (split bins, per octant) ---- */
+    {
+        int nthreads = P->threads;
+        (void)nthreads;
+        long long t0 = 0, t1 = 0, t2 = 0;
+#ifdef _OPENMP
+        if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads) reduction(+ : t0, t1, t2)
+#endif
+        {
+            int cand_max = 27 * 1024;
+            int *cand = (int *)malloc(sizeof(int) * (size_t)cand_max);
+            int nb27[27], k = 0;
+            for (int a = -1; a <= 1; a++)
+                for (int b = -1; b <= 1; b++)
+                    for (int c = -1; c <= 1; c++) nb27[k++] = a * G * G + b * G + c;     /* cu:130-132 */
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+            for (int o = 0; o < nocc; o++) {
+                int bidx = occ[o];
+                long long lst[2] = {0, 0}, drop = 0;
+                if (split[bidx] == -1) {
+                    int nc = ucandidates(P, bidx, nb27, 27, start, end, nlive, cand, cand_max, &drop);
+                    for (int i = start[bidx]; i <= end[bidx]; i++) {
+                        upair_acc a = {0, 0, 0, 0, 0, 0, 0, 0};
+                        for (int q = 0; q < nc; q++)
+                            if (cand[q] >= 0) upair_body(P, s, i, cand[q], &a, lst);
+                        acc[i] = a;
+                    }
+                } else {
+                    for (int oct = 0; oct < 8; oct++) {
+                        /* cu:579-583: pow(-1,1+dirx)*G*G etc.; z polarity is opposite (pow(-1,dirz)) */
+                        int dirx = oct & 1, diry = (oct & 2) >> 1, dirz = (oct & 4) >> 2;
+                        int ox = (dirx ? 1 : -1) * G * G, oy = (diry ? 1 : -1) * G, oz = dirz ? -1 : 1;
+                        int nb8[8] = {0, ox, oy, oz, ox + oy, ox + oz, oy + oz, ox + oy + oz};
+                        int any = 0;
+                        for (int i = start[bidx]; i <= end[bidx]; i++) any |= (s->subindex[i] == oct);
+                        if (!any) continue;
+                        int nc = ucandidates(P, bidx, nb8, 8, start, end, nlive, cand, cand_max, &drop);
+                        for (int i = start[bidx]; i <= end[bidx]; i++) {
+                            if (s->subindex[i] != oct) continue;
+                            upair_acc a = {0, 0, 0, 0, 0, 0, 0, 0};
+                            for (int q = 0; q < nc; q++)
+                                if (cand[q] >= 0) upair_body(P, s, i, cand[q], &a, lst);
+                            acc[i] = a;
+                        }
+                    }
+                }
+                t0 += lst[0];
+                t1 += lst[1];
+                t2 += drop;
+            }
+            free(cand);
+        }
+        st[0] = t0;
+        st[1] = t1;
+        st[2] = t2;
+    }
+
+    /* ---- mykernel2 (cu:451-497) + Particle::update(t) (cuh:296-423) + cell_calc (cu:544-551) ---- */
+    {
+        const double DT = P->dt;
+        for (int i = 0; i < nlive; i++) {
+            float *x = s->pos + 3 * (size_t)i, *v = s->vel + 3 * (size_t)i, *a = s->acc + 3 * (size_t)i;
+            float newdens = s->newdens[i] + acc[i].dens;
+            float ndx = s->newdelpress[3 * (size_t)i + 0] + acc[i].px, ndy = s->newdelpress[3 * (size_t)i + 1] + acc[i].py,
+                  ndz = s->newdelpress[3 * (size_t)i + 2] + acc[i].pz;
+            float diffx = acc[i].dx, diffy = acc[i].dy, diffz = acc[i].dz;
+            float delfluid = acc[i].delfluid, delsolid = 0.0f;
+            if (spts) { spts[3 * (size_t)i] = x[0]; spts[3 * (size_t)i + 1] = x[1]; spts[3 * (size_t)i + 2] = x[2]; }   /* cu:462-464 */
+            if (a3) a3[i] = 1.0f;                                                                                       /* mass, :465 */
+            if (b3) b3[i] = powf(diffx, 2) + powf(diffy, 2) + powf(diffz, 2);                                          /* :466 */
+            int bnd = s->boundary[i] != 0;
+            float solid = s->solid[i], fluid = s->fluid[i];
+            s->dens[i] = u_set_dens(newdens, bnd, P->h);                 /* cuh:300 */
+            s->press[i] = u_pressure(s->dens[i], solid, P->sound);       /* cuh:301 */
+            float *dp = s->delpress + 3 * (size_t)i;
+            dp[0] = ndx; dp[1] = ndy; dp[2] = ndz;                      /* cuh:302 */
+            if (!bnd) {
+                volatile float friction = fabsf(diffx) + fabsf(diffy) + fabsf(diffz);   /* cuh:311 */
+                solid += DT * delsolid;                                   /* :312-313 */
+                solid *= (solid >= 0.0);
+                if (fluid + delfluid < 0.2) delfluid = 0;                 /* :315 */
+                fluid += DT * delfluid;                                   /* :316-317 */
+                fluid *= (fluid >= 0);
+                fluid *= 1 / (fluid + solid);                             /* :319-320 */
+                solid *= 1 / (fluid + solid);
+                /* leapfrog :328-330 (DIFF == 0: + 0*diffusion) */
+                x[0] = x[0] + DT * v[0] + 0.5 * DT * DT * a[0] + 0 * diffx;
+                x[1] = x[1] + DT * v[1] + 0.5 * DT * DT * a[1] + 0 * diffy;
+                x[2] = x[2] + DT * v[2] + 0.5 * DT * DT * a[2] + 0 * diffz;
+                if (x[2] < -0.89) { v[0] = 0; v[1] = 0; }                 /* :332-341 */
+                /* :351-353 — stress_accel = mixture_accel = 0 here; the y and z lines test the NEW xvel (sic) */
+                v[0] = (v[0] + 0.5 * DT * a[0] + DT * (0.0f) + 5 * DT * DT * (0.0f)) -
+                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) > 0) * friction * 0.0000002 * solid +
+                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) < 0) * friction * 0.0000002 * solid;
+                v[1] = (v[1] + 0.5 * DT * a[1] + DT * (0.0f) + 5 * DT * DT * (0.0f)) -
+                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) > 0) * friction * 0.0000002 * solid +
+                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) < 0) * friction * 0.0000002 * solid;
+                v[2] = (v[2] + 0.5 * DT * a[2] + DT * (0.0f) + 5 * DT * DT * (0.0f)) -
+                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) > 0) * friction * 0.0000002 * solid +
+                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) < 0) * friction * 0.0000002 * solid;
+                /* :357-359 */
+                a[0] = -((220.0 - 70.0 * solid) / s->dens[i]) * dp[0];
+                a[1] = -((220.0 - 70.0 * solid) / s->dens[i]) * dp[1];
+                a[2] = P->gravity + ((-220.0 + 70.0 * solid) / s->dens[i]) * dp[2];
+                /* :390-392 */
+                v[0] += 0.5 * a[0] * DT;
+                v[1] += 0.5 * a[1] * DT;
+                v[2] += 0.5 * a[2] * DT;
+                /* walls :404-413 */
+                if (fabsf(x[2]) > 0.98) { x[2] = 0.97 / x[2]; v[2] = 0; }
+                if (fabsf(x[1]) > 0.98) v[1] = -v[1];
+                if (fabsf(x[0]) > 0.98) v[0] = -v[0];
+                s->solid[i] = solid;
+                s->fluid[i] = fluid;
+            }
+            /* cell_calc, FluidGPU-unidyn.cu:547 */
+            {
+                float fx = x[0] - P->origin, fy = x[1] - P->origin, fz = x[2] - P->origin;
+                double qx = fx / P->cellsize, qy = fy / P->cellsize, qz = fz / P->cellsize;
+                int cid;
+                if (!(fabs(qx) < 1e6 && fabs(qy) < 1e6 && fabs(qz) < 1e6)) cid = numcells;
+                else {
+                    long long l = (long long)(int)qx * G * G + (long long)(int)qy * G + (int)qz;
+                    cid = (l < 0 || l >= numcells) ? numcells : (int)l;
+                }
+                s->cell[i] = cid;
+            }
+            s->newdens[i] = 0;                                            /* cu:475-478 */
+            s->newdelpress[3 * (size_t)i] = s->newdelpress[3 * (size_t)i + 1] = s->newdelpress[3 * (size_t)i + 2] = 0;
+        }
+        if (spts || a3 || b3)
+            for (int i = nlive; i < n; i++) {
+                if (spts) { spts[3 * (size_t)i] = s->pos[3 * (size_t)i]; spts[3 * (size_t)i + 1] = s->pos[3 * (size_t)i + 1]; spts[3 * (size_t)i + 2] = s->pos[3 * (size_t)i + 2]; }
+                if (a3) a3[i] = 1.0f;
+                if (b3) b3[i] = 0.0f;
+            }
+    }
+    if (stats) memcpy(stats, st, sizeof(st));
+    rc = 0;
+done:
+    free(perm); free(tmp); free(start); free(end); free(split); free(cnt); free(acc); free(occ);
+    return rc;
+}

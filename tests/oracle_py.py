@@ -23,6 +23,11 @@ class State(C.Structure):
                                                               "newdelpress", "index", "cell", "boundary")]
 
 
+class UState(C.Structure):
+    _fields_ = [("n", C.c_int)] + [(k, C.c_void_p) for k in ("pos", "vel", "acc", "dens", "press", "delpress", "newdens",
+                                                              "newdelpress", "index", "cell", "boundary", "solid", "fluid", "subindex")]
+
+
 _lib = None
 
 
@@ -47,6 +52,9 @@ def load():
         lib.fsgo_params_base.argtypes = [C.POINTER(Params)]
         lib.fsgo_base_step.restype = C.c_int
         lib.fsgo_base_step.argtypes = [C.POINTER(Params), C.POINTER(State)] + [C.c_void_p] * 7
+        lib.fsgo_params_unidyn.argtypes = [C.POINTER(Params)]
+        lib.fsgo_unidyn_step.restype = C.c_int
+        lib.fsgo_unidyn_step.argtypes = [C.POINTER(Params), C.POINTER(UState), C.c_int] + [C.c_void_p] * 8
         _lib = lib
     return _lib
 
@@ -64,6 +72,50 @@ def params_from_cfg(cfg, threads=0) -> Params:
     return base_params(grid=cfg.grid, origin=cfg.origin, cellsize=cfg.cellsize, h=cfg.h, dt=cfg.dt,
                        alpha_fluid=cfg.alpha_fluid, alpha_boundary=cfg.alpha_boundary, sound=cfg.sound,
                        gravity=cfg.gravity, block_threads=cfg.neighbour_cap, bin_cap=cfg.bin_cap, threads=threads)
+
+
+def unidyn_params(**kw) -> Params:
+    p = Params()
+    load().fsgo_params_unidyn(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class OracleSimUnidyn:
+    """Runs fsgo_unidyn_step on a copy of a state dict that also holds solid / fluid."""
+
+    def __init__(self, params: Params, state: dict):
+        self.lib = load()
+        self.p = params
+        self.s = {k: np.array(v, copy=True) for k, v in state.items()}
+        n = self.s["pos"].shape[0]
+        self.n = n
+        self.s["cell"] = np.clip(cell_ids(self.p, self.s["pos"]), -1, params.grid ** 3).astype(np.int32)
+        self.s.setdefault("subindex", np.zeros(n, np.int32))
+        nc = params.grid ** 3
+        self.cells_sorted = np.zeros(n, np.int32)
+        self.start, self.end, self.split = np.zeros(nc, np.int32), np.zeros(nc, np.int32), np.zeros(nc, np.int32)
+        self.spts, self.a3, self.b3 = np.zeros(3 * n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self.stats = np.zeros(4, np.int64)
+        self.t = 0
+
+    def step(self, nsteps=1):
+        st = UState()
+        st.n = self.n
+        for k in ("pos", "vel", "acc", "dens", "press", "delpress", "newdens", "newdelpress", "index", "cell", "boundary", "solid",
+                  "fluid", "subindex"):
+            setattr(st, k, self.s[k].ctypes.data)
+        for _ in range(nsteps):
+            rc = self.lib.fsgo_unidyn_step(C.byref(self.p), C.byref(st), self.t, self.cells_sorted.ctypes.data, self.start.ctypes.data,
+                                           self.end.ctypes.data, self.split.ctypes.data, self.spts.ctypes.data, self.a3.ctypes.data,
+                                           self.b3.ctypes.data, self.stats.ctypes.data)
+            assert rc == 0, rc
+            self.t += 1
+        return self
+
+    def state(self) -> dict:
+        return {k: v.copy() for k, v in self.s.items()}
 
 
 class OracleSim:

@@ -50,8 +50,10 @@ def test_config_defaults_are_the_reference_constants(fsg):
     assert (cfg.neighbour_cap, cfg.bin_cap, cfg.capacity) == (64, 64, 8000)
     u = fsg.FsgConfig()
     assert fsg._lib.load().fsg_config_default(C.byref(u), fsg._lib.FSG_MODEL_UNIDYN) == 0
-    # FluidGPU-unidyn.cuh:1-36
-    assert (u.grid, u.cellsize, u.dt, u.alpha_fluid, u.alpha_boundary) == (17, 0.12, 0.0018, -0.155, 80.0)
+    # FluidGPU-unidyn.cuh:1-36; alpha_boundary is ALPHA__SAND_BOUNDARY (:21), the boundary factor the unidyn
+    # pair term uses (FluidGPU-unidyn.cu:307) — ALPHA_BOUNDARY (:18) only appears in the unused calculate_sigma
+    assert (u.grid, u.cellsize, u.dt, u.alpha_fluid, u.alpha_boundary) == (17, 0.12, 0.0018, -0.155, 10.0)
+    assert (u.neighbour_cap, u.bin_cap, u.capacity) == (1024, 0, 14040)
 
 
 def test_no_cpu_fallback(fsg):

@@ -444,3 +444,111 @@ def test_stage_api_follows_the_reference_launch_sequence(fsg, scene):
                 err = rel_l2(got[f], ref[f])
                 assert err <= TOL, (scene, step, f, err)
             assert float(np.abs(got["newdens"]).max()) == 0.0 and float(np.abs(got["newdelpress"]).max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# unidyn model (FluidGPU-unidyn.cu): configs[1] of BASELINE.json
+# ---------------------------------------------------------------------------------------------
+UFIELDS = FIELDS + ("fluid", "solid")
+
+
+def unidyn_resync_step(fsg, s):
+    """One step of the CUDA path and of the unidyn oracle from identical bits."""
+    state = s.download()
+    p = oracle_py.unidyn_params(grid=s.cfg.grid, origin=s.cfg.origin, cellsize=s.cfg.cellsize, h=s.cfg.h, dt=s.cfg.dt,
+                                alpha_fluid=s.cfg.alpha_fluid, alpha_boundary=s.cfg.alpha_boundary, sound=s.cfg.sound,
+                                gravity=s.cfg.gravity)
+    sim = oracle_py.OracleSimUnidyn(p, {k: v for k, v in state.items() if k != "cell"})
+    s.step(1)
+    sim.step(1)
+    got, ref = s.download(), sim.state()
+    cells, start, end = s.tables()
+    assert np.array_equal(cells, sim.cells_sorted) and np.array_equal(start, sim.start) and np.array_equal(end, sim.end)
+    assert np.array_equal(s.split(), sim.split), "split bins differ"
+    assert np.array_equal(got["index"], ref["index"]) and np.array_equal(got["cell"], ref["cell"])
+    assert np.array_equal(got["boundary"], ref["boundary"])
+    spts, a3, b3 = s.export_viz()
+    assert np.array_equal(spts, sim.spts) and np.array_equal(a3, sim.a3)
+    assert rel_l2(b3, sim.b3) <= TOL
+    errs = {f: rel_l2(got[f], ref[f]) for f in UFIELDS}
+    assert all(e <= TOL for e in errs.values()), errs
+    st = s.stats()
+    if s.cfg.collect_stats:
+        assert st["pairs_tested"] == sim.stats[0] and st["pairs_in_range"] == sim.stats[1], (st, sim.stats)
+        assert st["dropped"] == 0 and st["occupied_bins"] == sim.stats[3]
+    return errs
+
+
+def test_config2_unidyn_default_scene(fsg):
+    """configs[1]: solver-unidyn.cu default scene (10 000 fluid + 4 040 boundary particles), 100 steps:
+    per-step parity at 8 points of the trajectory + whole-trajectory comparison with the dumps of the
+    reference's own CUDA kernels (this scene is smooth: the reference's run-to-run noise stays <= 6e-6)."""
+    cfg = fsg.FluidSolver.unidyn_config(collect_stats=1)
+    state = fsg.scenes.unidyn_default_scene()
+    with fsg.FluidSolver(cfg) as s:
+        s.upload(state)
+        done = 0
+        for k in (0, 1, 4, 9, 24, 49, 74, 99):
+            s.step(k - done)
+            errs = unidyn_resync_step(fsg, s)
+            done = k + 1
+            print("unidyn step", done, errs)
+        assert s.stats()["steps"] == 100
+    # free-running trajectory against the reference GPU goldens
+    cfg = fsg.FluidSolver.unidyn_config()
+    with fsg.FluidSolver(cfg) as s:
+        s.upload(state)
+        done = 0
+        for k in (1, 2, 10, 100):
+            f = GOLD / f"ref_config2_step{k}.npz"
+            if not f.exists():
+                pytest.skip("golden dumps not generated yet")
+            s.step(k - done)
+            done = k
+            ref, got = dict(np.load(f)), s.download()
+            n = len(ref["index"])
+            if k == 1:
+                cells, start, end = s.tables()
+                assert np.array_equal(cells, ref["cells_sorted"]) and np.array_equal(start, ref["start"]) and np.array_equal(end, ref["end"])
+                assert np.array_equal(s.split(), ref["split"])
+                assert np.array_equal(got["index"], ref["index"]) and np.array_equal(got["cell"], ref["cell"])
+            o, r = np.argsort(got["index"], kind="stable"), np.argsort(ref["index"], kind="stable")
+            for fld in UFIELDS:
+                err = rel_l2(got[fld].reshape(n, -1)[o], ref[fld].reshape(n, -1)[r])
+                assert err <= (1e-5 if k <= 10 else 3e-5), (k, fld, err)
+
+
+@pytest.mark.parametrize("seed,n,bf", [(5, 6000, 0.1), (6, 2500, 0.3)])
+def test_unidyn_random_scenes(fsg, seed, n, bf):
+    state = fsg.scenes.random_unidyn_scene(n, seed, boundary_frac=bf)
+    cfg = fsg.FluidSolver.unidyn_config(capacity=state["pos"].shape[0], collect_stats=1)
+    with fsg.FluidSolver(cfg) as s:
+        s.upload(state)
+        for _ in range(3):
+            unidyn_resync_step(fsg, s)
+
+
+def test_unidyn_aos_and_scope(fsg):
+    import aos
+    state = fsg.scenes.random_unidyn_scene(1500, 9)
+    rec = aos.pack_unidyn(state)
+    cfg = fsg.FluidSolver.unidyn_config(capacity=1500)
+    with fsg.FluidSolver(cfg) as s:
+        s.upload_aos(rec)
+        back = aos.unpack_unidyn(s.download_aos())
+        for f in ("pos", "vel", "acc", "dens", "press", "newdens", "index", "boundary", "solid", "fluid"):
+            assert np.array_equal(back[f], state[f]), f
+        s.step(2)
+        via_aos = aos.unpack_unidyn(s.download_aos())
+    with fsg.FluidSolver(cfg) as s:
+        s.upload(state)
+        s.step(2)
+        via_soa = s.download()
+        for f in UFIELDS + ("index", "cell"):
+            assert np.array_equal(via_aos[f], via_soa[f]), f
+        # mixed-phase scenes are outside what is built: refused, not silently mis-computed
+        bad = dict(state)
+        bad["solid"] = state["solid"].copy()
+        bad["solid"][np.flatnonzero(state["boundary"] == 0)[0]] = 0.5
+        with pytest.raises(fsg.FsgError):
+            s.upload(bad)

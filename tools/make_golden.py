@@ -44,6 +44,24 @@ def run(out: pathlib.Path, name: str, tag: str, scene, steps):
     return dumps, json.loads(timing)
 
 
+UNIDYN_HARNESS = ROOT / "oracle" / "_ref" / "ref_harness_unidyn"
+UKEEP = KEEP[:-3] + ("solid", "fluid", "diffusion", "subindex", "split", "spts", "a3", "b3")
+UNIDYN_CASES = {
+    "config2": (lambda: scenes.unidyn_default_scene(), (1, 2, 10, 100)),
+    "unidyn_random": (lambda: scenes.random_unidyn_scene(6000, 5), (1, 2, 3)),
+}
+
+
+def run_unidyn(out: pathlib.Path, name: str, tag: str, scene, steps):
+    prefix = out / f"{name}_{tag}"
+    inp = out / f"{name}_in.bin"
+    sections.write_sections(inp, {k: scene[k] for k in ("pos", "vel", "acc", "dens", "press", "newdens", "index", "boundary", "solid", "fluid")})
+    cmd = [str(UNIDYN_HARNESS), "--steps", str(max(steps)), "--dump", ",".join(map(str, steps)), "--out", str(prefix), "--in", str(inp)]
+    timing = subprocess.check_output(cmd, timeout=300).decode().strip().splitlines()[-1]
+    dumps = {k: sections.read_sections(f"{prefix}_step{k}.bin") for k in steps}
+    return dumps, json.loads(timing)
+
+
 def rel_l2(a, b):
     a, b = a.astype(np.float64), b.astype(np.float64)
     d = np.sqrt((b * b).sum())
@@ -66,6 +84,19 @@ def main():
                                         for f in ("pos", "vel", "acc", "dens", "press", "delpress")}
             noise[f"{name}_step{k}"]["int_equal"] = bool(all(np.array_equal(a[f], b[f]) for f in ("cells_sorted", "start", "end", "index", "cell")))
             np.savez_compressed(out / f"ref_{name}_step{k}.npz", **{f: a[f] for f in KEEP})
+    if UNIDYN_HARNESS.exists():
+        for name, (factory, steps) in UNIDYN_CASES.items():
+            scene = factory()
+            d1, t1 = run_unidyn(out, name, "run1", scene, steps)
+            d2, _ = run_unidyn(out, name, "run2", scene, steps)
+            timings[name] = t1
+            for k in steps:
+                a, b = d1[k], d2[k]
+                oa, ob = np.argsort(a["index"], kind="stable"), np.argsort(b["index"], kind="stable")
+                noise[f"{name}_step{k}"] = {f: rel_l2(a[f].reshape(len(oa), -1)[oa], b[f].reshape(len(ob), -1)[ob])
+                                            for f in ("pos", "vel", "acc", "dens", "press", "delpress", "fluid")}
+                noise[f"{name}_step{k}"]["int_equal"] = bool(all(np.array_equal(a[f], b[f]) for f in ("cells_sorted", "start", "end", "split", "index", "cell")))
+                np.savez_compressed(out / f"ref_{name}_step{k}.npz", **{f: a[f] for f in UKEEP})
     (out / "golden_noise.json").write_text(json.dumps({"run_to_run_rel_l2": noise, "timing": timings}, indent=1))
     for p in out.glob("*.bin"):
         p.unlink()
