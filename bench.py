@@ -173,9 +173,12 @@ def fsg_arm(args):
         hist = fsg.slab.plume_layer_hist(cfg, SPACING)
         cuts = fsg.slab_cuts(hist, world)
         owned = [int(hist[a:b].sum()) for a, b in cuts]
-        cap = int(max(owned) * 1.15) + 4 * int(hist.max()) + 65536
+        cap = int(max(owned) * 1.05) + 3 * int(hist.max()) + 65536
         cfg = fsg.slab_config(cfg, rank, world, cuts, cap, local)
-        solver = fsg.SlabSolver(cfg, fsg.DistExchange(), msg_bytes=max(1 << 22, 3 * int(hist.max()) * 64))
+        cap_m, cap_g = fsg.slab.message_caps(hist, cuts)
+        solver = fsg.SlabSolver(cfg, fsg.DistExchange(), cap_m, cap_g)
+        if args.exchange == "peer":
+            solver.setup_peer_exchange()
 
     def barrier():
         if world > 1:
@@ -189,6 +192,8 @@ def fsg_arm(args):
     barrier()
     l0 = solver.stats()["kernel_launches"]
     solver.set_profiling(True)
+    if world > 1:
+        solver.time_exchange = True
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -209,15 +214,30 @@ def fsg_arm(args):
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t[0])
-        t2 = torch.tensor([float(launches), float(solver.owned_count()), float(solver.traffic_bytes)], device="cuda", dtype=torch.float64)
+        info = solver.check()          # raises if a message / the capacity overflowed or a particle left the ghost band
+        ph = [phase[k] / max(1, phase["steps"]) for k in ("sort", "reorder", "pair_update", "other")]
+        payload = 64.0 * (info["sent"][0] + info["sent"][2]) + 32.0 * (info["sent"][1] + info["sent"][3])
+        xm = solver.exchange_ms()
+        mine = torch.tensor(ph + [float(n_local), payload, float(solver.wire_bytes_per_step), xm["pack"], xm["exchange"], xm["unpack"]],
+                            device="cuda", dtype=torch.float64)
+        allr = torch.empty(world * mine.numel(), device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.cpu().view(world, -1)
+        per_rank = {"ms_sort": allr[:, 0].tolist(), "ms_reorder": allr[:, 1].tolist(), "ms_pair_update": allr[:, 2].tolist(),
+                    "ms_pack": allr[:, 7].tolist(), "ms_exchange_incl_wait": allr[:, 8].tolist(), "ms_unpack": allr[:, 9].tolist(),
+                    "particles": [int(v) for v in allr[:, 4].tolist()]}
+        t2 = torch.tensor([float(launches), float(solver.owned_count())], device="cuda", dtype=torch.float64)
         dist.all_reduce(t2, op=dist.ReduceOp.SUM)
         launches = int(t2[0])
         if int(t2[1]) != n_total:
             raise SystemExit(f"particle count not conserved across slabs: {int(t2[1])} != {n_total}")
-        per_step = float(t2[2]) / (args.steps + args.warmup)
-        halo = {"bytes_per_step_all_ranks": per_step, "GBps_all_ranks": per_step / (ms_total / args.steps * 1e-3) / 1e9,
-                "nvlink_peak_GBps_per_direction": 770.0,
-                "note": "neighbour P2P (migrants 64 B + ghosts 32 B per particle) over torch.distributed/NCCL; not overlapped with compute yet"}
+        wire, payload_all = float(allr[:, 6].sum()), float(allr[:, 5].sum())
+        halo = {"wire_bytes_per_step_all_ranks": wire, "payload_bytes_last_step_all_ranks": payload_all,
+                "wire_GBps_all_ranks": wire / (ms_total / args.steps * 1e-3) / 1e9, "nvlink_peak_GBps_per_direction": 770.0,
+                "exchange": args.exchange,
+                "note": "one fixed-size message per neighbour and direction (counts in the header, read on the device): no host "
+                        "synchronisation inside a step; peer = copied into the neighbour's inbox over NVLink by the copy engines "
+                        "(CUDA IPC mapping) + a 4-byte NCCL send/recv that orders the neighbour's stream; nccl = NCCL send/recv"}
     ms_step = ms_total / args.steps
     value = G ** 3 / (ms_step * 1e-3)
 
@@ -271,6 +291,7 @@ def fsg_arm(args):
                 "roofline": roofline, "cpu_baseline": cpu}
         if halo:
             line["halo"] = halo
+            line["per_rank"] = per_rank
         line.update(extra)
         print(json.dumps(line))
     solver.close()
@@ -326,6 +347,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: peer = messages copied into the neighbours' memory over NVLink (CUDA IPC) + 4-byte NCCL signal; "
+                         "nccl = whole messages through NCCL send/recv")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "fsg":
         args.warmup = 3

@@ -68,9 +68,16 @@ SIGNATURES = {
                                        C.POINTER(C.c_int64)]),
     "fsg_scene_plume_hist": (C.c_int, [C.POINTER(FsgConfig), C.c_double, P]),
     "fsg_device_ptr": (C.c_int, [P, C.c_int, C.POINTER(P)]),
-    "fsg_slab_pack": (C.c_int, [P, P, P, C.c_int64, C.POINTER(C.c_int64 * 5)]),
-    "fsg_slab_unpack": (C.c_int, [P, P, C.c_int64, C.c_int64, P, C.c_int64, C.c_int64]),
+    "fsg_slab_pack": (C.c_int, [P, P, P, C.c_int64, C.c_int64]),
+    "fsg_slab_unpack": (C.c_int, [P, P, P, C.c_int64, C.c_int64]),
+    "fsg_slab_check": (C.c_int, [P, C.POINTER(C.c_int64 * 9)]),
     "fsg_slab_message_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "fsg_slab_alloc_messages": (C.c_int, [P, C.c_int64, C.c_int64]),
+    "fsg_slab_inbox_handle": (C.c_int, [P, C.c_int, C.c_int, P]),
+    "fsg_slab_open_peer": (C.c_int, [P, C.c_int, C.c_int, P]),
+    "fsg_slab_pack_send": (C.c_int, [P]),
+    "fsg_slab_unpack_recv": (C.c_int, [P]),
+    "fsg_slab_close_peers": (C.c_int, [P]),
     "fsg_stage_sort": (C.c_int, [P, P, P, C.c_int64]),
     "fsg_stage_findneighbours": (C.c_int, [P, P, P, P, C.c_int64]),
     "fsg_stage_mykernel": (C.c_int, [P, P, P, P, P, C.c_int64]),

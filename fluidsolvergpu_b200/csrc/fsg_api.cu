@@ -129,6 +129,9 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
     cudaFree(c->counters); cudaFree(c->dstats); cudaFree(c->sort_tmp);
     cudaFree(c->slab_cnt); cudaFree(c->scan_tmp);
+    for (int k = 0; k < 4; k++) if (c->peer_inbox[k]) cudaIpcCloseMemHandle(c->peer_inbox[k]);
+    for (int k = 0; k < 2; k++) cudaFree(c->outbox[k]);
+    for (int k = 0; k < 4; k++) cudaFree(c->inbox[k]);
     cudaFree(c->stage);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
@@ -271,6 +274,14 @@ static int after_upload(fsg_ctx *c, int64_t n)
         c->tables_dirty = false;
     }
     c->n = n;
+    if (c->cfg.world > 1) {
+        // a slab context always works on all `cap` slots (nothing on the host depends on how many are in use):
+        // the tail holds the dead key, the device-side count of slots in use starts at n
+        CU(c, fsg_launch_fill(c->keysB + n, c->dev.dead, c->cap - n, c->stream));
+        const int n32 = (int)n;
+        CU(c, cudaMemcpyAsync(c->counters + 5, &n32, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemsetAsync(c->counters + 9, 0, sizeof(int), c->stream));
+    }
     CU(c, cudaMemsetAsync(c->counters + 4, 0, sizeof(int), c->stream));
     CU(c, cudaMemsetAsync(c->counters + 6, 0, sizeof(int), c->stream));
     CU(c, fsg_launch_keys(c->dev, c->B.posd, c->keysB, n, c->counters + 4, c->cfg.world > 1, c->stream));   // solver.cu:119
@@ -279,6 +290,7 @@ static int after_upload(fsg_ctx *c, int64_t n)
     CU(c, cudaMemcpyAsync(flag, c->counters + 4, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->has_boundary = flag[0] != 0;
+    if (c->cfg.world > 1) c->n = c->cap;
     CU(c, cudaMemsetAsync(c->counters + 8, 0, sizeof(int), c->stream));
     if (c->cfg.model == FSG_MODEL_UNIDYN && flag[4]) {
         c->n = 0;

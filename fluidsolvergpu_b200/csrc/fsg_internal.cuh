@@ -76,6 +76,10 @@ struct fsg_ctx {
     void *scan_tmp;
     size_t scan_tmp_bytes;
     int64_t slab_warps;
+    void *outbox[2];    // slab messages packed here (to left, to right) when the library owns the buffers
+    void *inbox[4];     // [2*side + parity]: from left / from right, double-buffered by step parity
+    void *peer_inbox[4];// the neighbours' inboxes mapped through CUDA IPC: [0..1] left neighbour's from-right, [2..3] right neighbour's from-left
+    int64_t msg_cap_m, msg_cap_g;
     void *sort_tmp;
     void *stage;        // device staging area for host<->device conversion
     size_t stage_bytes;

@@ -14,6 +14,7 @@
 
 #include <cub/device/device_scan.cuh>
 #include <stdio.h>
+#include <string.h>
 
 size_t fsg_scan_temp_bytes(int64_t n)
 {
@@ -64,30 +65,40 @@ k_slab_count(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ k
     if (i == 0) cnt[4 * nw] = 0;
 }
 
+// Fixed-layout message (device memory), the same size on every rank so that nothing on the host depends
+// on how many particles cross a face this step:
+//   [header 64 B: int64 m, int64 g][posd cap_m][velp cap_m][accf cap_m][dpi cap_m][posd cap_g][velp cap_g]
 struct SlabMsg {
+    long long *hdr;
     float4 *m_posd, *m_velp, *m_accf, *m_dpi, *g_posd, *g_velp;
 };
-__host__ __device__ inline SlabMsg slab_msg(void *base, int64_t m, int64_t g)
+__host__ __device__ inline SlabMsg slab_msg(void *base, int64_t cap_m, int64_t cap_g)
 {
     SlabMsg r;
-    float4 *p = (float4 *)base;
-    r.m_posd = p; r.m_velp = p + m; r.m_accf = p + 2 * m; r.m_dpi = p + 3 * m;
-    r.g_posd = p + 4 * m; r.g_velp = p + 4 * m + g;
+    r.hdr = (long long *)base;
+    float4 *p = (float4 *)((char *)base + 64);
+    r.m_posd = p; r.m_velp = p + cap_m; r.m_accf = p + 2 * cap_m; r.m_dpi = p + 3 * cap_m;
+    r.g_posd = p + 4 * cap_m; r.g_velp = p + 4 * cap_m + cap_g;
     return r;
 }
 
-// off = exclusive scan of cnt (length 4*nw + 1).  tot[k] = off[(k+1)*nw] - off[k*nw].
-__global__ void k_slab_totals(const int *__restrict__ off, int64_t nw, const int *__restrict__ nkeep_dev, int have_nkeep,
-                              int64_t n_host, const int *violation, int64_t *out)
+// off = exclusive scan of cnt (length 4*nw + 1): totals of the four categories -> message headers (clamped to
+// the message capacities; an overflow is flagged, the excess is not sent) and the diagnostics array
+__global__ void k_slab_headers(const int *__restrict__ off, int64_t nw, void *to_left, void *to_right, int64_t cap_m, int64_t cap_g,
+                               int *overflow, long long *diag)
 {
-    if (threadIdx.x < 4) out[threadIdx.x] = off[(threadIdx.x + 1) * nw] - off[threadIdx.x * nw];
-    if (threadIdx.x == 4) out[4] = have_nkeep ? (int64_t)*nkeep_dev : n_host;
-    if (threadIdx.x == 5) out[5] = *violation;
+    if (threadIdx.x != 0) return;
+    long long t[4];
+    for (int k = 0; k < 4; k++) t[k] = off[(k + 1) * nw] - off[k * nw];
+    for (int k = 0; k < 4; k++) diag[k] = t[k];
+    if (t[0] > cap_m || t[2] > cap_m || t[1] > cap_g || t[3] > cap_g) atomicOr(overflow, 1);
+    if (to_left) { long long *h = (long long *)to_left; h[0] = t[0] < cap_m ? t[0] : cap_m; h[1] = t[1] < cap_g ? t[1] : cap_g; }
+    if (to_right) { long long *h = (long long *)to_right; h[0] = t[2] < cap_m ? t[2] : cap_m; h[1] = t[3] < cap_g ? t[3] : cap_g; }
 }
 
 __global__ void __launch_bounds__(256)
 k_slab_scatter(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ keys, FsgState B, const int *__restrict__ off,
-               int64_t nw, void *to_left, void *to_right)
+               int64_t nw, void *to_left, void *to_right, int64_t cap_m, int64_t cap_g)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int c = i < n ? slab_category(d, keys[i], rank, world) : 0;
@@ -101,37 +112,51 @@ k_slab_scatter(FsgDev d, int rank, int world, int64_t n, const int *__restrict__
         pos[k] = (w < nw ? off[k * nw + w] - off[k * nw] : 0) + __popc(m & lt);
     }
     if (!c) return;
-    const int64_t mL = off[1 * nw] - off[0], gL = off[2 * nw] - off[1 * nw], mR = off[3 * nw] - off[2 * nw], gR = off[4 * nw] - off[3 * nw];
     float4 pd = B.posd[i], vp = B.velp[i];
     if (c & 5) {
         // migrant: full state goes to the neighbour.  The slot is NOT freed here: a particle moves less
         // than one bin per step, so it lands in the neighbour's outermost layer, where this slab still
         // needs it as a candidate for one more step.  Its bin is outside [x0, x1), so it is treated as
         // a ghost (never a home particle) and k_update drops it.
-        SlabMsg M = (c & 1) ? slab_msg(to_left, mL, gL) : slab_msg(to_right, mR, gR);
+        SlabMsg M = slab_msg((c & 1) ? to_left : to_right, cap_m, cap_g);
         int q = (c & 1) ? pos[0] : pos[2];
-        M.m_posd[q] = pd;
-        M.m_velp[q] = vp;
-        M.m_accf[q] = B.accf[i];
-        M.m_dpi[q] = B.dpi[i];
+        if (q < cap_m) {
+            M.m_posd[q] = pd;
+            M.m_velp[q] = vp;
+            M.m_accf[q] = B.accf[i];
+            M.m_dpi[q] = B.dpi[i];
+        }
     }
-    if (c & 2) { SlabMsg M = slab_msg(to_left, mL, gL); M.g_posd[pos[1]] = pd; M.g_velp[pos[1]] = vp; }
-    if (c & 8) { SlabMsg M = slab_msg(to_right, mR, gR); M.g_posd[pos[3]] = pd; M.g_velp[pos[3]] = vp; }
+    if ((c & 2) && pos[1] < cap_g) { SlabMsg M = slab_msg(to_left, cap_m, cap_g); M.g_posd[pos[1]] = pd; M.g_velp[pos[1]] = vp; }
+    if ((c & 8) && pos[3] < cap_g) { SlabMsg M = slab_msg(to_right, cap_m, cap_g); M.g_posd[pos[3]] = pd; M.g_velp[pos[3]] = vp; }
 }
 
-// appended slots: migrants (full state) then ghosts (read state); keys from the positions, exactly
-// as the owner computed them (bin_id is the same function on both sides)
+// Appends both received messages behind the slots in use (*n_used, a device-side count: nothing here needs
+// the host to know how many particles arrived): migrants (full state) then ghosts (read state); keys from
+// the positions, exactly as the owner computed them (bin_id is the same function on both sides).
 __global__ void __launch_bounds__(256)
-k_slab_unpack(FsgDev d, const void *msg, int64_t m, int64_t g, int64_t at, FsgState B, float4 *carry, int *keys)
+k_slab_unpack(FsgDev d, const void *from_left, const void *from_right, int64_t cap_m, int64_t cap_g, const int *n_used, int64_t cap,
+              FsgState B, float4 *carry, int *keys, int *overflow, long long *diag)
 {
+    const int64_t per = cap_m + cap_g;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m + g) return;
-    SlabMsg M = slab_msg(const_cast<void *>(msg), m, g);
-    int64_t i = at + t;
+    if (t >= 2 * per) return;
+    const int side = t >= per;
+    const void *msg = side ? from_right : from_left;
+    const long long *hl = (const long long *)from_left, *hr = (const long long *)from_right;
+    const long long nl = from_left ? hl[0] + hl[1] : 0;
+    if (t == 0) { diag[4] = from_left ? hl[0] : 0; diag[5] = from_left ? hl[1] : 0; diag[6] = from_right ? hr[0] : 0; diag[7] = from_right ? hr[1] : 0; }
+    if (!msg) return;
+    SlabMsg M = slab_msg(const_cast<void *>(msg), cap_m, cap_g);
+    const long long m = M.hdr[0], g = M.hdr[1];
+    int64_t u = t - (side ? per : 0);
+    if (u >= m + g) return;
+    int64_t i = (int64_t)*n_used + (side ? nl : 0) + u;
+    if (i >= cap) { atomicOr(overflow, 2); return; }
     float4 pd, vp, af, dp;
-    if (t < m) { pd = M.m_posd[t]; vp = M.m_velp[t]; af = M.m_accf[t]; dp = M.m_dpi[t]; }
+    if (u < m) { pd = M.m_posd[u]; vp = M.m_velp[u]; af = M.m_accf[u]; dp = M.m_dpi[u]; }
     else {
-        pd = M.g_posd[t - m]; vp = M.g_velp[t - m];
+        pd = M.g_posd[u - m]; vp = M.g_velp[u - m];
         af = make_float4(0.f, 0.f, 0.f, __int_as_float(pd.w < 0.f ? 1 : 0));
         dp = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     }
@@ -151,14 +176,16 @@ k_slab_unpack(FsgDev d, const void *msg, int64_t m, int64_t g, int64_t at, FsgSt
         }                                                                                               \
     } while (0)
 
-extern "C" int64_t fsg_slab_message_bytes(int64_t m, int64_t g) { return (4 * m + 2 * g) * (int64_t)sizeof(float4); }
+extern "C" int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g) { return 64 + (4 * cap_m + 2 * cap_g) * (int64_t)sizeof(float4); }
 
-extern "C" int fsg_slab_pack(fsg_ctx *c, void *d_to_left, void *d_to_right, int64_t cap_bytes, int64_t counts[5])
+// counters: [5] slots in use (device-side), [6] ghost-band violation, [9] message / capacity overflow
+extern "C" int fsg_slab_pack(fsg_ctx *c, void *d_to_left, void *d_to_right, int64_t cap_m, int64_t cap_g)
 {
-    if (!c || !counts) return FSG_E_INVALID;
+    if (!c || cap_m < 0 || cap_g < 0) return FSG_E_INVALID;
     if (c->cfg.world <= 1) { c->err = "fsg_slab_pack: not a slab context (world == 1)"; return FSG_E_STATE; }
+    if ((c->cfg.rank > 0 && !d_to_left) || (c->cfg.rank < c->cfg.world - 1 && !d_to_right)) return FSG_E_INVALID;
     CUS(c, cudaSetDevice(c->device));
-    const int64_t n = c->n;
+    const int64_t n = c->n;                           // == capacity for a slab context: unused slots hold the dead key
     const int64_t nw = (n + 31) / 32 > 0 ? (n + 31) / 32 : 1;
     if (nw > c->slab_warps) {
         CUS(c, cudaStreamSynchronize(c->stream));
@@ -171,67 +198,157 @@ extern "C" int fsg_slab_pack(fsg_ctx *c, void *d_to_left, void *d_to_right, int6
         c->slab_warps = capw;
     }
     int *cnt = c->slab_cnt, *off = c->slab_cnt + (4 * c->slab_warps + 8);
-    // the 5 totals live in the 8-byte aligned tail of the same allocation
-    int64_t *d_out = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
+    long long *diag = reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
     const unsigned blocks = (unsigned)((nw * 32 + 255) / 256);
-    if (n > 0) {
-        k_slab_count<<<blocks, 256, 0, c->stream>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, cnt, nw, c->counters + 6);
-        CUS(c, cudaGetLastError());
-    } else {
-        CUS(c, cudaMemsetAsync(cnt, 0, sizeof(int) * (4 * nw + 1), c->stream));
-    }
-    CUS(c, fsg_scan_exclusive(c->scan_tmp, c->scan_tmp_bytes, cnt, off, 4 * nw + 1, c->stream));
-    k_slab_totals<<<1, 32, 0, c->stream>>>(off, nw, c->counters + 5, c->steps > 0 ? 1 : 0, n, c->counters + 6, d_out);
+    k_slab_count<<<blocks, 256, 0, c->stream>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, cnt, nw, c->counters + 6);
     CUS(c, cudaGetLastError());
-    c->launches += 2;
-    int64_t h[6];
-    CUS(c, cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-    CUS(c, cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < 5; k++) counts[k] = h[k];
-    if (h[5]) {
-        c->err = "fsg_slab_pack: a particle moved more than one bin layer in a step and left the one-layer ghost band "
-                 "(solver-unidyn.cu:187 makes the same assumption); reduce dt or use fewer slabs";
-        return FSG_E_STATE;
-    }
-    if (fsg_slab_message_bytes(h[0], h[1]) > cap_bytes || fsg_slab_message_bytes(h[2], h[3]) > cap_bytes) {
-        c->err = "fsg_slab_pack: message buffer too small";
-        return FSG_E_NOMEM;
-    }
-    if ((h[0] + h[1] > 0 && !d_to_left) || (h[2] + h[3] > 0 && !d_to_right)) return FSG_E_INVALID;
-    if (n > 0 && h[0] + h[1] + h[2] + h[3] > 0) {
-        k_slab_scatter<<<blocks, 256, 0, c->stream>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, c->B, off, nw, d_to_left,
-                                                      d_to_right);
-        CUS(c, cudaGetLastError());
-        c->launches++;
-    }
-    // slots in use: after a step the sort has moved the dead slots behind n_keep
-    if (c->steps > 0 && h[4] <= c->n) c->n = h[4];
-    counts[4] = c->n;
+    CUS(c, fsg_scan_exclusive(c->scan_tmp, c->scan_tmp_bytes, cnt, off, 4 * nw + 1, c->stream));
+    k_slab_headers<<<1, 32, 0, c->stream>>>(off, nw, c->cfg.rank > 0 ? d_to_left : nullptr,
+                                            c->cfg.rank < c->cfg.world - 1 ? d_to_right : nullptr, cap_m, cap_g, c->counters + 9, diag);
+    CUS(c, cudaGetLastError());
+    k_slab_scatter<<<blocks, 256, 0, c->stream>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, c->B, off, nw, d_to_left, d_to_right,
+                                                  cap_m, cap_g);
+    CUS(c, cudaGetLastError());
+    c->launches += 3;
     return FSG_OK;
 }
 
-extern "C" int fsg_slab_unpack(fsg_ctx *c, const void *d_from_left, int64_t mig_left, int64_t ghost_left,
-                               const void *d_from_right, int64_t mig_right, int64_t ghost_right)
+extern "C" int fsg_slab_unpack(fsg_ctx *c, const void *d_from_left, const void *d_from_right, int64_t cap_m, int64_t cap_g)
 {
-    if (!c || mig_left < 0 || ghost_left < 0 || mig_right < 0 || ghost_right < 0) return FSG_E_INVALID;
+    if (!c || cap_m < 0 || cap_g < 0) return FSG_E_INVALID;
     if (c->cfg.world <= 1) { c->err = "fsg_slab_unpack: not a slab context (world == 1)"; return FSG_E_STATE; }
     CUS(c, cudaSetDevice(c->device));
-    const int64_t nl = mig_left + ghost_left, nr = mig_right + ghost_right;
-    if (c->n + nl + nr > c->cap) { c->err = "fsg_slab_unpack: received particles exceed the context capacity"; return FSG_E_NOMEM; }
-    if ((nl > 0 && !d_from_left) || (nr > 0 && !d_from_right)) return FSG_E_INVALID;
-    if (nl > 0) {
-        k_slab_unpack<<<(unsigned)((nl + 255) / 256), 256, 0, c->stream>>>(c->dev, d_from_left, mig_left, ghost_left, c->n, c->B,
-                                                                         c->carryB, c->keysB);
+    if (c->cfg.rank == 0) d_from_left = nullptr;
+    if (c->cfg.rank == c->cfg.world - 1) d_from_right = nullptr;
+    if (!c->slab_cnt) { c->err = "fsg_slab_unpack: call fsg_slab_pack first"; return FSG_E_STATE; }
+    long long *diag = reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
+    const int64_t threads = 2 * (cap_m + cap_g);
+    if (threads > 0) {
+        k_slab_unpack<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->dev, d_from_left, d_from_right, cap_m, cap_g,
+                                                                              c->counters + 5, c->cap, c->B, c->carryB, c->keysB,
+                                                                              c->counters + 9, diag);
         CUS(c, cudaGetLastError());
         c->launches++;
-        c->n += nl;
     }
-    if (nr > 0) {
-        k_slab_unpack<<<(unsigned)((nr + 255) / 256), 256, 0, c->stream>>>(c->dev, d_from_right, mig_right, ghost_right, c->n, c->B,
-                                                                         c->carryB, c->keysB);
-        CUS(c, cudaGetLastError());
-        c->launches++;
-        c->n += nr;
+    return FSG_OK;
+}
+
+// Synchronises and reports: info[0..3] particles sent (migrants / ghosts to the left, to the right) and
+// info[4..7] received in the last round, info[8] slots in use after the last sort.  FSG_E_STATE if a particle
+// left the one-layer ghost band, FSG_E_NOMEM if a message or the particle capacity overflowed.
+extern "C" int fsg_slab_check(fsg_ctx *c, int64_t info[9])
+{
+    if (!c) return FSG_E_INVALID;
+    if (c->cfg.world <= 1) { c->err = "fsg_slab_check: not a slab context (world == 1)"; return FSG_E_STATE; }
+    CUS(c, cudaSetDevice(c->device));
+    int cnt[16];
+    long long diag[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CUS(c, cudaMemcpyAsync(cnt, c->counters, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    if (c->slab_cnt) {
+        long long *d = reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
+        CUS(c, cudaMemcpyAsync(diag, d, sizeof diag, cudaMemcpyDeviceToHost, c->stream));
     }
+    CUS(c, cudaStreamSynchronize(c->stream));
+    if (info) {
+        for (int k = 0; k < 8; k++) info[k] = diag[k];
+        info[8] = cnt[5];
+    }
+    if (cnt[6]) {
+        c->err = "slab exchange: a particle moved more than one bin layer in a step and left the one-layer ghost band "
+                 "(solver-unidyn.cu:187 makes the same assumption); reduce dt or use fewer slabs";
+        return FSG_E_STATE;
+    }
+    if (cnt[9]) {
+        c->err = (cnt[9] & 2) ? "slab exchange: received particles exceed the context capacity"
+                              : "slab exchange: a message exceeded its capacity (cap_m / cap_g)";
+        return FSG_E_NOMEM;
+    }
+    return FSG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Peer-memory exchange: the neighbour's inboxes are mapped into this process (CUDA IPC), and the
+// packed messages are copied straight into them over NVLink by the copy engines (no staging through a
+// communication library, no SMs taken from the pair kernel).  The caller only has to order the
+// neighbour's stream behind the copy — a few-byte NCCL send/recv on the same stream does that.
+// Inboxes are double-buffered by step parity: a message for step s+1 never lands in memory the
+// neighbour may still be unpacking for step s.
+// ------------------------------------------------------------------------------------------------
+extern "C" int fsg_slab_alloc_messages(fsg_ctx *c, int64_t cap_m, int64_t cap_g)
+{
+    if (!c || cap_m < 0 || cap_g < 0) return FSG_E_INVALID;
+    if (c->cfg.world <= 1) { c->err = "fsg_slab_alloc_messages: not a slab context (world == 1)"; return FSG_E_STATE; }
+    CUS(c, cudaSetDevice(c->device));
+    CUS(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 2; k++) { cudaFree(c->outbox[k]); c->outbox[k] = nullptr; }
+    for (int k = 0; k < 4; k++) { cudaFree(c->inbox[k]); c->inbox[k] = nullptr; }
+    const size_t bytes = (size_t)fsg_slab_message_bytes(cap_m, cap_g);
+    for (int k = 0; k < 2; k++) { CUS(c, cudaMalloc(&c->outbox[k], bytes)); CUS(c, cudaMemsetAsync(c->outbox[k], 0, bytes, c->stream)); }
+    for (int k = 0; k < 4; k++) { CUS(c, cudaMalloc(&c->inbox[k], bytes)); CUS(c, cudaMemsetAsync(c->inbox[k], 0, bytes, c->stream)); }
+    CUS(c, cudaStreamSynchronize(c->stream));
+    c->msg_cap_m = cap_m;
+    c->msg_cap_g = cap_g;
+    return FSG_OK;
+}
+
+// side 0: the inbox that receives from the LEFT neighbour, side 1: from the RIGHT one; parity 0/1
+extern "C" int fsg_slab_inbox_handle(fsg_ctx *c, int side, int parity, void *handle64)
+{
+    if (!c || !handle64 || side < 0 || side > 1 || parity < 0 || parity > 1) return FSG_E_INVALID;
+    if (!c->inbox[2 * side + parity]) { c->err = "fsg_slab_inbox_handle: call fsg_slab_alloc_messages first"; return FSG_E_STATE; }
+    CUS(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CUS(c, cudaIpcGetMemHandle(&h, c->inbox[2 * side + parity]));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle64, &h, 64);
+    return FSG_OK;
+}
+
+// side 0: `handle64` is the LEFT neighbour's from-right inbox, side 1: the RIGHT neighbour's from-left inbox
+extern "C" int fsg_slab_open_peer(fsg_ctx *c, int side, int parity, const void *handle64)
+{
+    if (!c || !handle64 || side < 0 || side > 1 || parity < 0 || parity > 1) return FSG_E_INVALID;
+    CUS(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    CUS(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_inbox[2 * side + parity] = p;
+    return FSG_OK;
+}
+
+extern "C" int fsg_slab_pack_send(fsg_ctx *c)
+{
+    if (!c) return FSG_E_INVALID;
+    if (!c->outbox[0]) { c->err = "fsg_slab_pack_send: call fsg_slab_alloc_messages first"; return FSG_E_STATE; }
+    const int par = (int)(c->steps & 1);
+    const bool left = c->cfg.rank > 0, right = c->cfg.rank < c->cfg.world - 1;
+    if ((left && !c->peer_inbox[par]) || (right && !c->peer_inbox[2 + par])) {
+        c->err = "fsg_slab_pack_send: the neighbours' inboxes are not mapped (fsg_slab_open_peer)";
+        return FSG_E_STATE;
+    }
+    int rc = fsg_slab_pack(c, c->outbox[0], c->outbox[1], c->msg_cap_m, c->msg_cap_g);
+    if (rc != FSG_OK) return rc;
+    const size_t bytes = (size_t)fsg_slab_message_bytes(c->msg_cap_m, c->msg_cap_g);
+    if (left) CUS(c, cudaMemcpyAsync(c->peer_inbox[par], c->outbox[0], bytes, cudaMemcpyDefault, c->stream));
+    if (right) CUS(c, cudaMemcpyAsync(c->peer_inbox[2 + par], c->outbox[1], bytes, cudaMemcpyDefault, c->stream));
+    return FSG_OK;
+}
+
+extern "C" int fsg_slab_unpack_recv(fsg_ctx *c)
+{
+    if (!c) return FSG_E_INVALID;
+    if (!c->inbox[0]) { c->err = "fsg_slab_unpack_recv: call fsg_slab_alloc_messages first"; return FSG_E_STATE; }
+    const int par = (int)(c->steps & 1);
+    return fsg_slab_unpack(c, c->inbox[par], c->inbox[2 + par], c->msg_cap_m, c->msg_cap_g);
+}
+
+extern "C" int fsg_slab_close_peers(fsg_ctx *c)
+{
+    if (!c) return FSG_E_INVALID;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 4; k++) if (c->peer_inbox[k]) { cudaIpcCloseMemHandle(c->peer_inbox[k]); c->peer_inbox[k] = nullptr; }
     return FSG_OK;
 }

@@ -7,10 +7,12 @@ generalised to N slabs, one process (and one libfsg context) per device:
 
     every step:  fsg_slab_pack  ->  exchange with the two x-neighbours  ->  fsg_slab_unpack  ->  fsg_step(1)
 
-Only the exchange lives in this file; it moves two device buffers per neighbour with
-torch.distributed P2P (NCCL over NVLink on GPUs, gloo in the CPU tests) after a count exchange.
-There is no data-path collective other than that neighbour exchange; `global_sum` is the one small
-all-reduce used for diagnostics (particle count conservation).
+Only the exchange lives in this file: one fixed-size message per neighbour and direction, moved with
+torch.distributed P2P (NCCL over NVLink on GPUs, gloo in the CPU tests).  The particle counts travel in
+the message header and are read on the device, so a step never waits for the host: every call only
+enqueues work on the solver's stream and the host runs steps ahead of the device.  There is no
+data-path collective other than that neighbour exchange; `global_sum` is the one small all-reduce used
+for diagnostics (particle count conservation).
 
 `SlabGroup` drives W contexts in ONE process on one device with an in-process exchange — the way the
 multi-rank algorithm is tested on a single GPU against the single-slab result.
@@ -30,7 +32,7 @@ from .solver import FluidSolver
 # partition
 # ---------------------------------------------------------------------------------------------
 def slab_cuts(hist, world: int, min_layers: int = 2) -> list[tuple[int, int]]:
-    """Cuts bin layers 0..G-1 into `world` contiguous slabs of (nearly) equal particle count.
+    """Cuts bin layers 0..G-1 into `world` contiguous slabs minimising the largest particle count.
     hist[ix] = particles in bin layer ix.  Empty outer layers go to the end ranks.
     Every slab is at least `min_layers` thick: a particle that migrates into a slab must not at the
     same time be needed as a ghost by the slab beyond it (the one-layer ghost band of the reference,
@@ -43,19 +45,41 @@ def slab_cuts(hist, world: int, min_layers: int = 2) -> list[tuple[int, int]]:
         return [(0, G)]
     if G < min_layers * world:
         raise ValueError(f"{G} bin layers cannot hold {world} slabs of at least {min_layers} layers")
-    total = int(hist.sum())
     cum = np.concatenate([[0], np.cumsum(hist)])
-    cuts = [0]
-    for r in range(1, world):
-        target = total * r / world
-        x = int(np.searchsorted(cum, target, side="left"))
-        # nearest layer boundary to the target, leaving room for the remaining slabs
-        if x > 0 and abs(cum[x - 1] - target) <= abs(cum[min(x, G)] - target):
-            x -= 1
-        x = max(x, cuts[-1] + min_layers)
-        x = min(x, G - min_layers * (world - r))
-        cuts.append(x)
-    cuts.append(G)
+
+    def feasible(limit):
+        """Greedy: can the layers be covered by `world` slabs of >= min_layers layers and <= limit particles?"""
+        cuts, x = [0], 0
+        for r in range(world):
+            remaining = world - r - 1
+            hi = G - min_layers * remaining                       # leave room for the slabs to come
+            lo = x + min_layers
+            if lo > hi:
+                return None
+            # furthest end with load <= limit
+            e = int(np.searchsorted(cum, cum[x] + limit, side="right")) - 1
+            e = min(e, hi)
+            if e < lo:
+                return None
+            if remaining == 0:
+                if cum[G] - cum[x] > limit:
+                    return None
+                e = G
+            cuts.append(e)
+            x = e
+        return cuts
+
+    # smallest achievable maximum load (binary search over the load limit)
+    lo_l, hi_l = int(hist.max()) * min_layers // 2, int(hist.sum()) + 1
+    best = feasible(hi_l)
+    while lo_l < hi_l:
+        mid = (lo_l + hi_l) // 2
+        c = feasible(mid)
+        if c is not None:
+            best, hi_l = c, mid
+        else:
+            lo_l = mid + 1
+    cuts = best
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
@@ -86,16 +110,26 @@ def slab_config(base: FsgConfig, rank: int, world: int, cuts, capacity: int, dev
     return cfg
 
 
-def message_bytes(m: int, g: int) -> int:
-    return (4 * m + 2 * g) * 16
+def message_bytes(cap_m: int, cap_g: int) -> int:
+    """Bytes of one slab message with room for cap_m migrants and cap_g ghosts (fsg_slab_message_bytes)."""
+    return 64 + (4 * cap_m + 2 * cap_g) * 16
+
+
+def message_caps(hist, cuts, slack: float = 1.2, floor: int = 4096) -> tuple[int, int]:
+    """Message capacities every rank agrees on: ghosts = the most populated face layer x slack, migrants =
+    a tenth of that (a particle moves much less than one bin per step)."""
+    hist = np.asarray(hist, dtype=np.int64)
+    faces = [int(hist[a]) for a, b in cuts] + [int(hist[b - 1]) for a, b in cuts]
+    cap_g = int(max(faces) * slack) + floor
+    return max(floor, cap_g // 32), cap_g
 
 
 # ---------------------------------------------------------------------------------------------
-# exchange back-ends
+# exchange back-end
 # ---------------------------------------------------------------------------------------------
 class DistExchange:
-    """Neighbour exchange over torch.distributed (one rank per process).  Buffers are torch uint8
-    tensors on the communication device (cuda for NCCL, cpu for gloo)."""
+    """Neighbour exchange over torch.distributed (one rank per process).  Buffers are torch uint8 tensors on
+    the communication device (cuda for NCCL, cpu for gloo); every message has the same, fixed size."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -104,46 +138,19 @@ class DistExchange:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def exchange_counts(self, counts4, device):
-        """counts4 = (mig_left, ghost_left, mig_right, ghost_right) of this rank -> what the left
-        neighbour sends right to us and what the right neighbour sends left to us."""
-        import torch
-        mine = torch.tensor(list(counts4), dtype=torch.int64, device=device)
-        every = torch.empty(self.world * 4, dtype=torch.int64, device=device)
-        self.dist.all_gather_into_tensor(every, mine, group=self.group)
-        every = every.cpu().view(self.world, 4)
-        from_left = (int(every[self.rank - 1, 2]), int(every[self.rank - 1, 3])) if self.rank > 0 else (0, 0)
-        from_right = (int(every[self.rank + 1, 0]), int(every[self.rank + 1, 1])) if self.rank < self.world - 1 else (0, 0)
-        return from_left, from_right
-
-    def exchange(self, counts4, to_left, to_right, from_left, from_right):
-        """Moves to_left -> rank-1's from_right and to_right -> rank+1's from_left.  Returns
-        ((mig, ghost) from the left neighbour, (mig, ghost) from the right neighbour)."""
+    def exchange(self, to_left, to_right, from_left, from_right, nbytes: int):
+        """to_left -> rank-1's from_right, to_right -> rank+1's from_left; asynchronous on the current stream."""
         dist = self.dist
-        fl, fr = self.exchange_counts(counts4, to_left.device)
         ops = []
         if self.rank > 0:
-            nb = message_bytes(counts4[0], counts4[1])
-            if nb:
-                ops.append(dist.P2POp(dist.isend, to_left[:nb], self.rank - 1, self.group))
-            nb = message_bytes(*fl)
-            if nb:
-                if nb > from_left.numel():
-                    raise RuntimeError("slab exchange: receive buffer too small")
-                ops.append(dist.P2POp(dist.irecv, from_left[:nb], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.isend, to_left[:nbytes], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, from_left[:nbytes], self.rank - 1, self.group))
         if self.rank < self.world - 1:
-            nb = message_bytes(counts4[2], counts4[3])
-            if nb:
-                ops.append(dist.P2POp(dist.isend, to_right[:nb], self.rank + 1, self.group))
-            nb = message_bytes(*fr)
-            if nb:
-                if nb > from_right.numel():
-                    raise RuntimeError("slab exchange: receive buffer too small")
-                ops.append(dist.P2POp(dist.irecv, from_right[:nb], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.isend, to_right[:nbytes], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, from_right[:nbytes], self.rank + 1, self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        return fl, fr
+                req.wait()            # CUDA: makes the current stream wait, not the host
 
     def global_sum(self, values, device):
         import torch
@@ -159,47 +166,129 @@ class SlabSolver(FluidSolver):
     """One slab: a libfsg context with rank/world/slab range set + the message buffers.  With
     `exchange` = DistExchange this is the per-process solver of a multi-GPU run."""
 
-    def __init__(self, cfg: FsgConfig, exchange=None, msg_bytes: int | None = None):
+    def __init__(self, cfg: FsgConfig, exchange=None, cap_m: int = 4096, cap_g: int = 65536):
         import torch
         super().__init__(cfg)
         self.torch = torch
         self.exchange = exchange
         self.tdev = torch.device("cuda", cfg.device)
-        if msg_bytes is None:
-            msg_bytes = max(1 << 20, int(cfg.capacity) * 64 // 4)
-        self.msg_bytes = int(msg_bytes)
+        self.cap_m, self.cap_g = int(cap_m), int(cap_g)
+        self.msg_bytes = message_bytes(self.cap_m, self.cap_g)
         with torch.cuda.device(self.tdev):
             self.to_left, self.to_right, self.from_left, self.from_right = (
-                torch.empty(self.msg_bytes, dtype=torch.uint8, device=self.tdev) for _ in range(4))
+                torch.zeros(self.msg_bytes, dtype=torch.uint8, device=self.tdev) for _ in range(4))
         self.tstream = torch.cuda.ExternalStream(self.stream(), device=self.tdev)
-        self.last_counts = (0, 0, 0, 0)
-        self.traffic_bytes = 0
+        self.steps_exchanged = 0
+        self.peer = False               # True after setup_peer_exchange(): messages go straight into the neighbours' memory
+        self.time_exchange = False      # record CUDA events around pack / exchange / unpack (exchange_ms())
+        self._ev = []
 
-    # -- the three slab phases --
+    def close(self):
+        if self._ctx and self.peer:
+            self._lib.fsg_slab_close_peers(self._ctx)
+            self.peer = False
+        super().close()
+
+    # -- the slab phases (all asynchronous) --
     def pack(self):
-        counts = (C.c_int64 * 5)()
-        self._check(self._lib.fsg_slab_pack(self._ctx, self.to_left.data_ptr(), self.to_right.data_ptr(), self.msg_bytes,
-                                            C.byref(counts)), "fsg_slab_pack")
-        self.last_counts = tuple(int(v) for v in counts[:4])
-        return self.last_counts
+        self._check(self._lib.fsg_slab_pack(self._ctx, self.to_left.data_ptr(), self.to_right.data_ptr(), self.cap_m, self.cap_g),
+                    "fsg_slab_pack")
 
-    def unpack(self, from_left_ptr, fl, from_right_ptr, fr):
-        self._check(self._lib.fsg_slab_unpack(self._ctx, from_left_ptr, fl[0], fl[1], from_right_ptr, fr[0], fr[1]), "fsg_slab_unpack")
+    def unpack(self, from_left_ptr, from_right_ptr):
+        self._check(self._lib.fsg_slab_unpack(self._ctx, from_left_ptr, from_right_ptr, self.cap_m, self.cap_g), "fsg_slab_unpack")
+
+    def setup_peer_exchange(self):
+        """Maps the neighbours' inboxes into this process (CUDA IPC; one process per GPU on one node).  From
+        then on a step copies its messages straight into the neighbours' memory over NVLink and only sends a
+        4-byte NCCL message per neighbour to order their streams behind the copy."""
+        torch, ex = self.torch, self.exchange
+        self._check(self._lib.fsg_slab_alloc_messages(self._ctx, self.cap_m, self.cap_g), "fsg_slab_alloc_messages")
+        mine = {}
+        for side in (0, 1):
+            for par in (0, 1):
+                buf = (C.c_ubyte * 64)()
+                self._check(self._lib.fsg_slab_inbox_handle(self._ctx, side, par, buf), "fsg_slab_inbox_handle")
+                mine[(side, par)] = bytes(buf)
+        every = [None] * ex.world
+        ex.dist.all_gather_object(every, mine, group=ex.group)
+        for par in (0, 1):
+            if ex.rank > 0:                  # the left neighbour receives from its right (side 1) what I send to my left
+                self._check(self._lib.fsg_slab_open_peer(self._ctx, 0, par, every[ex.rank - 1][(1, par)]), "fsg_slab_open_peer")
+            if ex.rank < ex.world - 1:
+                self._check(self._lib.fsg_slab_open_peer(self._ctx, 1, par, every[ex.rank + 1][(0, par)]), "fsg_slab_open_peer")
+        with torch.cuda.device(self.tdev):
+            self._sig = [torch.zeros(1, dtype=torch.int32, device=self.tdev) for _ in range(4)]
+        self.peer = True
+
+    def _signal_neighbours(self):
+        """Stream-ordered 4-byte send/recv with each neighbour: their unpack runs after my copy has landed."""
+        ex, dist = self.exchange, self.exchange.dist
+        ops = []
+        if ex.rank > 0:
+            ops += [dist.P2POp(dist.isend, self._sig[0], ex.rank - 1, ex.group), dist.P2POp(dist.irecv, self._sig[1], ex.rank - 1, ex.group)]
+        if ex.rank < ex.world - 1:
+            ops += [dist.P2POp(dist.isend, self._sig[2], ex.rank + 1, ex.group), dist.P2POp(dist.irecv, self._sig[3], ex.rank + 1, ex.group)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def check(self) -> dict:
+        """Synchronises; raises FsgError if a message / the capacity overflowed or a particle left the ghost band."""
+        info = (C.c_int64 * 9)()
+        self._check(self._lib.fsg_slab_check(self._ctx, C.byref(info)), "fsg_slab_check")
+        v = [int(x) for x in info]
+        return dict(sent=(v[0], v[1], v[2], v[3]), received=(v[4], v[5], v[6], v[7]), slots_in_use=v[8])
 
     def step(self, nsteps: int = 1, sync: bool = True):
         torch = self.torch
+
+        def mark():
+            if self.time_exchange:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(self.tstream)
+                self._ev.append(e)
         for _ in range(nsteps):
-            counts = self.pack()
-            with torch.cuda.stream(self.tstream):       # P2P ops are ordered after the pack kernels on the solver's stream
-                fl, fr = self.exchange.exchange(counts, self.to_left, self.to_right, self.from_left, self.from_right)
-            self.traffic_bytes += message_bytes(counts[0], counts[1]) + message_bytes(counts[2], counts[3])
-            self.unpack(self.from_left.data_ptr(), fl, self.from_right.data_ptr(), fr)
+            mark()
+            if self.peer:
+                self._check(self._lib.fsg_slab_pack_send(self._ctx), "fsg_slab_pack_send")      # pack + copy into the neighbours' inboxes
+                mark()
+                with torch.cuda.stream(self.tstream):
+                    self._signal_neighbours()
+                mark()
+                self._check(self._lib.fsg_slab_unpack_recv(self._ctx), "fsg_slab_unpack_recv")
+            else:
+                self.pack()
+                mark()
+                with torch.cuda.stream(self.tstream):   # P2P ops are ordered after the pack kernels on the solver's stream
+                    self.exchange.exchange(self.to_left, self.to_right, self.from_left, self.from_right, self.msg_bytes)
+                mark()
+                self.unpack(self.from_left.data_ptr(), self.from_right.data_ptr())
+            mark()
             self._check(self._lib.fsg_step(self._ctx, 1), "fsg_step")
+            self.steps_exchanged += 1
         if sync:
             self.sync()
 
+    def exchange_ms(self) -> dict:
+        """Mean device milliseconds per step of pack / exchange (incl. waiting for the neighbours) / unpack."""
+        self.sync()
+        ev, out = self._ev, {"pack": 0.0, "exchange": 0.0, "unpack": 0.0}
+        k = len(ev) // 4
+        for i in range(k):
+            a, b, c, d = ev[4 * i:4 * i + 4]
+            out["pack"] += a.elapsed_time(b)
+            out["exchange"] += b.elapsed_time(c)
+            out["unpack"] += c.elapsed_time(d)
+        self._ev = []
+        return {q: v / max(1, k) for q, v in out.items()}
+
+    @property
+    def wire_bytes_per_step(self) -> int:
+        """Bytes this rank sends per step (fixed-size messages to its 1 or 2 neighbours)."""
+        return self.msg_bytes * ((self.cfg.rank > 0) + (self.cfg.rank < self.cfg.world - 1))
+
     def download(self, fields=None) -> dict:
-        """Only the particles this slab owns (ghost / migrated slots are dropped)."""
+        """Only the particles this slab owns (ghost / migrated / unused slots are dropped)."""
         out = super().download()
         keep = out["cell"] <= self.numcells
         return {k: v[keep] for k, v in out.items() if fields is None or k in fields}
@@ -212,10 +301,10 @@ class SlabSolver(FluidSolver):
 # W slabs in one process on one device (tests; single-GPU emulation of the multi-rank algorithm)
 # ---------------------------------------------------------------------------------------------
 class SlabGroup:
-    def __init__(self, base_cfg: FsgConfig, world: int, cuts, capacity: int, device: int = 0, msg_bytes: int | None = None):
+    def __init__(self, base_cfg: FsgConfig, world: int, cuts, capacity: int, device: int = 0, cap_m: int = 4096, cap_g: int = 65536):
         self.world = world
         self.cuts = cuts
-        self.slabs = [SlabSolver(slab_config(base_cfg, r, world, cuts, capacity, device), None, msg_bytes) for r in range(world)]
+        self.slabs = [SlabSolver(slab_config(base_cfg, r, world, cuts, capacity, device), None, cap_m, cap_g) for r in range(world)]
 
     def close(self):
         for s in self.slabs:
@@ -236,21 +325,22 @@ class SlabGroup:
 
     def step(self, nsteps: int = 1):
         for _ in range(nsteps):
-            counts = [s.pack() for s in self.slabs]
+            for s in self.slabs:
+                s.pack()
             for s in self.slabs:
                 s.sync()             # messages are read by the neighbour's stream
             for r, s in enumerate(self.slabs):
                 left, right = (self.slabs[r - 1] if r > 0 else None), (self.slabs[r + 1] if r < self.world - 1 else None)
-                fl = (counts[r - 1][2], counts[r - 1][3]) if left else (0, 0)
-                fr = (counts[r + 1][0], counts[r + 1][1]) if right else (0, 0)
-                s.unpack(left.to_right.data_ptr() if left else None, fl, right.to_left.data_ptr() if right else None, fr)
-                s.traffic_bytes += message_bytes(counts[r][0], counts[r][1]) + message_bytes(counts[r][2], counts[r][3])
+                s.unpack(left.to_right.data_ptr() if left else None, right.to_left.data_ptr() if right else None)
             for s in self.slabs:
                 s.sync()
             for s in self.slabs:
                 s._check(s._lib.fsg_step(s._ctx, 1), "fsg_step")
             for s in self.slabs:
                 s.sync()
+
+    def check(self) -> list:
+        return [s.check() for s in self.slabs]
 
     def download(self) -> dict:
         parts = [s.download() for s in self.slabs]

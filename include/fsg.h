@@ -181,20 +181,34 @@ FSG_API int  fsg_device_ptr(fsg_ctx *ctx, int which, void **ptr);
 
 /* ---- slab decomposition along x (world > 1): the multi-device hand-off of solver-unidyn.cu:396-470 ----
  * Every step of a slab context is   fsg_slab_pack -> (caller moves the two messages to the x-neighbours,
- * e.g. NCCL send/recv) -> fsg_slab_unpack -> fsg_step(ctx, 1).
- * fsg_slab_pack classifies the particles by their new bin layer: those that left the slab are moved
- * out (migrants, full 64-byte state), those in the slab's outermost layers are copied (ghosts, the
- * 32-byte read state the neighbour's pair sums need; the reference ships a one-layer `buffer` of whole
- * Particle records instead, solver-unidyn.cu:187,421-462).  Message layout (device memory):
- *   [posd m][velp m][accf m][dpi m][posd g][velp g]   float4 arrays, m migrants then g ghosts.
- * counts[5] (host): migrants/ghosts for the left neighbour, migrants/ghosts for the right one, and the
- * number of particle slots in use.  Order inside the messages is the particles' current order
- * (deterministic).  d_to_left / d_to_right hold cap_bytes each. */
-FSG_API int  fsg_slab_pack(fsg_ctx *ctx, void *d_to_left, void *d_to_right, int64_t cap_bytes, int64_t counts[5]);
-FSG_API int  fsg_slab_unpack(fsg_ctx *ctx, const void *d_from_left, int64_t mig_left, int64_t ghost_left,
-                             const void *d_from_right, int64_t mig_right, int64_t ghost_right);
-/* bytes of a message holding m migrants and g ghosts */
-FSG_API int64_t fsg_slab_message_bytes(int64_t m, int64_t g);
+ * e.g. NCCL send/recv) -> fsg_slab_unpack -> fsg_step(ctx, 1).   ALL of it is asynchronous on the
+ * context's stream: no call reads anything back, so the host can run steps ahead of the device.
+ * fsg_slab_pack classifies the particles by their new bin layer: those that left the slab are sent with
+ * their full 64-byte state (migrants; the sender keeps them one more step as ghosts), those in the slab's
+ * outermost layers are copied with the 32-byte read state the neighbour's pair sums need (ghosts; the
+ * reference ships a one-layer `buffer` of whole Particle records instead, solver-unidyn.cu:187,421-462).
+ * Message = device memory of fsg_slab_message_bytes(cap_m, cap_g) bytes, the SAME size on every rank:
+ *   [64-byte header: int64 migrants, int64 ghosts][posd cap_m][velp cap_m][accf cap_m][dpi cap_m][posd cap_g][velp cap_g]
+ * The receiver reads the counts from the header on the device.  Order inside the messages is the
+ * particles' current order (two-phase count / scan / scatter: deterministic).  A slab context always
+ * works on `capacity` slots; unused slots hold a dead key and sort last.
+ * fsg_slab_check synchronises and reports overflow / ghost-band violations (see fsg_slab.cu). */
+FSG_API int  fsg_slab_pack(fsg_ctx *ctx, void *d_to_left, void *d_to_right, int64_t cap_m, int64_t cap_g);
+FSG_API int  fsg_slab_unpack(fsg_ctx *ctx, const void *d_from_left, const void *d_from_right, int64_t cap_m, int64_t cap_g);
+FSG_API int  fsg_slab_check(fsg_ctx *ctx, int64_t info[9]);
+FSG_API int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g);
+/* Peer-memory variant (one process per GPU on one node): the library owns the message buffers, the
+ * neighbours' inboxes are mapped through CUDA IPC and fsg_slab_pack_send copies the packed messages straight
+ * into them over NVLink (copy engines).  The caller exchanges the 64-byte handles once
+ * (fsg_slab_inbox_handle -> neighbour -> fsg_slab_open_peer) and, every step, orders the neighbour's stream
+ * behind the copy with any stream-ordered signal (a few-byte NCCL send/recv).  side 0 = left, 1 = right;
+ * inboxes are double-buffered by step parity. */
+FSG_API int  fsg_slab_alloc_messages(fsg_ctx *ctx, int64_t cap_m, int64_t cap_g);
+FSG_API int  fsg_slab_inbox_handle(fsg_ctx *ctx, int side, int parity, void *handle64);
+FSG_API int  fsg_slab_open_peer(fsg_ctx *ctx, int side, int parity, const void *handle64);
+FSG_API int  fsg_slab_pack_send(fsg_ctx *ctx);
+FSG_API int  fsg_slab_unpack_recv(fsg_ctx *ctx);
+FSG_API int  fsg_slab_close_peers(fsg_ctx *ctx);
 
 /* ---- (2) stage API: caller-owned DEVICE buffers in the reference's own layout ---- */
 /* replaces thrust::sort_by_key(t_v, t_v + n, t_a)            solver.cu:181 */

@@ -341,7 +341,7 @@ def test_slabs_match_single_device(fsg, world, fast):
             s.upload({f: cur[f] for f in cur if f != "cell"})
             g.step(1)
             s.step(1)
-            moved += sum(sl.last_counts[0] + sl.last_counts[2] for sl in g.slabs)
+            moved += sum(c["sent"][0] + c["sent"][2] for c in g.check())
             a, b = fsg.by_index(g.download()), fsg.by_index(s.download())
             assert np.array_equal(a["index"], b["index"])
             for f in ("pos", "vel", "cell", "boundary"):
@@ -385,8 +385,21 @@ def test_slab_ghost_band_violation_is_reported(fsg):
     with fsg.SlabGroup(cfg, 2, cuts, capacity=16) as g:
         g.upload(state)
         g.step(1)
+        g.check()
+        g.step(1)
         with pytest.raises(fsg.FsgError, match="ghost band"):
-            g.step(1)
+            g.check()
+
+
+def test_slab_message_overflow_is_reported(fsg):
+    cfg, state = _slab_scene(fsg, False)
+    n = state["pos"].shape[0]
+    cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), 2)
+    with fsg.SlabGroup(cfg, 2, cuts, capacity=2 * n, cap_m=16, cap_g=16) as g:
+        g.upload(state)
+        g.step(1)
+        with pytest.raises(fsg.FsgError, match="capacity"):
+            g.check()
 
 
 # ---------------------------------------------------------------------------------------------

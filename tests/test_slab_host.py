@@ -32,7 +32,9 @@ def test_plume_layer_hist_matches_scene(fsg):
     state = fsg.scenes.plume_scene(cfg, jitter=0.0)
     assert hist.sum() == state["pos"].shape[0]
     assert np.array_equal(hist, fsg.slab.layer_hist_from_positions(cfg, state["pos"]))
-    assert fsg.slab.message_bytes(3, 5) == fsg._lib.load().fsg_slab_message_bytes(3, 5) == (4 * 3 + 2 * 5) * 16
+    assert fsg.slab.message_bytes(3, 5) == fsg._lib.load().fsg_slab_message_bytes(3, 5) == 64 + (4 * 3 + 2 * 5) * 16
+    cap_m, cap_g = fsg.slab.message_caps(hist, fsg.slab_cuts(hist, 3))
+    assert cap_g >= hist.max() and cap_m >= 4096
 
 
 def _free_port():
@@ -47,46 +49,25 @@ def _exchange_worker(rank, world, port, rounds):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         ex = DistExchange()
-        cap = 1 << 16
-        for rnd in range(rounds):
-            # counts every rank can recompute for every other rank
-            def counts_of(r):
-                g = np.random.default_rng(1000 * rnd + r)
-                c = [int(v) for v in g.integers(0, 40, 4)]
-                if rnd == 1:
-                    c = [0, 0, 0, 0]                    # a round with nothing to move
-                if r == 0:
-                    c[0] = c[1] = 0                     # no left neighbour
-                if r == world - 1:
-                    c[2] = c[3] = 0
-                return c
+        nbytes = message_bytes(37, 211)
 
-            def payload(r, side, nbytes):
-                g = np.random.default_rng(7 + 10 * r + side + 100 * rnd)
-                return torch.from_numpy(g.integers(0, 256, nbytes, dtype=np.uint8))
-            c = counts_of(rank)
-            to_left, to_right = torch.zeros(cap, dtype=torch.uint8), torch.zeros(cap, dtype=torch.uint8)
-            nl, nr = message_bytes(c[0], c[1]), message_bytes(c[2], c[3])
-            to_left[:nl] = payload(rank, 0, nl)
-            to_right[:nr] = payload(rank, 1, nr)
-            from_left, from_right = torch.full((cap,), 255, dtype=torch.uint8), torch.full((cap,), 255, dtype=torch.uint8)
-            fl, fr = ex.exchange(c, to_left, to_right, from_left, from_right)
+        def payload(r, side, rnd):
+            g = np.random.default_rng(7 + 10 * r + side + 100 * rnd)
+            return torch.from_numpy(g.integers(0, 256, nbytes, dtype=np.uint8))
+        for rnd in range(rounds):
+            to_left, to_right = payload(rank, 0, rnd), payload(rank, 1, rnd)
+            from_left, from_right = torch.full((nbytes,), 255, dtype=torch.uint8), torch.full((nbytes,), 255, dtype=torch.uint8)
+            ex.exchange(to_left, to_right, from_left, from_right, nbytes)
             if rank > 0:
-                cl = counts_of(rank - 1)
-                assert fl == (cl[2], cl[3])
-                nb = message_bytes(*fl)
-                assert torch.equal(from_left[:nb], payload(rank - 1, 1, nb))
+                assert torch.equal(from_left, payload(rank - 1, 1, rnd))        # the left neighbour's message to its right
             else:
-                assert fl == (0, 0)
+                assert bool((from_left == 255).all())                           # untouched: no left neighbour
             if rank < world - 1:
-                cr = counts_of(rank + 1)
-                assert fr == (cr[0], cr[1])
-                nb = message_bytes(*fr)
-                assert torch.equal(from_right[:nb], payload(rank + 1, 0, nb))
+                assert torch.equal(from_right, payload(rank + 1, 0, rnd))
             else:
-                assert fr == (0, 0)
-            tot = ex.global_sum([c[0] + c[2], 1], "cpu")
-            assert tot[1] == world and tot[0] == sum(counts_of(r)[0] + counts_of(r)[2] for r in range(world))
+                assert bool((from_right == 255).all())
+            tot = ex.global_sum([rank + 1, 1], "cpu")
+            assert tot[1] == world and tot[0] == world * (world + 1) // 2
     finally:
         dist.destroy_process_group()
 
