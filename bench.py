@@ -38,6 +38,7 @@ import numpy as np  # noqa: E402
 
 ALG_BYTES_STEP = 272      # algorithmic HBM bytes per particle-step (reorder 136 + tables 4 + pair/update 132)
 ALG_BYTES_PAIR = 132      # the fused pair-sum/EOS/integrate/re-bin kernel: read 64 + write 64 + new key 4
+NCU_PAIR_DRAM_BYTES_PER_PARTICLE = 47.2   # measured: ncu --set full on k_pair_v2 at 256^3 (profiles/r1_ncu_pair_v2_final.txt)
 FLOP_IN_RANGE, FLOP_REJECTED = 50, 12   # SURVEY.md §8d algorithmic flop per in-range / rejected candidate
 SPACING, JITTER, SEED = 0.05, 0.005, 20261018
 CPU_SAMPLE_GRID = 128     # bounded sample for the CPU legs: the same plume at 128^3 bins (1.07 M particles)
@@ -249,8 +250,12 @@ def fsg_arm(args):
     # ---- roofline of the dominant kernel ----
     pair_ms = phase["pair_update"] / max(1, phase["steps"])
     achieved = ALG_BYTES_PAIR * n_local / (pair_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_pair_update_fast (pair sums + EOS/integrate/re-bin)", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "k_pair_v2 + k_update (pair sums, then EOS/integrate/re-bin)", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": NCU_PAIR_DRAM_BYTES_PER_PARTICLE * n_local + 152.0 * n_local, "peak_source": peak_src,
+                "traffic_note": "k_pair_v2: dram__bytes_read+write = 402.6 MB per launch at 256^3 under ncu --set full "
+                                "(profiles/r1_ncu_pair_v2_final.txt) = 47.2 B/particle, scaled by the particle count; k_update: its 152 B/particle "
+                                "of streaming reads + writes",
                 "kernel_ms": pair_ms, "share_of_step": pair_ms / ms_step,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PAIR * n_local,
                 "note": "this kernel is CUDA-core (FP32 issue) bound, not HBM bound: see roofline_fp32; the HBM-bound phases are in `phases`"}

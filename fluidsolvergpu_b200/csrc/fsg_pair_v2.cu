@@ -22,14 +22,15 @@
 //   * sums (newdens, newdelpress x/y/z) go to a float4 array that k_update consumes.
 #include "fsg_device.cuh"
 
-#define V2_CWARPS 4                     // consumer warps per block
-#define V2_THREADS ((V2_CWARPS + 1) * 32)
+#include <stdlib.h>
+
+#define V2_CWARPS_MAX 8                 // consumer warps per block: template parameter CW (4, 6 or 8)
 #define V2_TILE 512                     // staged candidates per stage
 #define V2_NST 3                        // pipeline stages
 #define V2_QCAP 160                     // near-pair queue entries per warp (drained at >= 32)
 #define V2_GROUP 32                     // home particles per item
 #define V2_BINS_PER_GRAB 16
-#define V2_BLOCKS_PER_SM 6
+#define V2_DEFAULT_CW 4
 
 struct V2Stage {
     float4 sp[V2_TILE];                 // candidate (x, y, z, +-dens)
@@ -42,9 +43,10 @@ struct V2Warp {
     unsigned q[V2_QCAP];
     float4 acc[8];                      // the warp's home particles of the group: dens, delpress x/y/z
 };
+template <int CW>
 struct V2Smem {
     V2Stage st[V2_NST];
-    V2Warp w[V2_CWARPS];
+    V2Warp w[CW];
     unsigned long long full[V2_NST];
 };
 
@@ -75,18 +77,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // "stage is free again" goes through hardware named barriers (ids 1..V2_NST): the consumer warps
 // arrive without blocking, the producer warp blocks in bar.sync — no polling, no issue slots taken
 // from the consumers while the producer is stages ahead.
+template <int THREADS>
 __device__ __forceinline__ void stage_free_arrive(int stage)
 {
     // constant barrier ids, so that the kernel reserves V2_NST + 1 barriers and not all 16
-    if (stage == 0) asm volatile("bar.arrive 1, %0;" ::"n"(V2_THREADS) : "memory");
-    else if (stage == 1) asm volatile("bar.arrive 2, %0;" ::"n"(V2_THREADS) : "memory");
-    else asm volatile("bar.arrive 3, %0;" ::"n"(V2_THREADS) : "memory");
+    if (stage == 0) asm volatile("bar.arrive 1, %0;" ::"n"(THREADS) : "memory");
+    else if (stage == 1) asm volatile("bar.arrive 2, %0;" ::"n"(THREADS) : "memory");
+    else asm volatile("bar.arrive 3, %0;" ::"n"(THREADS) : "memory");
 }
+template <int THREADS>
 __device__ __forceinline__ void stage_free_wait(int stage)
 {
-    if (stage == 0) asm volatile("bar.sync 1, %0;" ::"n"(V2_THREADS) : "memory");
-    else if (stage == 1) asm volatile("bar.sync 2, %0;" ::"n"(V2_THREADS) : "memory");
-    else asm volatile("bar.sync 3, %0;" ::"n"(V2_THREADS) : "memory");
+    if (stage == 0) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+    else if (stage == 1) asm volatile("bar.sync 2, %0;" ::"n"(THREADS) : "memory");
+    else asm volatile("bar.sync 3, %0;" ::"n"(THREADS) : "memory");
 }
 static_assert(V2_NST == 3, "stage_free_* name one barrier per stage");
 // 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on `bar`
@@ -136,6 +140,7 @@ struct V2Args {
 };
 
 // one batch of <= 32 queued near pairs: lanes = pairs, segmented scan keyed by the home slot
+template <int CW>
 __device__ __forceinline__ void v2_drain_batch(const FsgDev &d, const V2Stage &S, V2Warp &W, const float4 *__restrict__ velp,
                                                int qh, int qn, int lane, int warp)
 {
@@ -147,7 +152,7 @@ __device__ __forceinline__ void v2_drain_batch(const FsgDev &d, const V2Stage &S
         unsigned ent = W.q[e];
         key = (int)(ent >> 16);                                   // slot within the warp: pass * 2 + which
         int c = (int)(ent & 0xffffu);
-        int k = 8 * (key >> 1) + 2 * warp + (key & 1);            // home particle within the group
+        int k = 2 * CW * (key >> 1) + 2 * warp + (key & 1);       // home particle within the group (warp = rotated warp slot)
         int i = S.hs + k, j = 0;
 #pragma unroll
         for (int r = 0; r < 9; r++) {                             // runs are staged in ascending slot order
@@ -172,12 +177,13 @@ __device__ __forceinline__ void v2_drain_batch(const FsgDev &d, const V2Stage &S
     __syncwarp();
 }
 
-template <bool STATS, bool HASB>
-__global__ void __launch_bounds__(V2_THREADS, V2_BLOCKS_PER_SM)
+template <bool STATS, bool HASB, int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, (CW == 4 ? 6 : CW == 6 ? 5 : 4))
 k_pair_v2(V2Args va)
 {
+    constexpr int PASSES = (V2_GROUP + 2 * CW - 1) / (2 * CW);
     extern __shared__ __align__(128) unsigned char s_raw[];
-    V2Smem &SM = *reinterpret_cast<V2Smem *>(s_raw);
+    V2Smem<CW> &SM = *reinterpret_cast<V2Smem<CW> *>(s_raw);
     const PairArgs &a = va.a;
     const FsgDev &d = a.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,7 +198,7 @@ k_pair_v2(V2Args va)
     }
     __syncthreads();
 
-    if (warp == V2_CWARPS) {
+    if (warp == CW) {
         // =========================== producer ===========================
         int it = 0;
         int grab = 0, grab_end = 0, mybin = 0;
@@ -220,7 +226,7 @@ k_pair_v2(V2Args va)
             }
             if (grab >= nocc) {
                 const int stage = it % V2_NST;
-                if (it >= V2_NST) stage_free_wait(stage);
+                if (it >= V2_NST) stage_free_wait<(CW + 1) * 32>(stage);
                 if (lane == 0) {
                     SM.st[stage].gcount = -1;
                     mbar_arrive(&SM.full[stage]);
@@ -256,7 +262,7 @@ k_pair_v2(V2Args va)
                     const int ct = min(V2_TILE, C - t0);
                     const int stage = it % V2_NST;
                     V2Stage &S = SM.st[stage];
-                    if (it >= V2_NST) stage_free_wait(stage);
+                    if (it >= V2_NST) stage_free_wait<(CW + 1) * 32>(stage);
                     // run table + padding + header (generic-proxy writes, published by the arrive below)
                     if (lane < 12) {
                         int lo = max(excl, t0), hi = min(excl + rp, t0 + ct);
@@ -295,6 +301,7 @@ k_pair_v2(V2Args va)
     const float w_outer = d.w_c * 0.25f;
     const float inv_h = d.inv_h;
     unsigned long long st_tested = 0, st_in = 0;
+    int rot = 0;
 
     for (int it = 0;; it++) {
         const int stage = it % V2_NST;
@@ -304,12 +311,17 @@ k_pair_v2(V2Args va)
         if (gcount < 0) break;
         const int ct = S.ct;
         const int cpad = (ct + 31) & ~31;
+        // the pairs of home particles are dealt to the warps round-robin; rotating the deal from item to item
+        // keeps the warps of a block level over time (without it warp 0 always gets the odd pair out and the
+        // others end up waiting for it at the stage release)
+        if (S.first) rot = (rot + 1 == CW) ? 0 : rot + 1;       // (constant over the tiles of one group: acc[] persists across them)
+        const int wr = (warp + rot) % CW;
         if (S.first && lane < 8) W.acc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
         int qn = 0;
 #pragma unroll 1
-        for (int pass = 0; pass < 4; pass++) {
-            const int k0 = 8 * pass + 2 * warp;
+        for (int pass = 0; pass < PASSES; pass++) {
+            const int k0 = 2 * CW * pass + 2 * wr;
             if (k0 >= gcount) break;
             const bool has1 = k0 + 1 < gcount;
             const float4 pi0 = S.hp[k0];
@@ -378,7 +390,7 @@ k_pair_v2(V2Args va)
                     __syncwarp();
                     if (qn >= V2_QCAP - 32) {                      // keep room for one more round
                         int qh = 0;
-                        while (qn - qh >= 32) { v2_drain_batch(d, S, W, a.A.velp, qh, qn, lane, warp); qh += 32; }
+                        while (qn - qh >= 32) { v2_drain_batch<CW>(d, S, W, a.A.velp, qh, qn, lane, wr); qh += 32; }
                         int left = qn - qh;
                         unsigned ent = 0;
                         if (lane < left) ent = W.q[qh + lane];
@@ -392,12 +404,12 @@ k_pair_v2(V2Args va)
         }
         // ---- drain the queue (entries refer to this stage's candidates) ----
         __syncwarp();
-        for (int qh = 0; qh < qn; qh += 32) v2_drain_batch(d, S, W, a.A.velp, qh, qn, lane, warp);
+        for (int qh = 0; qh < qn; qh += 32) v2_drain_batch<CW>(d, S, W, a.A.velp, qh, qn, lane, wr);
         const int last = S.last, hs = S.hs;
         __syncwarp();
-        stage_free_arrive(stage);
-        if (last && lane < 8) {
-            int k = 8 * (lane >> 1) + 2 * warp + (lane & 1);
+        stage_free_arrive<(CW + 1) * 32>(stage);
+        if (last && lane < 2 * PASSES) {
+            int k = 2 * CW * (lane >> 1) + 2 * wr + (lane & 1);
             if (k < gcount) va.sums[hs + k] = W.acc[lane];
         }
         __syncwarp();
@@ -439,32 +451,48 @@ k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B,
     keysB[i] = key;
 }
 
-cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool has_boundary, int sm_count, cudaStream_t s)
+template <int CW>
+static cudaError_t launch_pair_v2_cw(const V2Args &va, bool stats, bool has_boundary, int sm_count, cudaStream_t s)
 {
     static bool attr_done = false;
-    const int smem = (int)sizeof(V2Smem);
+    const int smem = (int)sizeof(V2Smem<CW>);
     if (!attr_done) {
-        cudaFuncSetAttribute(k_pair_v2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(k_pair_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(k_pair_v2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(k_pair_v2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<false, false, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<false, true, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<true, false, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<true, true, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
+    const int per_sm = CW == 4 ? 6 : CW == 6 ? 5 : 4;
+    int64_t blocks = ((int64_t)va.a.n + 2 * CW - 1) / (2 * CW);
+    int64_t maxb = (int64_t)sm_count * per_sm;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    const unsigned threads = (CW + 1) * 32;
+    if (stats) {
+        if (has_boundary) k_pair_v2<true, true, CW><<<(unsigned)blocks, threads, smem, s>>>(va);
+        else k_pair_v2<true, false, CW><<<(unsigned)blocks, threads, smem, s>>>(va);
+    } else {
+        if (has_boundary) k_pair_v2<false, true, CW><<<(unsigned)blocks, threads, smem, s>>>(va);
+        else k_pair_v2<false, false, CW><<<(unsigned)blocks, threads, smem, s>>>(va);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool has_boundary, int sm_count, cudaStream_t s)
+{
     V2Args va;
     va.a = a;
     va.sums = sums;
-    int64_t blocks = ((int64_t)a.n + 7) / 8;
-    int64_t maxb = (int64_t)sm_count * V2_BLOCKS_PER_SM;
-    if (blocks > maxb) blocks = maxb;
-    if (blocks < 1) blocks = 1;
-    if (stats) {
-        if (has_boundary) k_pair_v2<true, true><<<(unsigned)blocks, V2_THREADS, smem, s>>>(va);
-        else k_pair_v2<true, false><<<(unsigned)blocks, V2_THREADS, smem, s>>>(va);
-    } else {
-        if (has_boundary) k_pair_v2<false, true><<<(unsigned)blocks, V2_THREADS, smem, s>>>(va);
-        else k_pair_v2<false, false><<<(unsigned)blocks, V2_THREADS, smem, s>>>(va);
+    static int cw = 0;
+    if (!cw) {                                        // FSG_PAIR_CW = 4 | 6 | 8: consumer warps per block (tuning knob)
+        const char *e = getenv("FSG_PAIR_CW");
+        cw = e ? atoi(e) : V2_DEFAULT_CW;
+        if (cw != 4 && cw != 6 && cw != 8) cw = V2_DEFAULT_CW;
     }
-    return cudaGetLastError();
+    if (cw == 6) return launch_pair_v2_cw<6>(va, stats, has_boundary, sm_count, s);
+    if (cw == 8) return launch_pair_v2_cw<8>(va, stats, has_boundary, sm_count, s);
+    return launch_pair_v2_cw<4>(va, stats, has_boundary, sm_count, s);
 }
 
 cudaError_t fsg_launch_update(const FsgDev &d, int64_t n, const int *keysA, FsgState A, FsgState B, int *keysB,
