@@ -68,6 +68,8 @@ SIGNATURES = {
                                        C.POINTER(C.c_int64)]),
     "fsg_scene_plume_hist": (C.c_int, [C.POINTER(FsgConfig), C.c_double, P]),
     "fsg_device_ptr": (C.c_int, [P, C.c_int, C.POINTER(P)]),
+    "fsg_write_point_mesh": (C.c_int, [C.c_char_p, C.c_int, C.c_int, P, C.c_int, P, P, P]),
+    "fsg_write_frame": (C.c_int, [P, C.c_char_p, C.c_int]),
     "fsg_slab_pack": (C.c_int, [P, P, P, C.c_int64, C.c_int64]),
     "fsg_slab_unpack": (C.c_int, [P, P, P, C.c_int64, C.c_int64]),
     "fsg_slab_check": (C.c_int, [P, C.POINTER(C.c_int64 * 9)]),
@@ -78,6 +80,9 @@ SIGNATURES = {
     "fsg_slab_pack_send": (C.c_int, [P]),
     "fsg_slab_unpack_recv": (C.c_int, [P]),
     "fsg_slab_close_peers": (C.c_int, [P]),
+    "fsg_slab_set_peer": (C.c_int, [P, C.c_int, C.c_int, P]),
+    "fsg_slab_inbox_ptr": (P, [P, C.c_int, C.c_int]),
+    "fsg_slab_set_overlap": (C.c_int, [P, C.c_int]),
     "fsg_stage_sort": (C.c_int, [P, P, P, C.c_int64]),
     "fsg_stage_findneighbours": (C.c_int, [P, P, P, P, C.c_int64]),
     "fsg_stage_mykernel": (C.c_int, [P, P, P, P, P, C.c_int64]),

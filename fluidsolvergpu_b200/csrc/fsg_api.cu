@@ -33,6 +33,8 @@ void fsg_derive_constants(const fsg_config &cfg, FsgDev &d)
     d.numcells = cfg.grid * cfg.grid * cfg.grid;
     d.x0 = cfg.world > 1 ? cfg.slab_x0 : 0;
     d.x1 = cfg.world > 1 ? cfg.slab_x1 : cfg.grid;
+    d.bx0 = d.x0;
+    d.bx1 = d.x1;
     d.dead = d.numcells + 1;
     d.cap = cfg.neighbour_cap;
     d.bin_cap = cfg.bin_cap;
@@ -129,7 +131,12 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
     cudaFree(c->counters); cudaFree(c->dstats); cudaFree(c->sort_tmp);
     cudaFree(c->slab_cnt); cudaFree(c->scan_tmp);
-    for (int k = 0; k < 4; k++) if (c->peer_inbox[k]) cudaIpcCloseMemHandle(c->peer_inbox[k]);
+    if (c->comm) cudaStreamSynchronize(c->comm);
+    for (int k = 0; k < 4; k++) if (c->peer_inbox[k] && !c->peer_local) cudaIpcCloseMemHandle(c->peer_inbox[k]);
+    if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
+    if (c->ev_sent) cudaEventDestroy(c->ev_sent);
+    if (c->comm) cudaStreamDestroy(c->comm);
+    cudaFree(c->binlistB);
     for (int k = 0; k < 2; k++) cudaFree(c->outbox[k]);
     for (int k = 0; k < 4; k++) cudaFree(c->inbox[k]);
     cudaFree(c->stage);
@@ -260,6 +267,7 @@ extern "C" int fsg_sync(fsg_ctx *c)
     if (!c) return FSG_E_INVALID;
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (c->comm) CU(c, cudaStreamSynchronize(c->comm));
     return FSG_OK;
 }
 
@@ -274,6 +282,8 @@ static int after_upload(fsg_ctx *c, int64_t n)
         c->tables_dirty = false;
     }
     c->n = n;
+    c->sent_ahead = false;
+    if (c->comm) CU(c, cudaStreamSynchronize(c->comm));
     if (c->cfg.world > 1) {
         // a slab context always works on all `cap` slots (nothing on the host depends on how many are in use):
         // the tail holds the dead key, the device-side count of slots in use starts at n
@@ -573,6 +583,7 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         CU(c, cudaMemsetAsync(c->counters + nxt, 0, sizeof(int), c->stream));
         CU(c, cudaMemsetAsync(c->counters + 2, 0, 2 * sizeof(int), c->stream));
         CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(int), c->stream));
+        CU(c, cudaMemsetAsync(c->counters + 10, 0, 2 * sizeof(int), c->stream));
         if (c->cfg.collect_stats) CU(c, cudaMemsetAsync(c->dstats, 0, 4 * sizeof(unsigned long long), c->stream));
         if (prof) prof_mark(c);
         // thrust::sort_by_key, key half (solver.cu:181)
@@ -580,7 +591,8 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         if (prof) prof_mark(c);
         // value half + findneighbours (solver.cu:181-182)
         CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA,
-                                 c->start, c->end, c->binlist[nxt], c->counters + nxt, c->counters + 3, c->counters + 5, c->stream));
+                                 c->start, c->end, c->binlist[nxt], c->counters + nxt, c->binlistB ? c->binlistB : c->binlist[nxt],
+                                 c->counters + 10, c->counters + 3, c->counters + 5, c->stream));
         c->n_sorted = n;
         c->launches++;
         if (prof) prof_mark(c);

@@ -112,11 +112,11 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
 __global__ void __launch_bounds__(256)
 k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restrict__ keysA, FsgState src,
           FsgState dst, const float4 *__restrict__ carry_src, float4 *__restrict__ carry_dst, int *start, int *end,
-          int *binlist, int *nocc, int *nlive, int *nkeep)
+          int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep)
 {
     const int numcells = d.numcells;
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool head = false;
+    bool head = false, headB = false;
     if (k < n) {
         int sidx = perm[k];
         float4 a = src.posd[sidx], b = src.velp[sidx], c = src.accf[sidx], e = src.dpi[sidx];
@@ -133,36 +133,39 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
             if (key != prev) {
                 start[key] = (int)k;
                 int ix = key / d.G2;
-                head = ix >= d.x0 && ix < d.x1;       // home bins: the ones this slab owns
+                head = ix >= d.bx0 && ix < d.bx1;                         // interior home bins
+                headB = ix >= d.x0 && ix < d.x1 && !head;                 // boundary home bins (empty list unless the exchange overlaps)
             }
             if (key != next) end[key] = (int)k;
             if (next >= numcells) *nlive = (int)k + 1;
         }
         if (key <= numcells && next > numcells) *nkeep = (int)k + 1;   // live + parked; dead slots are trimmed
     }
-    // block-aggregated append of the home-bin heads: ONE atomic per block (a per-warp atomic on the
+    // block-aggregated append of the home-bin heads: ONE atomic per block and list (a per-warp atomic on the
     // single counter serialises in L2 and was the bottleneck of this kernel)
-    __shared__ int s_cnt[8], s_base;
+    __shared__ int s_cnt[2][8], s_base[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned m = __ballot_sync(FULL, head);
-    if (lane == 0) s_cnt[warp] = __popc(m);
+    const unsigned m = __ballot_sync(FULL, head), mB = __ballot_sync(FULL, headB);
+    if (lane == 0) { s_cnt[0][warp] = __popc(m); s_cnt[1][warp] = __popc(mB); }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 2) {
+        const int L = threadIdx.x;
         int tot = 0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) { int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
-        s_base = tot ? atomicAdd(nocc, tot) : 0;
+        for (int w = 0; w < 8; w++) { int c = s_cnt[L][w]; s_cnt[L][w] = tot; tot += c; }
+        s_base[L] = tot ? atomicAdd(L ? noccB : nocc, tot) : 0;
     }
     __syncthreads();
-    if (head) binlist[s_base + s_cnt[warp] + __popc(m & ((1u << lane) - 1))] = keysA[k];
+    if (head) binlist[s_base[0] + s_cnt[0][warp] + __popc(m & ((1u << lane) - 1))] = keysA[k];
+    if (headB) binlistB[s_base[1] + s_cnt[1][warp] + __popc(mB & ((1u << lane) - 1))] = keysA[k];
 }
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *nlive, int *nkeep, cudaStream_t s)
+                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     k_reorder<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst,
-                                                          start, end, binlist, nocc, nlive, nkeep);
+                                                          start, end, binlist, nocc, binlistB, noccB, nlive, nkeep);
     return cudaGetLastError();
 }
 
@@ -443,9 +446,28 @@ cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binli
     // Uncapped configuration (every particle of the 27 bins is visited): the pipelined pair-sum kernel
     // + the streaming update kernel (fsg_pair_v2.cu).  pair_fp64 == 3 keeps the fused kernel instead.
     if (c->cfg.pair_fp64 == 0 && c->dev.cap <= 0 && c->dev.bin_cap <= 0) {
-        cudaError_t e2 = fsg_launch_pair_v2(a, c->sums, stats, c->has_boundary, c->sm_count, s);
+        cudaError_t e2;
+        if (c->overlap && c->cfg.world > 1) {
+            // boundary bins first; once their particles are updated the next step's messages are packed and copied
+            // on the communication stream while the interior bins are still being computed on this one
+            PairArgs b = a;
+            b.binlist = c->binlistB;
+            b.nocc = c->counters + 10;
+            b.work = c->counters + 11;
+            e2 = fsg_launch_pair_v2(b, c->sums, stats, c->has_boundary, c->sm_count, 0, s);
+            if (e2 != cudaSuccess) return e2;
+            e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 1, s);
+            if (e2 != cudaSuccess) return e2;
+            if (fsg_slab_send_next(const_cast<fsg_ctx *>(c)) != FSG_OK) return cudaErrorUnknown;
+            e2 = fsg_launch_pair_v2(a, c->sums, stats, c->has_boundary, c->sm_count, 5, s);      // leave room for the pack kernels
+            if (e2 != cudaSuccess) return e2;
+            e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 2, s);
+            *launches += 4;
+            return e2;
+        }
+        e2 = fsg_launch_pair_v2(a, c->sums, stats, c->has_boundary, c->sm_count, 0, s);
         if (e2 != cudaSuccess) return e2;
-        e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, s);
+        e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 0, s);
         *launches += 2;
         return e2;
     }

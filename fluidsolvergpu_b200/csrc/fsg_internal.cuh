@@ -16,6 +16,8 @@
 struct FsgDev {
     int G, G2, numcells;
     int x0, x1;      // bin layers this context owns (0, G without slab decomposition)
+    int bx0, bx1;    // interior layers [bx0, bx1): home bins outside are the slab's boundary bins (done first when the
+                     // exchange overlaps the interior; == x0, x1 otherwise)
     int dead;        // key of a slot that no longer holds a particle of this slab (sorts last, is trimmed)
     int cap, bin_cap;
     float origin;
@@ -80,6 +82,13 @@ struct fsg_ctx {
     void *inbox[4];     // [2*side + parity]: from left / from right, double-buffered by step parity
     void *peer_inbox[4];// the neighbours' inboxes mapped through CUDA IPC: [0..1] left neighbour's from-right, [2..3] right neighbour's from-left
     int64_t msg_cap_m, msg_cap_g;
+    long long seq_send, seq_recv;   // exchange sequence numbers (stamps at the tail of every message)
+    bool peer_local;    // peer_inbox holds plain pointers of this process (fsg_slab_set_peer), not IPC mappings
+    bool overlap;       // pack + copies of the NEXT step's messages run on `comm` behind the boundary bins, beside the interior bins
+    bool sent_ahead;    // the messages of the next step have already been issued by fsg_step
+    cudaStream_t comm;
+    cudaEvent_t ev_boundary, ev_sent;
+    int *binlistB;      // boundary home bins of the current step (overlap mode)
     void *sort_tmp;
     void *stage;        // device staging area for host<->device conversion
     size_t stage_bytes;
@@ -117,7 +126,8 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
                                     int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *nlive, int *nkeep, cudaStream_t s);
+                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, cudaStream_t s);
+int fsg_slab_send_next(fsg_ctx *c);   // fsg_slab.cu: pack + copies of the next step's messages on c->comm (overlap mode)
 cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work,
                                    const float4 *carry, int *launches, cudaStream_t s);
 cudaError_t fsg_launch_unpack_aos(int model, const unsigned char *aos, int64_t n, FsgState st, float4 *carry,

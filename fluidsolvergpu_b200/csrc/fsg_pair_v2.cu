@@ -428,12 +428,17 @@ k_pair_v2(V2Args va)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B, int *__restrict__ keysB,
-         const float4 *__restrict__ sums, const float4 *__restrict__ carry)
+         const float4 *__restrict__ sums, const float4 *__restrict__ carry, int part)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 pd = A.posd[i], vp = A.velp[i], af = A.accf[i], dpi = A.dpi[i];
     int key = keysA[i];
+    if (part) {      // 1: the slab's boundary slots (boundary bins, ghosts, parked, dead), 2: the interior slots
+        const int ixp = key / d.G2;
+        const bool interior = key < d.numcells && ixp >= d.bx0 && ixp < d.bx1;
+        if (interior != (part == 2)) return;
+    }
+    float4 pd = A.posd[i], vp = A.velp[i], af = A.accf[i], dpi = A.dpi[i];
     if (key < d.numcells) {
         const int ix = key / d.G2;
         if (ix < d.x0 || ix >= d.x1) {      // ghost copy of a neighbour slab's particle: drop it
@@ -452,7 +457,7 @@ k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B,
 }
 
 template <int CW>
-static cudaError_t launch_pair_v2_cw(const V2Args &va, bool stats, bool has_boundary, int sm_count, cudaStream_t s)
+static cudaError_t launch_pair_v2_cw(const V2Args &va, bool stats, bool has_boundary, int sm_count, int blocks_per_sm, cudaStream_t s)
 {
     static bool attr_done = false;
     const int smem = (int)sizeof(V2Smem<CW>);
@@ -463,7 +468,8 @@ static cudaError_t launch_pair_v2_cw(const V2Args &va, bool stats, bool has_boun
         cudaFuncSetAttribute(k_pair_v2<true, true, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
-    const int per_sm = CW == 4 ? 6 : CW == 6 ? 5 : 4;
+    int per_sm = CW == 4 ? 6 : CW == 6 ? 5 : 4;
+    if (blocks_per_sm > 0 && blocks_per_sm < per_sm) per_sm = blocks_per_sm;
     int64_t blocks = ((int64_t)va.a.n + 2 * CW - 1) / (2 * CW);
     int64_t maxb = (int64_t)sm_count * per_sm;
     if (blocks > maxb) blocks = maxb;
@@ -479,7 +485,8 @@ static cudaError_t launch_pair_v2_cw(const V2Args &va, bool stats, bool has_boun
     return cudaGetLastError();
 }
 
-cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool has_boundary, int sm_count, cudaStream_t s)
+cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool has_boundary, int sm_count, int blocks_per_sm,
+                               cudaStream_t s)
 {
     V2Args va;
     va.a = a;
@@ -490,15 +497,15 @@ cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool
         cw = e ? atoi(e) : V2_DEFAULT_CW;
         if (cw != 4 && cw != 6 && cw != 8) cw = V2_DEFAULT_CW;
     }
-    if (cw == 6) return launch_pair_v2_cw<6>(va, stats, has_boundary, sm_count, s);
-    if (cw == 8) return launch_pair_v2_cw<8>(va, stats, has_boundary, sm_count, s);
-    return launch_pair_v2_cw<4>(va, stats, has_boundary, sm_count, s);
+    if (cw == 6) return launch_pair_v2_cw<6>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
+    if (cw == 8) return launch_pair_v2_cw<8>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
+    return launch_pair_v2_cw<4>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
 }
 
 cudaError_t fsg_launch_update(const FsgDev &d, int64_t n, const int *keysA, FsgState A, FsgState B, int *keysB,
-                              const float4 *sums, const float4 *carry, cudaStream_t s)
+                              const float4 *sums, const float4 *carry, int part, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_update<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, (int)n, keysA, A, B, keysB, sums, carry);
+    k_update<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, (int)n, keysA, A, B, keysB, sums, carry, part);
     return cudaGetLastError();
 }

@@ -42,14 +42,26 @@ __device__ __forceinline__ int slab_category(const FsgDev &d, int key, int rank,
     return c;
 }
 
+// Overlap mode packs while the interior particles of the step are still being updated: only slots whose
+// bin BEFORE the update (region = the sorted key array) was a boundary bin can have become migrants or
+// ghosts (a particle moves less than one bin per step), and only their new keys are read.
+__device__ __forceinline__ bool slab_in_region(const FsgDev &d, const int *__restrict__ region, int64_t i)
+{
+    if (!region) return true;
+    int rk = region[i];
+    if (rk >= d.numcells) return false;
+    int ix = rk / d.G2;
+    return ix >= d.x0 && ix < d.x1 && !(ix >= d.bx0 && ix < d.bx1);
+}
+
 // counts per warp: cnt[cat * nw + warp]
 __global__ void __launch_bounds__(256)
-k_slab_count(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ keys, int *__restrict__ cnt, int64_t nw,
-             int *violation)
+k_slab_count(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ keys, const int *__restrict__ region, int *__restrict__ cnt,
+             int64_t nw, int *violation)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int c = 0;
-    if (i < n) {
+    if (i < n && slab_in_region(d, region, i)) {
         int key = keys[i];
         c = slab_category(d, key, rank, world);
         // a particle that moved more than one bin layer in a step has left the one-layer ghost band
@@ -67,7 +79,9 @@ k_slab_count(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ k
 
 // Fixed-layout message (device memory), the same size on every rank so that nothing on the host depends
 // on how many particles cross a face this step:
-//   [header 64 B: int64 m, int64 g][posd cap_m][velp cap_m][accf cap_m][dpi cap_m][posd cap_g][velp cap_g]
+//   [header 64 B: int64 m, int64 g][posd cap_m][velp cap_m][accf cap_m][dpi cap_m][posd cap_g][velp cap_g][tail 64 B: int64 stamp]
+// The stamp (exchange sequence number) is copied AFTER the rest of the message, so a receiver that sees it
+// has the whole message.
 struct SlabMsg {
     long long *hdr;
     float4 *m_posd, *m_velp, *m_accf, *m_dpi, *g_posd, *g_velp;
@@ -85,9 +99,12 @@ __host__ __device__ inline SlabMsg slab_msg(void *base, int64_t cap_m, int64_t c
 // off = exclusive scan of cnt (length 4*nw + 1): totals of the four categories -> message headers (clamped to
 // the message capacities; an overflow is flagged, the excess is not sent) and the diagnostics array
 __global__ void k_slab_headers(const int *__restrict__ off, int64_t nw, void *to_left, void *to_right, int64_t cap_m, int64_t cap_g,
-                               int *overflow, long long *diag)
+                               int *overflow, long long *diag, long long stamp)
 {
     if (threadIdx.x != 0) return;
+    const int64_t tail = (64 + (4 * cap_m + 2 * cap_g) * 16) / 8;
+    if (to_left) ((long long *)to_left)[tail] = stamp;
+    if (to_right) ((long long *)to_right)[tail] = stamp;
     long long t[4];
     for (int k = 0; k < 4; k++) t[k] = off[(k + 1) * nw] - off[k * nw];
     for (int k = 0; k < 4; k++) diag[k] = t[k];
@@ -97,11 +114,11 @@ __global__ void k_slab_headers(const int *__restrict__ off, int64_t nw, void *to
 }
 
 __global__ void __launch_bounds__(256)
-k_slab_scatter(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ keys, FsgState B, const int *__restrict__ off,
-               int64_t nw, void *to_left, void *to_right, int64_t cap_m, int64_t cap_g)
+k_slab_scatter(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ keys, const int *__restrict__ region, FsgState B,
+               const int *__restrict__ off, int64_t nw, void *to_left, void *to_right, int64_t cap_m, int64_t cap_g)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int c = i < n ? slab_category(d, keys[i], rank, world) : 0;
+    int c = (i < n && slab_in_region(d, region, i)) ? slab_category(d, keys[i], rank, world) : 0;
     int64_t w = i >> 5;
     int lane = threadIdx.x & 31;
     unsigned lt = (1u << lane) - 1u;
@@ -176,10 +193,26 @@ k_slab_unpack(FsgDev d, const void *from_left, const void *from_right, int64_t c
         }                                                                                               \
     } while (0)
 
-extern "C" int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g) { return 64 + (4 * cap_m + 2 * cap_g) * (int64_t)sizeof(float4); }
+extern "C" int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g) { return 64 + (4 * cap_m + 2 * cap_g) * (int64_t)sizeof(float4) + 64; }
+
+// Waits (on the device) until both neighbours' messages number `expected` have landed in this rank's inboxes:
+// the stamp is the last thing a sender copies.  One thread, bounded: a missing neighbour raises flag 4.
+__global__ void k_slab_wait(const volatile long long *tail_left, const volatile long long *tail_right, long long expected, int *flags)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long t0 = clock64();
+    for (;;) {
+        bool ok = (!tail_left || *tail_left >= expected) && (!tail_right || *tail_right >= expected);
+        if (ok) break;
+        if (clock64() - t0 > 6000000000ll) { atomicOr(flags, 4); break; }     // ~3 s
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
 
 // counters: [5] slots in use (device-side), [6] ghost-band violation, [9] message / capacity overflow
-extern "C" int fsg_slab_pack(fsg_ctx *c, void *d_to_left, void *d_to_right, int64_t cap_m, int64_t cap_g)
+static int slab_pack_on(fsg_ctx *c, void *d_to_left, void *d_to_right, int64_t cap_m, int64_t cap_g, const int *region, long long stamp,
+                        cudaStream_t st)
 {
     if (!c || cap_m < 0 || cap_g < 0) return FSG_E_INVALID;
     if (c->cfg.world <= 1) { c->err = "fsg_slab_pack: not a slab context (world == 1)"; return FSG_E_STATE; }
@@ -200,17 +233,23 @@ extern "C" int fsg_slab_pack(fsg_ctx *c, void *d_to_left, void *d_to_right, int6
     int *cnt = c->slab_cnt, *off = c->slab_cnt + (4 * c->slab_warps + 8);
     long long *diag = reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
     const unsigned blocks = (unsigned)((nw * 32 + 255) / 256);
-    k_slab_count<<<blocks, 256, 0, c->stream>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, cnt, nw, c->counters + 6);
+    k_slab_count<<<blocks, 256, 0, st>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, region, cnt, nw, c->counters + 6);
     CUS(c, cudaGetLastError());
-    CUS(c, fsg_scan_exclusive(c->scan_tmp, c->scan_tmp_bytes, cnt, off, 4 * nw + 1, c->stream));
-    k_slab_headers<<<1, 32, 0, c->stream>>>(off, nw, c->cfg.rank > 0 ? d_to_left : nullptr,
-                                            c->cfg.rank < c->cfg.world - 1 ? d_to_right : nullptr, cap_m, cap_g, c->counters + 9, diag);
+    CUS(c, fsg_scan_exclusive(c->scan_tmp, c->scan_tmp_bytes, cnt, off, 4 * nw + 1, st));
+    k_slab_headers<<<1, 32, 0, st>>>(off, nw, c->cfg.rank > 0 ? d_to_left : nullptr, c->cfg.rank < c->cfg.world - 1 ? d_to_right : nullptr,
+                                     cap_m, cap_g, c->counters + 9, diag, stamp);
     CUS(c, cudaGetLastError());
-    k_slab_scatter<<<blocks, 256, 0, c->stream>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, c->B, off, nw, d_to_left, d_to_right,
-                                                  cap_m, cap_g);
+    k_slab_scatter<<<blocks, 256, 0, st>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, region, c->B, off, nw, d_to_left, d_to_right,
+                                           cap_m, cap_g);
     CUS(c, cudaGetLastError());
     c->launches += 3;
     return FSG_OK;
+}
+
+extern "C" int fsg_slab_pack(fsg_ctx *c, void *d_to_left, void *d_to_right, int64_t cap_m, int64_t cap_g)
+{
+    if (!c) return FSG_E_INVALID;
+    return slab_pack_on(c, d_to_left, d_to_right, cap_m, cap_g, nullptr, 0, c->stream);
 }
 
 extern "C" int fsg_slab_unpack(fsg_ctx *c, const void *d_from_left, const void *d_from_right, int64_t cap_m, int64_t cap_g)
@@ -243,6 +282,7 @@ extern "C" int fsg_slab_check(fsg_ctx *c, int64_t info[9])
     CUS(c, cudaSetDevice(c->device));
     int cnt[16];
     long long diag[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c->comm) CUS(c, cudaStreamSynchronize(c->comm));
     CUS(c, cudaMemcpyAsync(cnt, c->counters, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
     if (c->slab_cnt) {
         long long *d = reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
@@ -259,7 +299,8 @@ extern "C" int fsg_slab_check(fsg_ctx *c, int64_t info[9])
         return FSG_E_STATE;
     }
     if (cnt[9]) {
-        c->err = (cnt[9] & 2) ? "slab exchange: received particles exceed the context capacity"
+        c->err = (cnt[9] & 4) ? "slab exchange: timed out waiting for a neighbour's message"
+                 : (cnt[9] & 2) ? "slab exchange: received particles exceed the context capacity"
                               : "slab exchange: a message exceeded its capacity (cap_m / cap_g)";
         return FSG_E_NOMEM;
     }
@@ -318,21 +359,46 @@ extern "C" int fsg_slab_open_peer(fsg_ctx *c, int side, int parity, const void *
     return FSG_OK;
 }
 
+// pack on `st`, copy both messages into the neighbours' inboxes (stamp last)
+static int slab_send_on(fsg_ctx *c, const int *region, cudaStream_t st)
+{
+    if (!c->outbox[0]) { c->err = "slab send: call fsg_slab_alloc_messages first"; return FSG_E_STATE; }
+    const long long seq = ++c->seq_send;
+    const int par = (int)(seq & 1);
+    const bool left = c->cfg.rank > 0, right = c->cfg.rank < c->cfg.world - 1;
+    if ((left && !c->peer_inbox[par]) || (right && !c->peer_inbox[2 + par])) {
+        c->err = "slab send: the neighbours' inboxes are not mapped (fsg_slab_open_peer)";
+        return FSG_E_STATE;
+    }
+    int rc = slab_pack_on(c, c->outbox[0], c->outbox[1], c->msg_cap_m, c->msg_cap_g, region, seq, st);
+    if (rc != FSG_OK) return rc;
+    const size_t bytes = (size_t)fsg_slab_message_bytes(c->msg_cap_m, c->msg_cap_g), body = bytes - 64;
+    for (int side = 0; side < 2; side++) {
+        if (side == 0 ? !left : !right) continue;
+        char *dst = (char *)c->peer_inbox[2 * side + par], *src = (char *)c->outbox[side];
+        CUS(c, cudaMemcpyAsync(dst, src, body, cudaMemcpyDefault, st));
+        CUS(c, cudaMemcpyAsync(dst + body, src + body, 8, cudaMemcpyDefault, st));     // the stamp, after the body
+    }
+    return FSG_OK;
+}
+
 extern "C" int fsg_slab_pack_send(fsg_ctx *c)
 {
     if (!c) return FSG_E_INVALID;
-    if (!c->outbox[0]) { c->err = "fsg_slab_pack_send: call fsg_slab_alloc_messages first"; return FSG_E_STATE; }
-    const int par = (int)(c->steps & 1);
-    const bool left = c->cfg.rank > 0, right = c->cfg.rank < c->cfg.world - 1;
-    if ((left && !c->peer_inbox[par]) || (right && !c->peer_inbox[2 + par])) {
-        c->err = "fsg_slab_pack_send: the neighbours' inboxes are not mapped (fsg_slab_open_peer)";
-        return FSG_E_STATE;
-    }
-    int rc = fsg_slab_pack(c, c->outbox[0], c->outbox[1], c->msg_cap_m, c->msg_cap_g);
+    if (c->sent_ahead) { c->sent_ahead = false; return FSG_OK; }      // fsg_step already issued this exchange (overlap mode)
+    return slab_send_on(c, nullptr, c->stream);
+}
+
+// overlap mode, called by fsg_step between the boundary and the interior bins: the next step's messages are
+// packed and copied on the communication stream, behind the update of the boundary particles
+int fsg_slab_send_next(fsg_ctx *c)
+{
+    CUS(c, cudaEventRecord(c->ev_boundary, c->stream));
+    CUS(c, cudaStreamWaitEvent(c->comm, c->ev_boundary, 0));
+    int rc = slab_send_on(c, c->keysA, c->comm);
     if (rc != FSG_OK) return rc;
-    const size_t bytes = (size_t)fsg_slab_message_bytes(c->msg_cap_m, c->msg_cap_g);
-    if (left) CUS(c, cudaMemcpyAsync(c->peer_inbox[par], c->outbox[0], bytes, cudaMemcpyDefault, c->stream));
-    if (right) CUS(c, cudaMemcpyAsync(c->peer_inbox[2 + par], c->outbox[1], bytes, cudaMemcpyDefault, c->stream));
+    CUS(c, cudaEventRecord(c->ev_sent, c->comm));
+    c->sent_ahead = true;
     return FSG_OK;
 }
 
@@ -340,8 +406,60 @@ extern "C" int fsg_slab_unpack_recv(fsg_ctx *c)
 {
     if (!c) return FSG_E_INVALID;
     if (!c->inbox[0]) { c->err = "fsg_slab_unpack_recv: call fsg_slab_alloc_messages first"; return FSG_E_STATE; }
-    const int par = (int)(c->steps & 1);
+    CUS(c, cudaSetDevice(c->device));
+    const long long seq = ++c->seq_recv;
+    const int par = (int)(seq & 1);
+    const bool left = c->cfg.rank > 0, right = c->cfg.rank < c->cfg.world - 1;
+    if (c->overlap) CUS(c, cudaStreamWaitEvent(c->stream, c->ev_sent, 0));   // my own pack (other stream) reads the slots unpack writes
+    const size_t tail = ((size_t)fsg_slab_message_bytes(c->msg_cap_m, c->msg_cap_g) - 64);
+    k_slab_wait<<<1, 32, 0, c->stream>>>(left ? (const long long *)((char *)c->inbox[par] + tail) : nullptr,
+                                         right ? (const long long *)((char *)c->inbox[2 + par] + tail) : nullptr, seq, c->counters + 9);
+    CUS(c, cudaGetLastError());
+    c->launches++;
     return fsg_slab_unpack(c, c->inbox[par], c->inbox[2 + par], c->msg_cap_m, c->msg_cap_g);
+}
+
+// In-process wiring (several slab contexts in ONE process, e.g. tests on one GPU): the neighbour's inbox is a
+// plain device pointer, no IPC mapping.  side / parity as fsg_slab_open_peer.
+extern "C" int fsg_slab_set_peer(fsg_ctx *c, int side, int parity, void *neighbour_inbox)
+{
+    if (!c || side < 0 || side > 1 || parity < 0 || parity > 1) return FSG_E_INVALID;
+    c->peer_inbox[2 * side + parity] = neighbour_inbox;
+    c->peer_local = true;
+    return FSG_OK;
+}
+extern "C" void *fsg_slab_inbox_ptr(fsg_ctx *c, int side, int parity)
+{
+    if (!c || side < 0 || side > 1 || parity < 0 || parity > 1) return nullptr;
+    return c->inbox[2 * side + parity];
+}
+
+// on: fsg_step computes the slab's boundary bins first and issues the NEXT step's pack + copies on a second
+// stream, beside the interior bins (needs the peer-memory exchange)
+extern "C" int fsg_slab_set_overlap(fsg_ctx *c, int on)
+{
+    if (!c) return FSG_E_INVALID;
+    if (c->cfg.world <= 1) { c->err = "fsg_slab_set_overlap: not a slab context (world == 1)"; return FSG_E_STATE; }
+    if (on && !c->outbox[0]) { c->err = "fsg_slab_set_overlap: needs the peer-memory exchange (fsg_slab_alloc_messages)"; return FSG_E_STATE; }
+    CUS(c, cudaSetDevice(c->device));
+    CUS(c, cudaStreamSynchronize(c->stream));
+    if (on && !c->comm) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CUS(c, cudaStreamCreateWithPriority(&c->comm, cudaStreamNonBlocking, hi));
+        CUS(c, cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
+        CUS(c, cudaEventCreateWithFlags(&c->ev_sent, cudaEventDisableTiming));
+        CUS(c, cudaEventRecord(c->ev_sent, c->comm));
+        const int64_t nb = c->cap < c->dev.numcells ? c->cap : c->dev.numcells;
+        CUS(c, cudaMalloc(&c->binlistB, sizeof(int) * (nb > 0 ? nb : 1)));
+    }
+    if (c->comm) CUS(c, cudaStreamSynchronize(c->comm));
+    c->overlap = on != 0;
+    // interior layers: everything further than two layers from a face that has a neighbour
+    c->dev.bx0 = c->dev.x0 + ((on && c->cfg.rank > 0) ? 2 : 0);
+    c->dev.bx1 = c->dev.x1 - ((on && c->cfg.rank < c->cfg.world - 1) ? 2 : 0);
+    if (c->dev.bx1 < c->dev.bx0) c->dev.bx1 = c->dev.bx0;
+    return FSG_OK;
 }
 
 extern "C" int fsg_slab_close_peers(fsg_ctx *c)
@@ -349,6 +467,7 @@ extern "C" int fsg_slab_close_peers(fsg_ctx *c)
     if (!c) return FSG_E_INVALID;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (int k = 0; k < 4; k++) if (c->peer_inbox[k]) { cudaIpcCloseMemHandle(c->peer_inbox[k]); c->peer_inbox[k] = nullptr; }
+    if (c->comm) cudaStreamSynchronize(c->comm);
+    for (int k = 0; k < 4; k++) if (c->peer_inbox[k]) { if (!c->peer_local) cudaIpcCloseMemHandle(c->peer_inbox[k]); c->peer_inbox[k] = nullptr; }
     return FSG_OK;
 }

@@ -171,7 +171,7 @@ extern "C" int fsg_stage_mykernel(fsg_ctx *c, void *d_particles, const int32_t *
     a.sums = c->sums;
     if (c->dev.cap <= 0 && c->dev.bin_cap <= 0) {
         bool hasb = true;                         // unknown scene: evaluate the boundary factors
-        CUG(c, fsg_launch_pair_v2(a, c->sums, false, hasb, c->sm_count, c->stream));
+        CUG(c, fsg_launch_pair_v2(a, c->sums, false, hasb, c->sm_count, 0, c->stream));
     } else {
         CUG(c, fsg_launch_pair_fast(a, false, c->sm_count, c->stream));
     }

@@ -112,7 +112,7 @@ def slab_config(base: FsgConfig, rank: int, world: int, cuts, capacity: int, dev
 
 def message_bytes(cap_m: int, cap_g: int) -> int:
     """Bytes of one slab message with room for cap_m migrants and cap_g ghosts (fsg_slab_message_bytes)."""
-    return 64 + (4 * cap_m + 2 * cap_g) * 16
+    return 64 + (4 * cap_m + 2 * cap_g) * 16 + 64
 
 
 def message_caps(hist, cuts, slack: float = 1.2, floor: int = 4096) -> tuple[int, int]:
@@ -197,11 +197,12 @@ class SlabSolver(FluidSolver):
     def unpack(self, from_left_ptr, from_right_ptr):
         self._check(self._lib.fsg_slab_unpack(self._ctx, from_left_ptr, from_right_ptr, self.cap_m, self.cap_g), "fsg_slab_unpack")
 
-    def setup_peer_exchange(self):
+    def setup_peer_exchange(self, overlap: bool = True):
         """Maps the neighbours' inboxes into this process (CUDA IPC; one process per GPU on one node).  From
-        then on a step copies its messages straight into the neighbours' memory over NVLink and only sends a
-        4-byte NCCL message per neighbour to order their streams behind the copy."""
-        torch, ex = self.torch, self.exchange
+        then on a step copies its messages straight into the neighbours' memory over NVLink (copy engines); the
+        sequence number copied last tells the receiver, on the device, that the message is complete — no
+        communication library and no host inside a step."""
+        ex = self.exchange
         self._check(self._lib.fsg_slab_alloc_messages(self._ctx, self.cap_m, self.cap_g), "fsg_slab_alloc_messages")
         mine = {}
         for side in (0, 1):
@@ -216,21 +217,13 @@ class SlabSolver(FluidSolver):
                 self._check(self._lib.fsg_slab_open_peer(self._ctx, 0, par, every[ex.rank - 1][(1, par)]), "fsg_slab_open_peer")
             if ex.rank < ex.world - 1:
                 self._check(self._lib.fsg_slab_open_peer(self._ctx, 1, par, every[ex.rank + 1][(0, par)]), "fsg_slab_open_peer")
-        with torch.cuda.device(self.tdev):
-            self._sig = [torch.zeros(1, dtype=torch.int32, device=self.tdev) for _ in range(4)]
         self.peer = True
+        if overlap:
+            self.set_overlap(True)
 
-    def _signal_neighbours(self):
-        """Stream-ordered 4-byte send/recv with each neighbour: their unpack runs after my copy has landed."""
-        ex, dist = self.exchange, self.exchange.dist
-        ops = []
-        if ex.rank > 0:
-            ops += [dist.P2POp(dist.isend, self._sig[0], ex.rank - 1, ex.group), dist.P2POp(dist.irecv, self._sig[1], ex.rank - 1, ex.group)]
-        if ex.rank < ex.world - 1:
-            ops += [dist.P2POp(dist.isend, self._sig[2], ex.rank + 1, ex.group), dist.P2POp(dist.irecv, self._sig[3], ex.rank + 1, ex.group)]
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+    def set_overlap(self, on: bool = True):
+        """Boundary bins first, then the next step's pack + peer copies on a second stream beside the interior bins."""
+        self._check(self._lib.fsg_slab_set_overlap(self._ctx, int(on)), "fsg_slab_set_overlap")
 
     def check(self) -> dict:
         """Synchronises; raises FsgError if a message / the capacity overflowed or a particle left the ghost band."""
@@ -250,12 +243,11 @@ class SlabSolver(FluidSolver):
         for _ in range(nsteps):
             mark()
             if self.peer:
-                self._check(self._lib.fsg_slab_pack_send(self._ctx), "fsg_slab_pack_send")      # pack + copy into the neighbours' inboxes
+                # pack + copy into the neighbours' inboxes (a no-op when the previous fsg_step already issued it: overlap mode)
+                self._check(self._lib.fsg_slab_pack_send(self._ctx), "fsg_slab_pack_send")
                 mark()
-                with torch.cuda.stream(self.tstream):
-                    self._signal_neighbours()
                 mark()
-                self._check(self._lib.fsg_slab_unpack_recv(self._ctx), "fsg_slab_unpack_recv")
+                self._check(self._lib.fsg_slab_unpack_recv(self._ctx), "fsg_slab_unpack_recv")     # waits for the neighbours' stamps on the device
             else:
                 self.pack()
                 mark()
@@ -301,10 +293,24 @@ class SlabSolver(FluidSolver):
 # W slabs in one process on one device (tests; single-GPU emulation of the multi-rank algorithm)
 # ---------------------------------------------------------------------------------------------
 class SlabGroup:
-    def __init__(self, base_cfg: FsgConfig, world: int, cuts, capacity: int, device: int = 0, cap_m: int = 4096, cap_g: int = 65536):
+    def __init__(self, base_cfg: FsgConfig, world: int, cuts, capacity: int, device: int = 0, cap_m: int = 4096, cap_g: int = 65536,
+                 peer: bool = False, overlap: bool = False):
         self.world = world
         self.cuts = cuts
+        self.peer = peer
         self.slabs = [SlabSolver(slab_config(base_cfg, r, world, cuts, capacity, device), None, cap_m, cap_g) for r in range(world)]
+        if peer:         # the peer-memory protocol with plain pointers instead of IPC mappings (same process)
+            for s in self.slabs:
+                s._check(s._lib.fsg_slab_alloc_messages(s._ctx, cap_m, cap_g), "fsg_slab_alloc_messages")
+            for r, s in enumerate(self.slabs):
+                for par in (0, 1):
+                    if r > 0:
+                        s._check(s._lib.fsg_slab_set_peer(s._ctx, 0, par, self.slabs[r - 1]._lib.fsg_slab_inbox_ptr(self.slabs[r - 1]._ctx, 1, par)), "fsg_slab_set_peer")
+                    if r < world - 1:
+                        s._check(s._lib.fsg_slab_set_peer(s._ctx, 1, par, self.slabs[r + 1]._lib.fsg_slab_inbox_ptr(self.slabs[r + 1]._ctx, 0, par)), "fsg_slab_set_peer")
+                s.peer = True
+                if overlap:
+                    s.set_overlap(True)
 
     def close(self):
         for s in self.slabs:
@@ -325,6 +331,21 @@ class SlabGroup:
 
     def step(self, nsteps: int = 1):
         for _ in range(nsteps):
+            if self.peer:
+                # every stamp is in place before a wait kernel is launched: nothing spins on this one device
+                for s in self.slabs:
+                    s._check(s._lib.fsg_slab_pack_send(s._ctx), "fsg_slab_pack_send")
+                for s in self.slabs:
+                    s.sync()
+                for s in self.slabs:
+                    s._check(s._lib.fsg_slab_unpack_recv(s._ctx), "fsg_slab_unpack_recv")
+                for s in self.slabs:
+                    s.sync()
+                for s in self.slabs:
+                    s._check(s._lib.fsg_step(s._ctx, 1), "fsg_step")
+                for s in self.slabs:
+                    s.sync()
+                continue
             for s in self.slabs:
                 s.pack()
             for s in self.slabs:

@@ -155,6 +155,10 @@ class FluidSolver:
         self._check(self._lib.fsg_export_viz(self._ctx, spts.ctypes.data, a3.ctypes.data, b3.ctypes.data), "fsg_export_viz")
         return spts, a3, b3
 
+    def write_frame(self, filename: str, binary: bool = False):
+        """The VTK frame the drivers write after a step (solver-unidyn.cu:472-493), byte-compatible with visit_writer."""
+        self._check(self._lib.fsg_write_frame(self._ctx, str(filename).encode(), int(binary)), "fsg_write_frame")
+
     def tables(self):
         n = self.stats()["n"]
         cells = np.empty(n, np.int32)
@@ -221,3 +225,17 @@ def by_index(state: dict) -> dict:
     """Re-orders a downloaded (bin-sorted) state by Particle::index so that runs can be compared."""
     order = np.argsort(state["index"], kind="stable")
     return {k: v[order] for k, v in state.items()}
+
+
+def write_point_mesh(filename, pts: np.ndarray, variables: dict, binary: bool = False):
+    """fsg_write_point_mesh from numpy: pts [n,3] float32, variables = {name: [n] or [n,3] float32} (insertion order)."""
+    lib = _lib.load()
+    pts = np.ascontiguousarray(pts, np.float32)
+    n = pts.shape[0]
+    arrs = [np.ascontiguousarray(v, np.float32) for v in variables.values()]
+    dims = (C.c_int * len(arrs))(*[1 if a.ndim == 1 else a.shape[1] for a in arrs])
+    names = (C.c_char_p * len(arrs))(*[k.encode() for k in variables])
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    rc = lib.fsg_write_point_mesh(str(filename).encode(), int(binary), n, pts.ctypes.data, len(arrs), dims, names, ptrs)
+    if rc != 0:
+        raise FsgError(rc, "fsg_write_point_mesh", str(filename))

@@ -179,6 +179,15 @@ FSG_API int  fsg_scene_plume_hist(const fsg_config *cfg, double spacing, int64_t
  * 4 = keys (int32).  Valid until the next fsg_* call that changes state. */
 FSG_API int  fsg_device_ptr(fsg_ctx *ctx, int which, void **ptr);
 
+/* ---- frame output: the file write_point_mesh (visit_writer.h:94-96, visit_writer.cpp:673-719) produces ----
+ * Byte-identical to the reference's VisIt writer for the same arrays (legacy VTK UNSTRUCTURED_GRID point cloud,
+ * ASCII "%20.12e" or big-endian binary), same argument list; returns FSG_E_INVALID when the file cannot be
+ * opened (the reference crashes).  Pure host code.  fsg_write_frame = fsg_export_viz + the call the drivers make
+ * (solver-unidyn.cu:487: "mass", "surface_level"; solver.cu:213: "dens", "cellnumber"). */
+FSG_API int  fsg_write_point_mesh(const char *filename, int use_binary, int npts, const float *pts, int nvars, const int *vardim,
+                                  const char *const *varnames, const float *const *vars);
+FSG_API int  fsg_write_frame(fsg_ctx *ctx, const char *filename, int use_binary);
+
 /* ---- slab decomposition along x (world > 1): the multi-device hand-off of solver-unidyn.cu:396-470 ----
  * Every step of a slab context is   fsg_slab_pack -> (caller moves the two messages to the x-neighbours,
  * e.g. NCCL send/recv) -> fsg_slab_unpack -> fsg_step(ctx, 1).   ALL of it is asynchronous on the
@@ -189,6 +198,7 @@ FSG_API int  fsg_device_ptr(fsg_ctx *ctx, int which, void **ptr);
  * reference ships a one-layer `buffer` of whole Particle records instead, solver-unidyn.cu:187,421-462).
  * Message = device memory of fsg_slab_message_bytes(cap_m, cap_g) bytes, the SAME size on every rank:
  *   [64-byte header: int64 migrants, int64 ghosts][posd cap_m][velp cap_m][accf cap_m][dpi cap_m][posd cap_g][velp cap_g]
+ *   [64-byte tail: int64 stamp — the exchange sequence number, copied after the rest (peer-memory variant)]
  * The receiver reads the counts from the header on the device.  Order inside the messages is the
  * particles' current order (two-phase count / scan / scatter: deterministic).  A slab context always
  * works on `capacity` slots; unused slots hold a dead key and sort last.
@@ -209,6 +219,12 @@ FSG_API int  fsg_slab_open_peer(fsg_ctx *ctx, int side, int parity, const void *
 FSG_API int  fsg_slab_pack_send(fsg_ctx *ctx);
 FSG_API int  fsg_slab_unpack_recv(fsg_ctx *ctx);
 FSG_API int  fsg_slab_close_peers(fsg_ctx *ctx);
+/* Several slab contexts inside ONE process (tests on one GPU): wire the neighbour's inbox as a plain device pointer. */
+FSG_API int  fsg_slab_set_peer(fsg_ctx *ctx, int side, int parity, void *neighbour_inbox);
+FSG_API void *fsg_slab_inbox_ptr(fsg_ctx *ctx, int side, int parity);
+/* on: fsg_step computes the slab's boundary bins first and issues the NEXT step's pack + peer copies on a second
+ * stream, beside the interior bins; the following fsg_slab_pack_send is then a no-op.  Needs the peer-memory exchange. */
+FSG_API int  fsg_slab_set_overlap(fsg_ctx *ctx, int on);
 
 /* ---- (2) stage API: caller-owned DEVICE buffers in the reference's own layout ---- */
 /* replaces thrust::sort_by_key(t_v, t_v + n, t_a)            solver.cu:181 */

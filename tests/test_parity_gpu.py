@@ -321,9 +321,10 @@ def _slab_scene(fsg, fast: bool):
     return cfg, state
 
 
+@pytest.mark.parametrize("mode", ["messages", "peer", "peer+overlap"])
 @pytest.mark.parametrize("world", [2, 3, 5])
 @pytest.mark.parametrize("fast", [False, True])
-def test_slabs_match_single_device(fsg, world, fast):
+def test_slabs_match_single_device(fsg, world, fast, mode):
     """W x-slabs with migration + one-layer ghost exchange against ONE context on the same scene,
     resynchronised every step: positions, velocities and every integer result bit-exact (they do
     not depend on the summation order), sums within 1e-5."""
@@ -332,7 +333,8 @@ def test_slabs_match_single_device(fsg, world, fast):
     cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), world)
     cfg.capacity = n
     moved = 0
-    with fsg.SlabGroup(cfg, world, cuts, capacity=2 * n + 64) as g, fsg.FluidSolver(cfg) as s:
+    kw = dict(peer=mode != "messages", overlap=mode == "peer+overlap")
+    with fsg.SlabGroup(cfg, world, cuts, capacity=2 * n + 64, **kw) as g, fsg.FluidSolver(cfg) as s:
         g.upload(state)
         # (the boundary scene is stiff — ALPHA_BOUNDARY = 200 — and is only followed for a few steps)
         for k in range(6 if fast else 3):

@@ -32,7 +32,7 @@ def test_plume_layer_hist_matches_scene(fsg):
     state = fsg.scenes.plume_scene(cfg, jitter=0.0)
     assert hist.sum() == state["pos"].shape[0]
     assert np.array_equal(hist, fsg.slab.layer_hist_from_positions(cfg, state["pos"]))
-    assert fsg.slab.message_bytes(3, 5) == fsg._lib.load().fsg_slab_message_bytes(3, 5) == 64 + (4 * 3 + 2 * 5) * 16
+    assert fsg.slab.message_bytes(3, 5) == fsg._lib.load().fsg_slab_message_bytes(3, 5) == 64 + (4 * 3 + 2 * 5) * 16 + 64
     cap_m, cap_g = fsg.slab.message_caps(hist, fsg.slab_cuts(hist, 3))
     assert cap_g >= hist.max() and cap_m >= 4096
 
