@@ -35,6 +35,9 @@ void fsg_derive_constants(const fsg_config &cfg, FsgDev &d)
     d.x1 = cfg.world > 1 ? cfg.slab_x1 : cfg.grid;
     d.bx0 = d.x0;
     d.bx1 = d.x1;
+    d.rl = d.x0 + ((cfg.world > 1 && cfg.rank > 0) ? 2 : 0);
+    d.rr = d.x1 - ((cfg.world > 1 && cfg.rank < cfg.world - 1) ? 2 : 0);
+    if (d.rr < d.rl) d.rr = d.rl;
     d.dead = d.numcells + 1;
     d.cap = cfg.neighbour_cap;
     d.bin_cap = cfg.bin_cap;
@@ -584,6 +587,7 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         CU(c, cudaMemsetAsync(c->counters + 2, 0, 2 * sizeof(int), c->stream));
         CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(int), c->stream));
         CU(c, cudaMemsetAsync(c->counters + 10, 0, 2 * sizeof(int), c->stream));
+        if (c->cfg.world > 1) CU(c, fsg_launch_fill(c->counters + 12, (int)n, 2, c->stream));
         if (c->cfg.collect_stats) CU(c, cudaMemsetAsync(c->dstats, 0, 4 * sizeof(unsigned long long), c->stream));
         if (prof) prof_mark(c);
         // thrust::sort_by_key, key half (solver.cu:181)
@@ -592,7 +596,8 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         // value half + findneighbours (solver.cu:181-182)
         CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA,
                                  c->start, c->end, c->binlist[nxt], c->counters + nxt, c->binlistB ? c->binlistB : c->binlist[nxt],
-                                 c->counters + 10, c->counters + 3, c->counters + 5, c->stream));
+                                 c->counters + 10, c->counters + 3, c->counters + 5, c->cfg.world > 1 ? c->counters + 12 : nullptr,
+                                 c->stream));
         c->n_sorted = n;
         c->launches++;
         if (prof) prof_mark(c);

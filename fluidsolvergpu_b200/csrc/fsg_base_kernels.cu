@@ -112,7 +112,7 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
 __global__ void __launch_bounds__(256)
 k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restrict__ keysA, FsgState src,
           FsgState dst, const float4 *__restrict__ carry_src, float4 *__restrict__ carry_dst, int *start, int *end,
-          int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep)
+          int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges)
 {
     const int numcells = d.numcells;
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,6 +140,14 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
             if (next >= numcells) *nlive = (int)k + 1;
         }
         if (key <= numcells && next > numcells) *nkeep = (int)k + 1;   // live + parked; dead slots are trimmed
+        if (ranges) {
+            // slab contexts: [0, ranges[0]) and [ranges[1], n) are the sorted slots within two layers of a face that has a
+            // neighbour (plus ghosts, parked, dead): the only ones the next pack has to look at.  Preset to n by the caller.
+            const int prevk = k > 0 ? keysA[k - 1] : -1;
+            const int KL = d.rl * d.G2, KR = d.rr * d.G2;
+            if (key >= KL && prevk < KL) ranges[0] = (int)k;
+            if (key >= KR && prevk < KR) ranges[1] = (int)k;
+        }
     }
     // block-aggregated append of the home-bin heads: ONE atomic per block and list (a per-warp atomic on the
     // single counter serialises in L2 and was the bottleneck of this kernel)
@@ -161,11 +169,11 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
 }
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, cudaStream_t s)
+                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     k_reorder<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst,
-                                                          start, end, binlist, nocc, binlistB, noccB, nlive, nkeep);
+                                                          start, end, binlist, nocc, binlistB, noccB, nlive, nkeep, ranges);
     return cudaGetLastError();
 }
 
@@ -456,18 +464,18 @@ cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binli
             b.work = c->counters + 11;
             e2 = fsg_launch_pair_v2(b, c->sums, stats, c->has_boundary, c->sm_count, 0, s);
             if (e2 != cudaSuccess) return e2;
-            e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 1, s);
+            e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 1, c->counters + 6, s);
             if (e2 != cudaSuccess) return e2;
             if (fsg_slab_send_next(const_cast<fsg_ctx *>(c)) != FSG_OK) return cudaErrorUnknown;
             e2 = fsg_launch_pair_v2(a, c->sums, stats, c->has_boundary, c->sm_count, 5, s);      // leave room for the pack kernels
             if (e2 != cudaSuccess) return e2;
-            e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 2, s);
+            e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 2, c->counters + 6, s);
             *launches += 4;
             return e2;
         }
         e2 = fsg_launch_pair_v2(a, c->sums, stats, c->has_boundary, c->sm_count, 0, s);
         if (e2 != cudaSuccess) return e2;
-        e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 0, s);
+        e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 0, c->cfg.world > 1 ? c->counters + 6 : nullptr, s);
         *launches += 2;
         return e2;
     }

@@ -88,4 +88,4 @@ cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool
                                cudaStream_t s);
 // part: 0 every slot, 1 the slab's boundary slots (boundary bins, ghosts, parked, dead), 2 the interior slots
 cudaError_t fsg_launch_update(const FsgDev &d, int64_t n, const int *keysA, FsgState A, FsgState B, int *keysB,
-                              const float4 *sums, const float4 *carry, int part, cudaStream_t s);
+                              const float4 *sums, const float4 *carry, int part, int *violation, cudaStream_t s);

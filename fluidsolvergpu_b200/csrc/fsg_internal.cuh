@@ -16,6 +16,7 @@
 struct FsgDev {
     int G, G2, numcells;
     int x0, x1;      // bin layers this context owns (0, G without slab decomposition)
+    int rl, rr;      // slab contexts: layers [x0, rl) and [rr, x1) are within two layers of a face that has a neighbour
     int bx0, bx1;    // interior layers [bx0, bx1): home bins outside are the slab's boundary bins (done first when the
                      // exchange overlaps the interior; == x0, x1 otherwise)
     int dead;        // key of a slot that no longer holds a particle of this slab (sorts last, is trimmed)
@@ -72,7 +73,7 @@ struct fsg_ctx {
     int *perm, *iota;
     int *start, *end;   // dense bin tables, -1 = empty  (FluidGPU.cu:106-117)
     int *binlist[2];    // ids of the occupied home bins (unordered), ping-pong
-    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live, [4] any-boundary flag, [5] n_keep
+    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live, [4] any-boundary flag, [5] n_keep, [12..13] pack ranges
     unsigned long long *dstats;   // [0] tested, [1] in range, [2] dropped
     int *slab_cnt;      // slab pack: per-warp counts of the 4 message categories, then their exclusive scan
     void *scan_tmp;
@@ -126,7 +127,7 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
                                     int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, cudaStream_t s);
+                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, cudaStream_t s);
 int fsg_slab_send_next(fsg_ctx *c);   // fsg_slab.cu: pack + copies of the next step's messages on c->comm (overlap mode)
 cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work,
                                    const float4 *carry, int *launches, cudaStream_t s);

@@ -428,7 +428,7 @@ k_pair_v2(V2Args va)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B, int *__restrict__ keysB,
-         const float4 *__restrict__ sums, const float4 *__restrict__ carry, int part)
+         const float4 *__restrict__ sums, const float4 *__restrict__ carry, int part, int *violation)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -448,6 +448,8 @@ k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B,
         float4 s = sums[i];
         if (carry) { float4 cy = carry[i]; s.x += cy.x; s.y += cy.y; s.z += cy.z; s.w += cy.w; }
         particle_update(d, pd, vp, af, dpi, s.x, s.y, s.z, s.w, key);
+        // slab contexts: the one-layer ghost band (and the pack's two-layer region) assume less than one bin layer per step
+        if (violation && key < d.numcells && abs(key / d.G2 - ix) > 1) atomicOr(violation, 1);
     }
     B.posd[i] = pd;
     B.velp[i] = vp;
@@ -503,9 +505,9 @@ cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool
 }
 
 cudaError_t fsg_launch_update(const FsgDev &d, int64_t n, const int *keysA, FsgState A, FsgState B, int *keysB,
-                              const float4 *sums, const float4 *carry, int part, cudaStream_t s)
+                              const float4 *sums, const float4 *carry, int part, int *violation, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_update<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, (int)n, keysA, A, B, keysB, sums, carry, part);
+    k_update<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, (int)n, keysA, A, B, keysB, sums, carry, part, violation);
     return cudaGetLastError();
 }

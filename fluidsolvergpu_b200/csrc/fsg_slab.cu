@@ -42,16 +42,13 @@ __device__ __forceinline__ int slab_category(const FsgDev &d, int key, int rank,
     return c;
 }
 
-// Overlap mode packs while the interior particles of the step are still being updated: only slots whose
-// bin BEFORE the update (region = the sorted key array) was a boundary bin can have become migrants or
-// ghosts (a particle moves less than one bin per step), and only their new keys are read.
-__device__ __forceinline__ bool slab_in_region(const FsgDev &d, const int *__restrict__ region, int64_t i)
+// After the first step the particles are in bin-sorted order, and only slots within two layers of a face that has
+// a neighbour can have become migrants or ghosts (a particle moves less than one bin per step): the sorted slots
+// [0, region[0]) and [region[1], n), found by k_reorder.  Everything in between is skipped without being read —
+// which is also what lets overlap mode pack while the interior particles are still being updated.
+__device__ __forceinline__ bool slab_in_region(const int *__restrict__ region, int64_t i)
 {
-    if (!region) return true;
-    int rk = region[i];
-    if (rk >= d.numcells) return false;
-    int ix = rk / d.G2;
-    return ix >= d.x0 && ix < d.x1 && !(ix >= d.bx0 && ix < d.bx1);
+    return !region || i < region[0] || i >= region[1];
 }
 
 // counts per warp: cnt[cat * nw + warp]
@@ -61,7 +58,7 @@ k_slab_count(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ k
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int c = 0;
-    if (i < n && slab_in_region(d, region, i)) {
+    if (i < n && slab_in_region(region, i)) {
         int key = keys[i];
         c = slab_category(d, key, rank, world);
         // a particle that moved more than one bin layer in a step has left the one-layer ghost band
@@ -69,12 +66,16 @@ k_slab_count(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ k
     }
     int64_t w = i >> 5;
     int lane = threadIdx.x & 31;
+    if (i == 0) cnt[4 * nw] = 0;
+    if (!__any_sync(FULL, c != 0)) {              // the common case (interior warps): four zeros, no ballots
+        if (lane < 4 && w < nw) cnt[lane * nw + w] = 0;
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         unsigned m = __ballot_sync(FULL, (c >> k) & 1);
         if (lane == 0 && w < nw) cnt[k * nw + w] = __popc(m);
     }
-    if (i == 0) cnt[4 * nw] = 0;
 }
 
 // Fixed-layout message (device memory), the same size on every rank so that nothing on the host depends
@@ -118,7 +119,8 @@ k_slab_scatter(FsgDev d, int rank, int world, int64_t n, const int *__restrict__
                const int *__restrict__ off, int64_t nw, void *to_left, void *to_right, int64_t cap_m, int64_t cap_g)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int c = (i < n && slab_in_region(d, region, i)) ? slab_category(d, keys[i], rank, world) : 0;
+    int c = (i < n && slab_in_region(region, i)) ? slab_category(d, keys[i], rank, world) : 0;
+    if (!__any_sync(FULL, c != 0)) return;
     int64_t w = i >> 5;
     int lane = threadIdx.x & 31;
     unsigned lt = (1u << lane) - 1u;
@@ -386,7 +388,8 @@ extern "C" int fsg_slab_pack_send(fsg_ctx *c)
 {
     if (!c) return FSG_E_INVALID;
     if (c->sent_ahead) { c->sent_ahead = false; return FSG_OK; }      // fsg_step already issued this exchange (overlap mode)
-    return slab_send_on(c, nullptr, c->stream);
+    // (before the first step the particles are in upload order: every slot is looked at)
+    return slab_send_on(c, c->steps > 0 ? c->counters + 12 : nullptr, c->stream);
 }
 
 // overlap mode, called by fsg_step between the boundary and the interior bins: the next step's messages are
@@ -395,7 +398,7 @@ int fsg_slab_send_next(fsg_ctx *c)
 {
     CUS(c, cudaEventRecord(c->ev_boundary, c->stream));
     CUS(c, cudaStreamWaitEvent(c->comm, c->ev_boundary, 0));
-    int rc = slab_send_on(c, c->keysA, c->comm);
+    int rc = slab_send_on(c, c->counters + 12, c->comm);
     if (rc != FSG_OK) return rc;
     CUS(c, cudaEventRecord(c->ev_sent, c->comm));
     c->sent_ahead = true;

@@ -197,7 +197,7 @@ class SlabSolver(FluidSolver):
     def unpack(self, from_left_ptr, from_right_ptr):
         self._check(self._lib.fsg_slab_unpack(self._ctx, from_left_ptr, from_right_ptr, self.cap_m, self.cap_g), "fsg_slab_unpack")
 
-    def setup_peer_exchange(self, overlap: bool = True):
+    def setup_peer_exchange(self, overlap: bool = False):
         """Maps the neighbours' inboxes into this process (CUDA IPC; one process per GPU on one node).  From
         then on a step copies its messages straight into the neighbours' memory over NVLink (copy engines); the
         sequence number copied last tells the receiver, on the device, that the message is complete — no
