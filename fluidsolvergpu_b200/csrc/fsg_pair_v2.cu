@@ -116,7 +116,9 @@ __device__ __forceinline__ float4 v2_near_pair(const FsgDev &d, const float4 &pi
     float densi = fabsf(pi.w), densj = fabsf(pj.w);
     bool bi = pi.w < 0.f, bj = pj.w < 0.f;
     float q = ds * d.inv_h;
-    float w = d.w_c * (1.f - 1.5f * q * q + 0.75f * q * q * q);                // FluidGPU.cu:13
+    float to = 2.f - q;
+    // inner branch (FluidGPU.cu:13) minus the outer-branch value the sweep has already added for this pair
+    float w = d.w_c * ((1.f - 1.5f * q * q + 0.75f * q * q * q) - 0.25f * to * to * to);
     float t = d.hf - ds;
     float dwv = d.dw_c * t * t;                                                // FluidGPU.cu:37 (0 at r == h)
     float g = dwv / ds;
@@ -341,29 +343,31 @@ k_pair_v2(V2Args va)
                     float rx = pi0.x - pj.x, ry = pi0.y - pj.y, rz = pi0.z - pj.z;
                     float d2 = STATS ? dist2(rx, ry, rz) : fmaf(rz, rz, fmaf(ry, ry, rx * rx));
                     unsigned u = __float_as_uint(d2) - 1u;       // 0 < d2 <= thr  <=>  bits(d2) - 1 < bits(thr)
-                    bool inr = u < d2max_bits;                   // FluidGPU.cu:236
                     bool nearp = u < d2h_bits;                   // r <= h
                     float inv = rsqrt_fast(d2);
-                    float tt = fmaf(-d2 * inv, inv_h, 2.f);      // 2 - r/h
+                    // (2 - r/h)^3 clamped at 0: zero beyond 2h (FluidGPU.cu:236), and zero for d2 == 0 (the particle
+                    // itself) and for the padding sentinels, where 0 * inf = NaN and fmaxf returns the other operand.
+                    // Pairs with r <= h also get this OUTER-branch value here; near_pair adds the difference to the inner
+                    // branch (FluidGPU.cu:13), so the sweep needs no range test and no select.
+                    float tt = fmaxf(fmaf(-d2 * inv, inv_h, 2.f), 0.f);
                     float t3 = tt * tt * tt;
                     if (HASB) t3 *= fmaf(ci0, bjf, 1.f);
-                    if (inr && !nearp) w0 += t3;
+                    w0 += t3;
                     if (nearp) m0 |= bit;
-                    if (STATS) nin += __popc(__ballot_sync(FULL, inr));
+                    if (STATS) nin += __popc(__ballot_sync(FULL, u < d2max_bits));
                 }
                 {
                     float rx = pi1.x - pj.x, ry = pi1.y - pj.y, rz = pi1.z - pj.z;
                     float d2 = STATS ? dist2(rx, ry, rz) : fmaf(rz, rz, fmaf(ry, ry, rx * rx));
                     unsigned u = __float_as_uint(d2) - 1u;
-                    bool inr = u < d2max_bits;
                     bool nearp = u < d2h_bits;
                     float inv = rsqrt_fast(d2);
-                    float tt = fmaf(-d2 * inv, inv_h, 2.f);
+                    float tt = fmaxf(fmaf(-d2 * inv, inv_h, 2.f), 0.f);
                     float t3 = tt * tt * tt;
                     if (HASB) t3 *= fmaf(ci1, bjf, 1.f);
-                    if (inr && !nearp) w1 += t3;
+                    w1 += t3;
                     if (nearp) m1 |= bit;
-                    if (STATS) nin += __popc(__ballot_sync(FULL, inr));
+                    if (STATS) nin += __popc(__ballot_sync(FULL, u < d2max_bits));
                 }
             }
             if (STATS && lane == 0) { st_tested += (unsigned long long)ct * (has1 ? 2 : 1); st_in += nin; }
