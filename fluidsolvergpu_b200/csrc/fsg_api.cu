@@ -256,6 +256,7 @@ extern "C" const char *fsg_last_error(const fsg_ctx *c) { return c ? c->err.c_st
 extern "C" int fsg_set_stream(fsg_ctx *c, void *s)
 {
     if (!c) return FSG_E_INVALID;
+    if (!c->own_stream && c->stream == (cudaStream_t)s) return FSG_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);

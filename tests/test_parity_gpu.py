@@ -565,3 +565,34 @@ def test_unidyn_aos_and_scope(fsg):
         bad["solid"][np.flatnonzero(state["boundary"] == 0)[0]] = 0.5
         with pytest.raises(fsg.FsgError):
             s.upload(bad)
+
+
+# ---------------------------------------------------------------------------------------------
+# link-compatible entry points (fsg_compat_base.cu): a driver-style program compiled against the
+# reference header, launching findneighbours / mykernel / mykernel2 with <<<>>>, linked against libfsg
+# ---------------------------------------------------------------------------------------------
+def test_reference_style_driver_links_and_runs_against_libfsg(fsg, tmp_path):
+    """oracle/_ref/compat_harness_base = oracle/ref_harness_base.cu (includes FluidGPU.cuh, mirrors the loop of
+    solver.cu:171-216) linked with fsg_compat_base.o + libfsg.so INSTEAD of the reference's FluidGPU.o.  Its dumps
+    must match the dumps the same harness produced with the reference's own kernels (tests/golden/ref_config1_*)."""
+    import subprocess
+    from fluidsolvergpu_b200 import sections
+    exe = GOLD.parents[1] / "oracle" / "_ref" / "compat_harness_base"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/compat_harness_base is built where the reference headers are available")
+    prefix = tmp_path / "compat"
+    out = subprocess.check_output([str(exe), "--steps", "10", "--dump", "1,2,10", "--out", str(prefix)], timeout=120).decode()
+    assert '"impl"' in out
+    noise = __import__("json").loads((GOLD / "golden_noise.json").read_text())["run_to_run_rel_l2"]
+    for k in (1, 2, 10):
+        got = sections.read_sections(f"{prefix}_step{k}.bin")
+        ref = dict(np.load(GOLD / f"ref_config1_step{k}.npz"))
+        n = len(ref["index"])
+        if k == 1:
+            for f in ("cells_sorted", "start", "end", "index", "cell", "spts", "b3"):
+                assert np.array_equal(got[f], ref[f]), f
+        o, r = np.argsort(got["index"], kind="stable"), np.argsort(ref["index"], kind="stable")
+        for f in FIELDS:
+            err = rel_l2(got[f].reshape(n, -1)[o], ref[f].reshape(n, -1)[r])
+            bound = 1e-5 if k <= 2 else max(1e-5, 5 * noise[f"config1_step{k}"][f])
+            assert err <= bound, (k, f, err, bound)
