@@ -279,6 +279,7 @@ def fsg_arm(args):
                          "frac_of_hbm_peak": ALG_BYTES_STEP * n_local / (ms_step * 1e-3) / 1e9 / hbm_peak}
 
     # ---- end to end through the C ABI with host buffers ----
+    args.n_total = n_total
     e2e = e2e_leg(solver, torch, stream, args, G, world, barrier, dist)
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
@@ -309,15 +310,19 @@ def e2e_leg(solver, torch, stream, args, G, world, barrier, dist):
     """Upload (pinned host -> device) + one step + download (device -> pinned host), every step."""
     import ctypes as C
     from fluidsolvergpu_b200 import FsgSoa
-    if world > 1:
-        return {"value": None, "unit": "cell-updates/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-                "note": "the host-buffer leg is measured at N=1; slab contexts keep their state resident"}
+    slab = world > 1
+    if slab:
+        # every rank round-trips ALL the slots it holds (owned particles, particles about to migrate, empty slots marked in `cell`)
+        solver.check()
+        solver._check(solver._lib.fsg_slab_keep_foreign(solver._ctx, 1), "fsg_slab_keep_foreign")
     n = solver.stats()["n"]
     shapes = {"pos": (n, 3), "vel": (n, 3), "acc": (n, 3), "dens": (n,), "press": (n,), "delpress": (n, 3), "newdens": (n,),
               "newdelpress": (n, 3)}
     bufs = {k: torch.empty(s, dtype=torch.float32, pin_memory=True) for k, s in shapes.items()}
     bufs["index"] = torch.empty(n, dtype=torch.int32, pin_memory=True)
     bufs["boundary"] = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    if slab:
+        bufs["cell"] = torch.empty(n, dtype=torch.int32, pin_memory=True)
     soa = FsgSoa()
     soa.n = n
     for k, b in bufs.items():
@@ -338,9 +343,24 @@ def e2e_leg(solver, torch, stream, args, G, world, barrier, dist):
         one()
     barrier()
     dt = (time.perf_counter() - t0) / steps
+    if slab:
+        solver.check()
+        t = torch.tensor([dt, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt, h2d, d2h = float(tmax[0]), int(t[1]), int(t[2])
+        solver._check(solver._lib.fsg_slab_keep_foreign(solver._ctx, 0), "fsg_slab_keep_foreign")
+        own = torch.tensor([float(solver.owned_count())], device="cuda", dtype=torch.float64)
+        dist.all_reduce(own)
+        if int(own[0]) != args.n_total:
+            raise SystemExit(f"end-to-end leg lost particles: {int(own[0])} != {args.n_total}")
     return {"value": G ** 3 / dt, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": dt * 1e3, "steps": steps,
-            "what": "fsg_upload_soa(pinned host) + fsg_step(1) + fsg_download_soa(pinned host) per step, wall clock around synchronised calls"}
+            "what": ("fsg_upload_soa(pinned host) + fsg_step(1) + fsg_download_soa(pinned host) per step, wall clock around synchronised calls"
+                     if not slab else
+                     "per rank: fsg_upload_soa(pinned host, every slot the rank holds) + slab exchange + fsg_step(1) + fsg_download_soa(pinned host) "
+                     "per step; wall clock, max over ranks; bytes summed over ranks")}
 
 
 def main():

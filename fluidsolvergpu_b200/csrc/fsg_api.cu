@@ -276,7 +276,7 @@ extern "C" int fsg_sync(fsg_ctx *c)
 }
 
 // after new particles have been written to B / carryB
-static int after_upload(fsg_ctx *c, int64_t n)
+static int after_upload(fsg_ctx *c, int64_t n, const int *slot_state = nullptr)
 {
     // the bin tables may hold the entries of a previous run
     if (c->tables_dirty) {
@@ -292,13 +292,16 @@ static int after_upload(fsg_ctx *c, int64_t n)
         // a slab context always works on all `cap` slots (nothing on the host depends on how many are in use):
         // the tail holds the dead key, the device-side count of slots in use starts at n
         CU(c, fsg_launch_fill(c->keysB + n, c->dev.dead, c->cap - n, c->stream));
-        const int n32 = (int)n;
-        CU(c, cudaMemcpyAsync(c->counters + 5, &n32, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        if (!c->keep_foreign) {      // (a re-uploaded download keeps the device-side count of the slots in use)
+            const int n32 = (int)n;
+            CU(c, cudaMemcpyAsync(c->counters + 5, &n32, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        }
         CU(c, cudaMemsetAsync(c->counters + 9, 0, sizeof(int), c->stream));
     }
     CU(c, cudaMemsetAsync(c->counters + 4, 0, sizeof(int), c->stream));
     CU(c, cudaMemsetAsync(c->counters + 6, 0, sizeof(int), c->stream));
-    CU(c, fsg_launch_keys(c->dev, c->B.posd, c->keysB, n, c->counters + 4, c->cfg.world > 1, c->stream));   // solver.cu:119
+    CU(c, fsg_launch_keys(c->dev, c->B.posd, c->keysB, n, c->counters + 4, c->cfg.world > 1 && !c->keep_foreign, slot_state,
+                          c->stream));   // solver.cu:119
     c->launches++;
     int flag[5] = {0, 0, 0, 0, 0};
     CU(c, cudaMemcpyAsync(flag, c->counters + 4, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
@@ -464,7 +467,9 @@ extern "C" int fsg_upload_soa(fsg_ctx *c, const fsg_soa *h)
     CU(c, cudaSetDevice(c->device));
     SoaStage s;
     fsg_soa hh = *h;
-    hh.cell = nullptr;   // recomputed, solver.cu:119
+    // bin ids are recomputed (solver.cu:119).  Slab contexts that re-upload what they downloaded (keep_foreign) use the
+    // cell array only to tell empty slots (cell == numcells + 1) from particles.
+    if (!(c->cfg.world > 1 && c->keep_foreign)) hh.cell = nullptr;
     size_t bytes = soa_stage_layout(nullptr, n, &hh, s);
     int rc = ensure_stage(c, bytes);
     if (rc != FSG_OK) return rc;
@@ -474,6 +479,7 @@ extern "C" int fsg_upload_soa(fsg_ctx *c, const fsg_soa *h)
     H2D(s.press, h->press, 4 * n); H2D(s.delp, h->delpress, 12 * n); H2D(s.nd, h->newdens, 4 * n);
     H2D(s.ndp, h->newdelpress, 12 * n); H2D(s.index, h->index, 4 * n); H2D(s.bnd, h->boundary, n);
     H2D(s.solid, h->solid, 4 * n); H2D(s.fluid, h->fluid, 4 * n);
+    if (hh.cell) CU(c, cudaMemcpyAsync(s.cell, h->cell, (size_t)(4 * n), cudaMemcpyHostToDevice, c->stream));
 #undef H2D
     if (n > 0) {
         k_pack_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, s.pos, s.vel, s.acc, s.dens, s.press, s.delp, s.nd,
@@ -482,7 +488,7 @@ extern "C" int fsg_upload_soa(fsg_ctx *c, const fsg_soa *h)
         CU(c, cudaGetLastError());
         c->launches++;
     }
-    return after_upload(c, n);
+    return after_upload(c, n, hh.cell ? s.cell : nullptr);
 }
 
 extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
@@ -689,6 +695,16 @@ extern "C" int fsg_get_stats(fsg_ctx *c, fsg_stats *out)
     out->dropped = (int64_t)ds[2];
     out->steps = c->steps;
     out->kernel_launches = c->launches;
+    return FSG_OK;
+}
+
+// Slab contexts: 0 (default) — an upload hands every rank the whole scene and each keeps the particles of its own slab;
+// 1 — an upload returns what fsg_download_soa gave (the particles this rank holds, including ones that have just
+// crossed a face and migrate at the next pack; `cell` marks the empty slots): nothing is filtered by position.
+extern "C" int fsg_slab_keep_foreign(fsg_ctx *c, int on)
+{
+    if (!c) return FSG_E_INVALID;
+    c->keep_foreign = on != 0;
     return FSG_OK;
 }
 

@@ -36,7 +36,7 @@ cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s)
 // slab_filter: a freshly uploaded particle that lies outside this context's slab is not this context's
 // (every rank is handed the same scene): its slot is marked dead and disappears at the next sort.
 __global__ void k_keys(FsgDev d, const float4 *__restrict__ posd, int *__restrict__ keys, int64_t n, int *any_boundary,
-                       bool slab_filter)
+                       bool slab_filter, const int *__restrict__ slot_state)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool b = false;
@@ -48,16 +48,17 @@ __global__ void k_keys(FsgDev d, const float4 *__restrict__ posd, int *__restric
             if (key >= d.numcells) key = (d.x1 == d.G) ? key : d.dead;     // parked particles stay with the last slab
             else if (ix < d.x0 || ix >= d.x1) key = d.dead;
         }
+        if (slot_state && slot_state[i] > d.numcells) key = d.dead;      // an empty slot of a downloaded slab state
         keys[i] = key;
         b = p.w < 0.f;      // (slab contexts: any boundary particle of the scene may arrive later as a ghost)
     }
     if (__any_sync(FULL, b) && (threadIdx.x & 31) == 0) atomicOr(any_boundary, 1);
 }
 cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, int *any_boundary, bool slab_filter,
-                            cudaStream_t s)
+                            const int *slot_state, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, posd, keys, n, any_boundary, slab_filter);
+    k_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, posd, keys, n, any_boundary, slab_filter, slot_state);
     return cudaGetLastError();
 }
 

@@ -84,6 +84,7 @@ struct fsg_ctx {
     void *peer_inbox[4];// the neighbours' inboxes mapped through CUDA IPC: [0..1] left neighbour's from-right, [2..3] right neighbour's from-left
     int64_t msg_cap_m, msg_cap_g;
     long long seq_send, seq_recv;   // exchange sequence numbers (stamps at the tail of every message)
+    bool keep_foreign;  // slab contexts: uploads are not filtered by position (fsg_slab_keep_foreign)
     bool peer_local;    // peer_inbox holds plain pointers of this process (fsg_slab_set_peer), not IPC mappings
     bool overlap;       // pack + copies of the NEXT step's messages run on `comm` behind the boundary bins, beside the interior bins
     bool sent_ahead;    // the messages of the next step have already been issued by fsg_step
@@ -118,7 +119,7 @@ cudaError_t fsg_sort_pairs(void *tmp, size_t tmp_bytes, const int *keys_in, int 
 cudaError_t fsg_launch_iota(int *p, int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, int *any_boundary, bool slab_filter,
-                            cudaStream_t s);
+                            const int *slot_state, cudaStream_t s);
 cudaError_t fsg_launch_reset_tables_keys(const FsgDev &d, const int *keysA, int *start, int *end, int64_t n, cudaStream_t s);
 // fsg_slab.cu
 size_t fsg_scan_temp_bytes(int64_t n);

@@ -225,6 +225,15 @@ class SlabSolver(FluidSolver):
         """Boundary bins first, then the next step's pack + peer copies on a second stream beside the interior bins."""
         self._check(self._lib.fsg_slab_set_overlap(self._ctx, int(on)), "fsg_slab_set_overlap")
 
+    def keep_foreign(self, on: bool = True):
+        """on: uploads return a raw download (all slots, `cell` marking the empty ones) and are not filtered by position."""
+        self._check(self._lib.fsg_slab_keep_foreign(self._ctx, int(on)), "fsg_slab_keep_foreign")
+        self._upload_cell = bool(on)
+
+    def download_slots(self) -> dict:
+        """Every slot this context holds, including empty ones (cell == grid^3 + 1): what keep_foreign uploads take back."""
+        return FluidSolver.download(self)
+
     def check(self) -> dict:
         """Synchronises; raises FsgError if a message / the capacity overflowed or a particle left the ghost band."""
         info = (C.c_int64 * 9)()

@@ -99,6 +99,8 @@ class FluidSolver:
             a = np.ascontiguousarray(state["index"], np.int32); keep.append(a); soa.index = a.ctypes.data
         if state.get("boundary") is not None:
             a = np.ascontiguousarray(state["boundary"], np.uint8); keep.append(a); soa.boundary = a.ctypes.data
+        if getattr(self, "_upload_cell", False) and state.get("cell") is not None:      # slab contexts, fsg_slab_keep_foreign
+            a = np.ascontiguousarray(state["cell"], np.int32); keep.append(a); soa.cell = a.ctypes.data
         self._check(self._lib.fsg_upload_soa(self._ctx, C.byref(soa)), "fsg_upload_soa")
         self._check(self._lib.fsg_sync(self._ctx), "fsg_sync")
 

@@ -206,6 +206,10 @@ FSG_API int  fsg_write_frame(fsg_ctx *ctx, const char *filename, int use_binary)
 FSG_API int  fsg_slab_pack(fsg_ctx *ctx, void *d_to_left, void *d_to_right, int64_t cap_m, int64_t cap_g);
 FSG_API int  fsg_slab_unpack(fsg_ctx *ctx, const void *d_from_left, const void *d_from_right, int64_t cap_m, int64_t cap_g);
 FSG_API int  fsg_slab_check(fsg_ctx *ctx, int64_t info[9]);
+/* Uploads into a slab context: 0 (default) every rank is handed the whole scene and keeps the particles of its slab;
+ * 1 the upload returns what fsg_download_soa gave — all `capacity` slots, `cell` == grid^3 + 1 marking the empty ones —
+ * and nothing is filtered by position (particles that have just crossed a face migrate at the next pack). */
+FSG_API int  fsg_slab_keep_foreign(fsg_ctx *ctx, int on);
 FSG_API int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g);
 /* Peer-memory variant (one process per GPU on one node): the library owns the message buffers, the
  * neighbours' inboxes are mapped through CUDA IPC and fsg_slab_pack_send copies the packed messages straight

@@ -596,3 +596,28 @@ def test_reference_style_driver_links_and_runs_against_libfsg(fsg, tmp_path):
             err = rel_l2(got[f].reshape(n, -1)[o], ref[f].reshape(n, -1)[r])
             bound = 1e-5 if k <= 2 else max(1e-5, 5 * noise[f"config1_step{k}"][f])
             assert err <= bound, (k, f, err, bound)
+
+
+def test_slab_raw_round_trip_through_host_memory(fsg):
+    """The end-to-end path of a slab context: download every slot, upload it again (fsg_slab_keep_foreign), go on.
+    Must be bit-identical to a run that never left the device — including particles that had crossed a face and were
+    waiting to migrate when they were downloaded."""
+    cfg, state = _slab_scene(fsg, True)
+    n = state["pos"].shape[0]
+    cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), 3)
+    with fsg.SlabGroup(cfg, 3, cuts, capacity=2 * n + 64) as a, fsg.SlabGroup(cfg, 3, cuts, capacity=2 * n + 64) as b:
+        a.upload(state)
+        b.upload(state)
+        for sl in b.slabs:
+            sl.keep_foreign(True)
+        for k in range(5):
+            a.step(1)
+            b.step(1)
+            for sl in b.slabs:
+                sl.upload(sl.download_slots())
+        a.check()
+        b.check()
+        ga, gb = fsg.by_index(a.download()), fsg.by_index(b.download())
+        assert ga["index"].shape[0] == n and np.array_equal(ga["index"], gb["index"])
+        for f in FIELDS + ("cell",):
+            assert np.array_equal(ga[f], gb[f]), f
