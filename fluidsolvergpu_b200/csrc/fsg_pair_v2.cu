@@ -31,6 +31,9 @@
 #define V2_GROUP 32                     // home particles per item
 #define V2_BINS_PER_GRAB 16
 #define V2_DEFAULT_CW 4
+#ifndef V2_BPS4
+#define V2_BPS4 7                       // resident blocks per SM for CW == 4
+#endif
 
 struct V2Stage {
     float4 sp[V2_TILE];                 // candidate (x, y, z, +-dens)
@@ -180,7 +183,7 @@ __device__ __forceinline__ void v2_drain_batch(const FsgDev &d, const V2Stage &S
 }
 
 template <bool STATS, bool HASB, int CW>
-__global__ void __launch_bounds__((CW + 1) * 32, (CW == 4 ? 6 : CW == 6 ? 5 : 4))
+__global__ void __launch_bounds__((CW + 1) * 32, (CW == 4 ? V2_BPS4 : CW == 6 ? 5 : 4))
 k_pair_v2(V2Args va)
 {
     constexpr int PASSES = (V2_GROUP + 2 * CW - 1) / (2 * CW);
@@ -474,7 +477,7 @@ static cudaError_t launch_pair_v2_cw(const V2Args &va, bool stats, bool has_boun
         cudaFuncSetAttribute(k_pair_v2<true, true, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
-    int per_sm = CW == 4 ? 6 : CW == 6 ? 5 : 4;
+    int per_sm = CW == 4 ? V2_BPS4 : CW == 6 ? 5 : 4;
     if (blocks_per_sm > 0 && blocks_per_sm < per_sm) per_sm = blocks_per_sm;
     int64_t blocks = ((int64_t)va.a.n + 2 * CW - 1) / (2 * CW);
     int64_t maxb = (int64_t)sm_count * per_sm;

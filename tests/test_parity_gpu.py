@@ -212,6 +212,24 @@ def test_uncapped_random_scene(fsg, stats, boundary_frac):
             print("uncapped random", stats, boundary_frac, k + 1, errs)
 
 
+def test_uncapped_scene_touching_the_grid_faces(fsg):
+    """Particles in the outermost bin layers: the 27 LINEAR bin offsets (FluidGPU.cu:124-126) wrap into neighbouring
+    rows and planes there — candidates the distance test has to reject, in the oracle and here alike."""
+    rng = np.random.default_rng(17)
+    pos = rng.uniform(-1.0, 1.0, (6000, 3)).astype(np.float32)
+    pos[:2000] = np.where(rng.uniform(size=(2000, 3)) < 0.5, -1.0, 1.0) * rng.uniform(0.93, 1.0, (2000, 3))   # corners / faces
+    pos = pos.astype(np.float32)
+    state = fsg.scenes.default_state(pos, vel=rng.uniform(-0.1, 0.1, pos.shape).astype(np.float32))
+    cfg = fsg.scenes.plume_config(17)
+    cfg.origin = -1.02
+    cfg.capacity = pos.shape[0]
+    cfg.collect_stats = 1
+    with fsg.FluidSolver(cfg) as s:
+        s.upload(state)
+        for _ in range(2):
+            resync_step(fsg, s)
+
+
 def test_large_bins_and_many_tiles(fsg):
     """Bins far above 32 particles and neighbourhoods above one staging tile (512): exercises the
     home-particle groups and the candidate tiling of the pair kernel."""

@@ -1,2 +1,2 @@
-N=2
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --grid 256 --steps 10 --warmup 3 > "gpurun_out/bench256_n2_e2e.json" 2> "gpurun_out/bench256_n2_e2e.err"; echo "rc=$?"; tail -4 "gpurun_out/bench256_n2_e2e.err" | cut -c1-300
+timeout 300 python -m pytest tests -m gpu -q -k "uncapped or plume or large_bins" 2>&1 | tail -1
+timeout 300 python bench.py --no-cpu --e2e-steps 1 > gpurun_out/bench512_bps7.json 2> gpurun_out/bench512_bps7.err; echo "rc=$?"
