@@ -72,10 +72,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 {
     unsigned ok = 0;
     const unsigned addr = smem_u32(bar);
-    do {
+    for (;;) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
-    } while (!ok);
+        if (ok) break;
+        __nanosleep(256);      // a warp that is ahead of its block's slowest warp must not eat issue slots
+    }
 }
 // "stage is free again" goes through hardware named barriers (ids 1..V2_NST): the consumer warps
 // arrive without blocking, the producer warp blocks in bar.sync — no polling, no issue slots taken
@@ -109,13 +111,48 @@ __device__ __forceinline__ float rsqrt_fast(float x)
     return r;
 }
 
+// Packed FP32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): one instruction works on the two home particles of a pass.
+// A scalar operand duplicated into both halves costs nothing — ptxas encodes it as a broadcast (`R4.F32`).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // pressure / viscosity / inner-W terms of one r <= h pair (FluidGPU.cu:238-279)
 __device__ __forceinline__ float4 v2_near_pair(const FsgDev &d, const float4 &pi, const float4 &vi, const float4 &pj,
                                                const float4 &vj)
 {
+    // approximate reciprocals (rsqrt.approx / div.approx, <= 2 ulp): the reference forms these terms in mixed
+    // float / double, the 1e-5 parity bar is three orders of magnitude above either rounding
     float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-    float d2 = dist2(rx, ry, rz);
-    float ds = sqrtf(d2);
+    float d2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+    float inv = rsqrt_fast(d2);
+    float ds = d2 * inv;
     float densi = fabsf(pi.w), densj = fabsf(pj.w);
     bool bi = pi.w < 0.f, bj = pj.w < 0.f;
     float q = ds * d.inv_h;
@@ -123,20 +160,19 @@ __device__ __forceinline__ float4 v2_near_pair(const FsgDev &d, const float4 &pi
     // inner branch (FluidGPU.cu:13) minus the outer-branch value the sweep has already added for this pair
     float w = d.w_c * ((1.f - 1.5f * q * q + 0.75f * q * q * q) - 0.25f * to * to * to);
     float t = d.hf - ds;
-    float dwv = d.dw_c * t * t;                                                // FluidGPU.cu:37 (0 at r == h)
-    float g = dwv / ds;
+    float g = d.dw_c * t * t * inv;                                            // FluidGPU.cu:37 (0 at r == h), / ds
     float vabx = vi.x - vj.x, vaby = vi.y - vj.y, vabz = vi.z - vj.z;
     float dd = vabx * rx + vaby * ry + vabz * rz;                              // :253
     float s = 0.f;
+    const bool ib = !bi && bj;
     if (dd < 0.f) {                                                            // :255
-        float mu = dd / (ds * ds + d.eps);
-        float hm = d.hf * mu;
-        float bf = (!bi && bj) ? 1.f + (float)d.alpha_boundary : 1.f;
-        s = d.visc_c * (hm + d.visc_q * hm * hm) / ((densi + densj) * 0.5f) * bf;
+        float hm = d.hf * __fdividef(dd, d2 + d.eps);
+        float bf = ib ? 2.f * (1.f + (float)d.alpha_boundary) : 2.f;
+        s = d.visc_c * (hm + d.visc_q * hm * hm) * __fdividef(bf, densi + densj);
     }
-    float pp = vj.w / (densj * densj) + vi.w / (densi * densi) + s;            // :258-260
+    float pp = __fdividef(vj.w, densj * densj) + __fdividef(vi.w, densi * densi) + s;   // :258-260
     float pg = pp * g;
-    return make_float4(w * ((!bi && bj) ? 2.5f : 1.f), pg * rx, pg * ry, pg * rz);
+    return make_float4(w * (ib ? 2.5f : 1.f), pg * rx, pg * ry, pg * rz);
 }
 
 struct V2Args {
@@ -182,7 +218,7 @@ __device__ __forceinline__ void v2_drain_batch(const FsgDev &d, const V2Stage &S
     __syncwarp();
 }
 
-template <bool STATS, bool HASB, int CW>
+template <bool STATS, bool HASB, int CW, bool PK>
 __global__ void __launch_bounds__((CW + 1) * 32, (CW == 4 ? V2_BPS4 : CW == 6 ? 5 : 4))
 k_pair_v2(V2Args va)
 {
@@ -337,6 +373,37 @@ k_pair_v2(V2Args va)
             float w0 = 0.f, w1 = 0.f;
             unsigned m0 = 0, m1 = 0, bit = 1;
             int nin = 0;
+            if (!STATS && PK) {
+                // packed sweep: both home particles of the pass in the two halves of every FP32 instruction
+                const f32x2 nhx = pk2(-pi0.x, -pi1.x), nhy = pk2(-pi0.y, -pi1.y), nhz = pk2(-pi0.z, -pi1.z);
+                const f32x2 ninvh = pk2(-inv_h, -inv_h), two = pk2(2.f, 2.f), one = pk2(1.f, 1.f), ci = pk2(ci0, ci1);
+                f32x2 wacc = pk2(0.f, 0.f);
+#pragma unroll 4
+                for (int c0 = 0; c0 < cpad; c0 += 32, bit <<= 1) {
+                    const float4 pj = S.sp[c0 + lane];
+                    const f32x2 rx = add2(pk2(pj.x, pj.x), nhx), ry = add2(pk2(pj.y, pj.y), nhy), rz = add2(pk2(pj.z, pj.z), nhz);
+                    const f32x2 d2p = fma2(rz, rz, fma2(ry, ry, mul2(rx, rx)));
+                    float d2a, d2b;
+                    upk2(d2p, d2a, d2b);
+                    const f32x2 r = mul2(d2p, pk2(rsqrt_fast(d2a), rsqrt_fast(d2b)));
+                    float ta, tb;
+                    upk2(fma2(r, ninvh, two), ta, tb);
+                    ta = fmaxf(ta, 0.f);                                     // NaN (d2 == 0: the particle itself; padding) -> 0
+                    tb = fmaxf(tb, 0.f);
+                    // 2 - r/h >= 1  <=>  0 < r <= h: the near test costs one compare on a value the sweep has anyway.  A pair
+                    // within rounding of r == h may land on either side: its near terms are O((h - r)^2) ~ 0 there.
+                    if (ta >= 1.f) m0 |= bit;
+                    if (tb >= 1.f) m1 |= bit;
+                    const f32x2 tt = pk2(ta, tb);
+                    f32x2 t3 = mul2(mul2(tt, tt), tt);
+                    if (HASB) {
+                        const float bjf = pj.w < 0.f ? 1.f : 0.f;
+                        t3 = mul2(t3, fma2(ci, pk2(bjf, bjf), one));
+                    }
+                    wacc = add2(wacc, t3);
+                }
+                upk2(wacc, w0, w1);
+            } else {
 #pragma unroll 4
             for (int c0 = 0; c0 < cpad; c0 += 32, bit <<= 1) {
                 const float4 pj = S.sp[c0 + lane];
@@ -373,6 +440,7 @@ k_pair_v2(V2Args va)
                     if (STATS) nin += __popc(__ballot_sync(FULL, u < d2max_bits));
                 }
             }
+            }
             if (STATS && lane == 0) { st_tested += (unsigned long long)ct * (has1 ? 2 : 1); st_in += nin; }
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
@@ -394,8 +462,8 @@ k_pair_v2(V2Args va)
                         m &= m - 1;
                     }
                     qn += __popc(any);
-                    __syncwarp();
                     if (qn >= V2_QCAP - 32) {                      // keep room for one more round
+                        __syncwarp();
                         int qh = 0;
                         while (qn - qh >= 32) { v2_drain_batch<CW>(d, S, W, a.A.velp, qh, qn, lane, wr); qh += 32; }
                         int left = qn - qh;
@@ -465,16 +533,16 @@ k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B,
     keysB[i] = key;
 }
 
-template <int CW>
+template <int CW, bool PK>
 static cudaError_t launch_pair_v2_cw(const V2Args &va, bool stats, bool has_boundary, int sm_count, int blocks_per_sm, cudaStream_t s)
 {
     static bool attr_done = false;
     const int smem = (int)sizeof(V2Smem<CW>);
     if (!attr_done) {
-        cudaFuncSetAttribute(k_pair_v2<false, false, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(k_pair_v2<false, true, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(k_pair_v2<true, false, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(k_pair_v2<true, true, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<false, false, CW, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<false, true, CW, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<true, false, CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_pair_v2<true, true, CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
     int per_sm = CW == 4 ? V2_BPS4 : CW == 6 ? 5 : 4;
@@ -484,12 +552,12 @@ static cudaError_t launch_pair_v2_cw(const V2Args &va, bool stats, bool has_boun
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
     const unsigned threads = (CW + 1) * 32;
-    if (stats) {
-        if (has_boundary) k_pair_v2<true, true, CW><<<(unsigned)blocks, threads, smem, s>>>(va);
-        else k_pair_v2<true, false, CW><<<(unsigned)blocks, threads, smem, s>>>(va);
+    if (stats) {     // the counting build keeps the scalar sweep (its range test uses the reference's unfused distance)
+        if (has_boundary) k_pair_v2<true, true, CW, false><<<(unsigned)blocks, threads, smem, s>>>(va);
+        else k_pair_v2<true, false, CW, false><<<(unsigned)blocks, threads, smem, s>>>(va);
     } else {
-        if (has_boundary) k_pair_v2<false, true, CW><<<(unsigned)blocks, threads, smem, s>>>(va);
-        else k_pair_v2<false, false, CW><<<(unsigned)blocks, threads, smem, s>>>(va);
+        if (has_boundary) k_pair_v2<false, true, CW, PK><<<(unsigned)blocks, threads, smem, s>>>(va);
+        else k_pair_v2<false, false, CW, PK><<<(unsigned)blocks, threads, smem, s>>>(va);
     }
     return cudaGetLastError();
 }
@@ -506,9 +574,15 @@ cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool
         cw = e ? atoi(e) : V2_DEFAULT_CW;
         if (cw != 4 && cw != 6 && cw != 8) cw = V2_DEFAULT_CW;
     }
-    if (cw == 6) return launch_pair_v2_cw<6>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
-    if (cw == 8) return launch_pair_v2_cw<8>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
-    return launch_pair_v2_cw<4>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
+    static int pk = -1;
+    if (pk < 0) {                                     // FSG_PAIR_PK = 0: scalar sweep (A/B knob; default packed FFMA2 sweep)
+        const char *e = getenv("FSG_PAIR_PK");
+        pk = e ? (atoi(e) != 0) : 1;
+    }
+    if (cw == 6) return launch_pair_v2_cw<6, true>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
+    if (cw == 8) return launch_pair_v2_cw<8, true>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
+    if (!pk) return launch_pair_v2_cw<4, false>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
+    return launch_pair_v2_cw<4, true>(va, stats, has_boundary, sm_count, blocks_per_sm, s);
 }
 
 cudaError_t fsg_launch_update(const FsgDev &d, int64_t n, const int *keysA, FsgState A, FsgState B, int *keysB,
