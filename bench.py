@@ -38,7 +38,8 @@ import numpy as np  # noqa: E402
 
 ALG_BYTES_STEP = 272      # algorithmic HBM bytes per particle-step (reorder 136 + tables 4 + pair/update 132)
 ALG_BYTES_PAIR = 132      # the fused pair-sum/EOS/integrate/re-bin kernel: read 64 + write 64 + new key 4
-NCU_PAIR_DRAM_BYTES_PER_PARTICLE = 47.2   # measured: ncu --set full on k_pair_v2 at 256^3 (profiles/r1_ncu_pair_v2_final.txt)
+# measured DRAM bytes per particle of the pair kernel (ncu --set full at 256^3): [symmetric k_pair_v3, gather k_pair_v2]
+NCU_PAIR_DRAM_BYTES_PER_PARTICLE = [(47.2, "profiles/r1_ncu_pair_v3.txt"), (47.2, "profiles/r1_ncu_pair_v2_final.txt")]
 FLOP_IN_RANGE, FLOP_REJECTED = 50, 12   # SURVEY.md §8d algorithmic flop per in-range / rejected candidate
 SPACING, JITTER, SEED = 0.05, 0.005, 20261018
 CPU_SAMPLE_GRID = 128     # bounded sample for the CPU legs: the same plume at 128^3 bins (1.07 M particles)
@@ -163,6 +164,7 @@ def fsg_arm(args):
     hbm_peak, peak_src, sm_max = peaks()
     G = args.grid
     cfg = fsg.scenes.plume_config(G)
+    cfg.pair_mode = args.pair_mode
     cfg.device = local
     cfg.rank, cfg.world = rank, world
     n_total = fsg.scenes.plume_count(cfg, SPACING)
@@ -251,12 +253,14 @@ def fsg_arm(args):
     # ---- roofline of the dominant kernel ----
     pair_ms = phase["pair_update"] / max(1, phase["steps"])
     achieved = ALG_BYTES_PAIR * n_local / (pair_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_pair_v2 + k_update (pair sums, then EOS/integrate/re-bin)", "achieved": achieved,
+    symmetric = args.pair_mode == 0 and not (world > 1 and args.exchange == "peer" and args.overlap)
+    kname = "k_pair_v3 (symmetric pair sums)" if symmetric else "k_pair_v2 (gather pair sums)"
+    ncu_b = NCU_PAIR_DRAM_BYTES_PER_PARTICLE[0 if symmetric else 1]
+    roofline = {"bound": "hbm", "kernel": kname + " + k_update (EOS/integrate/re-bin)", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": NCU_PAIR_DRAM_BYTES_PER_PARTICLE * n_local + 152.0 * n_local, "peak_source": peak_src,
-                "traffic_note": "k_pair_v2: dram__bytes_read+write = 402.6 MB per launch at 256^3 under ncu --set full "
-                                "(profiles/r1_ncu_pair_v2_final.txt) = 47.2 B/particle, scaled by the particle count; k_update: its 152 B/particle "
-                                "of streaming reads + writes",
+                "traffic": ncu_b[0] * n_local + 152.0 * n_local, "peak_source": peak_src,
+                "traffic_note": f"pair kernel: dram__bytes_read+write = {ncu_b[0]} B/particle under ncu --set full at 256^3 ({ncu_b[1]}), "
+                                "scaled by the particle count; k_update: its 152 B/particle of streaming reads + writes",
                 "kernel_ms": pair_ms, "share_of_step": pair_ms / ms_step,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PAIR * n_local,
                 "note": "this kernel is CUDA-core (FP32 issue) bound, not HBM bound: see roofline_fp32; the HBM-bound phases are in `phases`"}
@@ -373,6 +377,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--pair-mode", type=int, default=0, choices=[0, 1],
+                    help="0: symmetric pair kernel (default); 1: deterministic gather kernel (fsg_config.pair_mode)")
     ap.add_argument("--overlap", action="store_true",
                     help="N>1, peer exchange: boundary bins first, next step's pack + copies on a second stream beside the interior bins "
                          "(measured slower than the plain order at 512^3: splitting the pair kernel costs more than the exchange it hides)")

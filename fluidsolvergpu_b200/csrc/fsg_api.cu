@@ -1,6 +1,7 @@
 // fsg_api.cu — the extern "C" boundary of libfsg (include/fsg.h): context lifetime, host<->device
 // movement and the step schedule.  No torch types, no exceptions across the boundary, no CPU path.
 #include "fsg_internal.cuh"
+#include <stdlib.h>
 
 #include <math.h>
 #include <stdio.h>
@@ -26,8 +27,24 @@ int fsg_scene_plume_device(fsg_ctx *c, double spacing, double jitter, uint64_t s
 static float largest_float_le(double v) { float f = (float)v; while ((double)f > v) f = nextafterf(f, -INFINITY); return f; }
 static float largest_float_lt(double v) { float f = (float)v; while ((double)f >= v) f = nextafterf(f, -INFINITY); return f; }
 
+// Which pair kernel the uncapped fp32 configuration runs: the symmetric one (fsg_pair_v3.cu) unless the caller asked for
+// the deterministic gather kernel (pair_mode = 1, or FSG_PAIR_SYM=0 in the environment), pair counts are being collected
+// (the counting build is the gather kernel) or the exchange overlaps the interior bins (two launches per step).
+void fsg_update_pair_mode(fsg_ctx *c)
+{
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("FSG_PAIR_SYM");
+        env = e ? (atoi(e) != 0) : 1;
+    }
+    const fsg_config &f = c->cfg;
+    c->dev.sym = env && f.model == FSG_MODEL_BASE && f.pair_mode == 0 && f.pair_fp64 == 0 && f.neighbour_cap == 0 && f.bin_cap == 0 &&
+                 f.collect_stats == 0 && !c->overlap && f.grid >= 4;
+}
+
 void fsg_derive_constants(const fsg_config &cfg, FsgDev &d)
 {
+    d.sym = 0;
     d.G = cfg.grid;
     d.G2 = cfg.grid * cfg.grid;
     d.numcells = cfg.grid * cfg.grid * cfg.grid;
@@ -241,6 +258,7 @@ extern "C" int fsg_create(const fsg_config *cfg, fsg_ctx **out)
     c->cfg = *cfg;
     c->device = cfg->device;
     fsg_derive_constants(*cfg, c->dev);
+    fsg_update_pair_mode(c);
     int rc = create_impl(c);
     if (rc != FSG_OK) {
         g_create_err = c->err;
@@ -712,6 +730,7 @@ extern "C" int fsg_set_collect_stats(fsg_ctx *c, int on)
 {
     if (!c) return FSG_E_INVALID;
     c->cfg.collect_stats = on != 0;
+    fsg_update_pair_mode(c);
     return FSG_OK;
 }
 

@@ -134,7 +134,7 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
             if (key != prev) {
                 start[key] = (int)k;
                 int ix = key / d.G2;
-                head = ix >= d.bx0 && ix < d.bx1;                         // interior home bins
+                head = (ix >= d.bx0 && ix < d.bx1) || (d.sym && ix == d.x0 - 1);   // interior home bins (+ the lower ghost layer for the symmetric kernel)
                 headB = ix >= d.x0 && ix < d.x1 && !head;                 // boundary home bins (empty list unless the exchange overlaps)
             }
             if (key != next) end[key] = (int)k;
@@ -474,7 +474,8 @@ cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binli
             *launches += 4;
             return e2;
         }
-        e2 = fsg_launch_pair_v2(a, c->sums, stats, c->has_boundary, c->sm_count, 0, s);
+        if (c->dev.sym) e2 = fsg_launch_pair_v3(a, c->sums, c->has_boundary, c->sm_count, s);
+        else e2 = fsg_launch_pair_v2(a, c->sums, stats, c->has_boundary, c->sm_count, 0, s);
         if (e2 != cudaSuccess) return e2;
         e2 = fsg_launch_update(c->dev, n, c->keysA, c->A, c->B, c->keysB, c->sums, carry, 0, c->cfg.world > 1 ? c->counters + 6 : nullptr, s);
         *launches += 2;

@@ -86,6 +86,8 @@ cudaError_t fsg_launch_pair_fast(const PairArgs &a, bool stats, int sm_count, cu
 // fsg_pair_v2.cu
 cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool has_boundary, int sm_count, int blocks_per_sm,
                                cudaStream_t s);
+// fsg_pair_v3.cu — symmetric pair sums (each pair of particles in different bins is evaluated once); clears `sums` first
+cudaError_t fsg_launch_pair_v3(const PairArgs &a, float4 *sums, bool has_boundary, int sm_count, cudaStream_t s);
 // part: 0 every slot, 1 the slab's boundary slots (boundary bins, ghosts, parked, dead), 2 the interior slots
 cudaError_t fsg_launch_update(const FsgDev &d, int64_t n, const int *keysA, FsgState A, FsgState B, int *keysB,
                               const float4 *sums, const float4 *carry, int part, int *violation, cudaStream_t s);

@@ -21,6 +21,7 @@
 //     warp scan, so the result is deterministic (no atomics, fixed order).
 //   * sums (newdens, newdelpress x/y/z) go to a float4 array that k_update consumes.
 #include "fsg_device.cuh"
+#include "fsg_pair_common.cuh"
 
 #include <stdlib.h>
 
@@ -53,32 +54,6 @@ struct V2Smem {
     unsigned long long full[V2_NST];
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// try_wait suspends the thread in hardware until the phase completes or the hint (ns) elapses, so the
-// loop below is not a busy spin
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    unsigned ok = 0;
-    const unsigned addr = smem_u32(bar);
-    for (;;) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
-        if (ok) break;
-        __nanosleep(256);      // a warp that is ahead of its block's slowest warp must not eat issue slots
-    }
-}
 // "stage is free again" goes through hardware named barriers (ids 1..V2_NST): the consumer warps
 // arrive without blocking, the producer warp blocks in bar.sync — no polling, no issue slots taken
 // from the consumers while the producer is stages ahead.
@@ -98,51 +73,6 @@ __device__ __forceinline__ void stage_free_wait(int stage)
     else asm volatile("bar.sync 3, %0;" ::"n"(THREADS) : "memory");
 }
 static_assert(V2_NST == 3, "stage_free_* name one barrier per stage");
-// 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ float rsqrt_fast(float x)
-{
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// Packed FP32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): one instruction works on the two home particles of a pass.
-// A scalar operand duplicated into both halves costs nothing — ptxas encodes it as a broadcast (`R4.F32`).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi)
-{
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
-{
-    f32x2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-    f32x2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
 // pressure / viscosity / inner-W terms of one r <= h pair (FluidGPU.cu:238-279)
 __device__ __forceinline__ float4 v2_near_pair(const FsgDev &d, const float4 &pi, const float4 &vi, const float4 &pj,
                                                const float4 &vj)

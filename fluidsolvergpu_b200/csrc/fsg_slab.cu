@@ -462,6 +462,7 @@ extern "C" int fsg_slab_set_overlap(fsg_ctx *c, int on)
     c->dev.bx0 = c->dev.x0 + ((on && c->cfg.rank > 0) ? 2 : 0);
     c->dev.bx1 = c->dev.x1 - ((on && c->cfg.rank < c->cfg.world - 1) ? 2 : 0);
     if (c->dev.bx1 < c->dev.bx0) c->dev.bx1 = c->dev.bx0;
+    fsg_update_pair_mode(c);
     return FSG_OK;
 }
 

@@ -80,7 +80,11 @@ typedef struct fsg_config {
     /* slab decomposition along x, the slowest bin axis (solver-unidyn.cu:187-193) */
     int32_t rank, world;    /* this context's slab and the number of slabs (1 = no decomposition) */
     int32_t slab_x0, slab_x1; /* world > 1: this slab owns the bin layers slab_x0 <= ix < slab_x1 (ix = bin id / grid^2) */
-    int32_t reserved[3];
+    int32_t pair_mode;      /* uncapped fp32 configuration only.  0 (default): symmetric pair kernel — a pair of particles in
+                               two bins is evaluated once and added to both through float reductions, so sums are
+                               reproducible to rounding (~1e-7), not bit for bit; 1: deterministic gather kernel
+                               (every particle sums its own 27 bins in a fixed order)                         */
+    int32_t reserved[2];
 } fsg_config;
 
 /* Host-side structure-of-arrays view used by fsg_upload_soa / fsg_download_soa: the live fields

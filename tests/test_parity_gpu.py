@@ -621,6 +621,7 @@ def test_slab_raw_round_trip_through_host_memory(fsg):
     Must be bit-identical to a run that never left the device — including particles that had crossed a face and were
     waiting to migrate when they were downloaded."""
     cfg, state = _slab_scene(fsg, True)
+    cfg.pair_mode = 1      # bit-identity needs the deterministic gather kernel; the symmetric one sums through float reductions
     n = state["pos"].shape[0]
     cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), 3)
     with fsg.SlabGroup(cfg, 3, cuts, capacity=2 * n + 64) as a, fsg.SlabGroup(cfg, 3, cuts, capacity=2 * n + 64) as b:
@@ -639,3 +640,77 @@ def test_slab_raw_round_trip_through_host_memory(fsg):
         assert ga["index"].shape[0] == n and np.array_equal(ga["index"], gb["index"])
         for f in FIELDS + ("cell",):
             assert np.array_equal(ga[f], gb[f]), f
+
+
+# ---------------------------------------------------------------------------------------------
+# symmetric pair kernel (fsg_pair_v3.cu, pair_mode = 0, the default of the uncapped configuration when pair counts are
+# not being collected) — the same per-step bar against the oracle, and agreement with the deterministic gather kernel
+# ---------------------------------------------------------------------------------------------
+def _symmetric_scenes(fsg):
+    cfg = fsg.scenes.plume_config(24)
+    yield "plume24", cfg, fsg.scenes.plume_scene(cfg), 4
+    for bf in (0.0, 0.2):
+        cfg = fsg.scenes.plume_config(17)
+        cfg.origin = -1.02
+        yield f"random bf={bf}", cfg, fsg.scenes.random_base_scene(6000, 21, box=((-0.4, 0.4),) * 3, spacing=0.05, jitter=0.012,
+                                                                   boundary_frac=bf), 3
+    rng = np.random.default_rng(17)      # particles in the outermost bin layers: the linear bin offsets wrap there
+    pos = rng.uniform(-1.0, 1.0, (6000, 3)).astype(np.float32)
+    pos[:2000] = np.where(rng.uniform(size=(2000, 3)) < 0.5, -1.0, 1.0) * rng.uniform(0.93, 1.0, (2000, 3))
+    cfg = fsg.scenes.plume_config(17)
+    cfg.origin = -1.02
+    yield "grid faces", cfg, fsg.scenes.default_state(pos.astype(np.float32), vel=rng.uniform(-0.1, 0.1, pos.shape).astype(np.float32)), 2
+    rng = np.random.default_rng(5)       # ~60 particles per bin, ~900 per half neighbourhood: home groups, candidate tiles, mark slices
+    cfg = fsg.scenes.plume_config(17)
+    cfg.origin = -1.02
+    yield "dense", cfg, fsg.scenes.default_state(rng.uniform(-0.1, 0.1, (4000, 3)).astype(np.float32)), 1
+    rng = np.random.default_rng(6)       # a clump far inside h: hundreds of near pairs per home particle
+    cfg = fsg.scenes.plume_config(17)
+    cfg.origin = -1.02
+    yield "clump", cfg, fsg.scenes.default_state(rng.uniform(-0.03, 0.03, (1500, 3)).astype(np.float32)), 1
+
+
+def test_symmetric_pair_kernel_against_oracle(fsg):
+    for name, cfg, state, steps in _symmetric_scenes(fsg):
+        cfg.capacity = state["pos"].shape[0]
+        cfg.collect_stats = 0
+        cfg.pair_mode = 0
+        with fsg.FluidSolver(cfg) as s:
+            s.upload(state)
+            for k in range(steps):
+                errs = resync_step(fsg, s)
+                print("symmetric", name, k + 1, errs)
+
+
+def test_symmetric_and_gather_kernels_agree(fsg):
+    """Same scene, same bits in: the two kernels differ only in the order of their float additions."""
+    for name, cfg, state, steps in _symmetric_scenes(fsg):
+        cfg.capacity = state["pos"].shape[0]
+        cfg.collect_stats = 0
+        outs = []
+        for mode in (0, 1):
+            cfg.pair_mode = mode
+            with fsg.FluidSolver(cfg) as s:
+                s.upload(state)
+                s.step(1)
+                outs.append(fsg.by_index(s.download()))
+        for f in ("pos", "vel", "cell", "boundary", "index"):
+            assert np.array_equal(outs[0][f], outs[1][f]), (name, f)
+        for f in ("acc", "dens", "press", "delpress"):
+            err = rel_l2(outs[0][f], outs[1][f])
+            assert err <= 2e-6, (name, f, err)
+
+
+def test_gather_kernel_is_deterministic_on_the_plume(fsg):
+    cfg = fsg.scenes.plume_config(24)
+    state = fsg.scenes.plume_scene(cfg)
+    cfg.capacity = state["pos"].shape[0]
+    cfg.pair_mode = 1
+    outs = []
+    for _ in range(2):
+        with fsg.FluidSolver(cfg) as s:
+            s.upload(state)
+            s.step(5)
+            outs.append(s.download())
+    for f in FIELDS + ("index", "cell"):
+        assert np.array_equal(outs[0][f], outs[1][f]), f
