@@ -39,7 +39,7 @@ import numpy as np  # noqa: E402
 ALG_BYTES_STEP = 272      # algorithmic HBM bytes per particle-step (reorder 136 + tables 4 + pair/update 132)
 ALG_BYTES_PAIR = 132      # the fused pair-sum/EOS/integrate/re-bin kernel: read 64 + write 64 + new key 4
 # measured DRAM bytes per particle of the pair kernel (ncu --set full at 256^3): [symmetric k_pair_v3, gather k_pair_v2]
-NCU_PAIR_DRAM_BYTES_PER_PARTICLE = [(47.2, "profiles/r1_ncu_pair_v3.txt"), (47.2, "profiles/r1_ncu_pair_v2_final.txt")]
+NCU_PAIR_DRAM_BYTES_PER_PARTICLE = [(62.6, "profiles/r1_ncu_pair_v3.txt"), (47.2, "profiles/r1_ncu_pair_v2_final.txt")]
 FLOP_IN_RANGE, FLOP_REJECTED = 50, 12   # SURVEY.md §8d algorithmic flop per in-range / rejected candidate
 SPACING, JITTER, SEED = 0.05, 0.005, 20261018
 CPU_SAMPLE_GRID = 128     # bounded sample for the CPU legs: the same plume at 128^3 bins (1.07 M particles)

@@ -26,13 +26,15 @@
 #include "fsg_device.cuh"
 #include "fsg_pair_common.cuh"
 
+#ifndef V3_WARPS
 #define V3_WARPS 4                      // independent warps per block
+#define V3_BPS 5                        // resident blocks per SM
+#endif
 #define V3_TILE 256                     // staged candidates per stage
 #define V3_CH (V3_TILE / 32)            // 32-candidate chunks per tile = candidate accumulators per lane
 #define V3_GROUP 32                     // home particles per item (lane k owns the row sums of home particle k)
 #define V3_QCAP 160                     // near-pair queue entries
 #define V3_GRAB 8                       // home bins per queue grab
-#define V3_BPS 5                        // resident blocks per SM
 
 struct V3Stage {
     float4 sp[V3_TILE];                 // candidate (x, y, z, +-dens)
