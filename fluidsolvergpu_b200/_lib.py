@@ -88,6 +88,12 @@ SIGNATURES = {
     "fsg_stage_findneighbours": (C.c_int, [P, P, P, P, C.c_int64]),
     "fsg_stage_mykernel": (C.c_int, [P, P, P, P, P, C.c_int64]),
     "fsg_stage_mykernel2": (C.c_int, [P, P, P, P, P, C.c_int64, P, P, P]),
+    "fsg_stage_unidyn_count_after_merge": (C.c_int, [P, P, C.c_int64, P]),
+    "fsg_stage_unidyn_findneighbours": (C.c_int, [P, P, P, P, P, C.c_int64, C.c_int32]),
+    "fsg_stage_unidyn_mykernel": (C.c_int, [P, P, P, P, P, P, P, C.c_int64]),
+    "fsg_stage_unidyn_mykernel3": (C.c_int, [P, P, P, P, P, C.c_int64]),
+    "fsg_stage_unidyn_mykernel2": (C.c_int, [P, P, P, P, P, P, P, P, C.c_int64, C.c_int32, C.c_int32, P, P, P]),
+    "fsg_stage_unidyn_cell_calc": (C.c_int, [P, P, P, C.c_int64]),
 }
 
 _lib = None

@@ -229,6 +229,61 @@ k_pair_unidyn(UniArgs a)
 // mykernel2 (cu:451-497) + Particle::update(t) (cuh:296-423) + cell_calc (cu:544-551), per sorted slot.
 // Follows the reference's float / double promotions expression by expression.
 // ------------------------------------------------------------------------------------------------
+// mykernel2's per-particle work after the export: Particle::update(t) (cuh:296-423) for one particle of a live bin,
+// then cell_calc's bin id (cu:547).  s = (newdens, newdelpress xyz), s2 = (diffusion xyz, delfluid).
+__device__ __forceinline__ void unidyn_particle_update(const FsgDev &d, float4 &pd, float4 &vp, float4 &af, float4 &dpi, float4 &mx,
+                                                       const float4 s, const float4 s2, int &key)
+{
+    const float diffx = s2.x, diffy = s2.y, diffz = s2.z;
+    float delfluid = s2.w;
+    const float delsolid = 0.f;
+    const bool bnd = pd.w < 0.f;
+    float solid = mx.x, fluid = mx.y;
+    const double DT = d.dt;
+    // set_dens cuh:183-185, calculate_pressure cuh:282-284 (double pow; RHO_0_SAND == RHO_0)
+    const float dens = (float)((double)(s.x + d.w0) / 23.0 * (double)(1 + (float)bnd * 1.5) + 9250);
+    const double eos = pow((double)(dens / 9550), 7.0) - 1;
+    const float press = (float)((double)((1 - solid) * 1000) * 1.0 * 9550 / 7.0 * eos + (double)(solid * 1000) * 1.0 * 9550 / 7.0 * eos);
+    dpi.x = s.y; dpi.y = s.z; dpi.z = s.w;                                // set_delpress cuh:302
+    if (!bnd) {
+        const float friction = fabsf(diffx) + fabsf(diffy) + fabsf(diffz);   // cuh:311
+        solid = (float)((double)solid + DT * (double)delsolid);           // :312-313
+        solid *= (solid >= 0.0);
+        if ((double)(fluid + delfluid) < 0.2) delfluid = 0;               // :315
+        fluid = (float)((double)fluid + DT * (double)delfluid);           // :316-317
+        fluid *= (fluid >= 0);
+        fluid *= 1 / (fluid + solid);                                     // :319-320
+        solid *= 1 / (fluid + solid);
+        float x = (float)((double)pd.x + DT * (double)vp.x + 0.5 * DT * DT * (double)af.x + (double)(0 * diffx));   // :328-330
+        float y = (float)((double)pd.y + DT * (double)vp.y + 0.5 * DT * DT * (double)af.y + (double)(0 * diffy));
+        float z = (float)((double)pd.z + DT * (double)vp.z + 0.5 * DT * DT * (double)af.z + (double)(0 * diffz));
+        float vx = vp.x, vy = vp.y, vz = vp.z;
+        if ((double)z < -0.89) { vx = 0; vy = 0; }                        // :332-341
+        // :351-353 — stress_accel == mixture_accel == 0 in scope; the y and z lines test the NEW xvel (sic)
+        const double fr = (double)friction * 0.0000002 * (double)solid;
+        double tx = (double)vx + DT * (double)af.x;
+        vx = (float)(((double)vx + 0.5 * DT * (double)af.x) - (tx > 0) * fr + (tx < 0) * fr);
+        tx = (double)vx + DT * (double)af.x;
+        vy = (float)(((double)vy + 0.5 * DT * (double)af.y) - (tx > 0) * fr + (tx < 0) * fr);
+        vz = (float)(((double)vz + 0.5 * DT * (double)af.z) - (tx > 0) * fr + (tx < 0) * fr);
+        af.x = (float)(-((220.0 - 70.0 * (double)solid) / (double)dens) * (double)dpi.x);     // :357-359
+        af.y = (float)(-((220.0 - 70.0 * (double)solid) / (double)dens) * (double)dpi.y);
+        af.z = (float)(d.gravity + ((-220.0 + 70.0 * (double)solid) / (double)dens) * (double)dpi.z);
+        vx = (float)((double)vx + 0.5 * (double)af.x * DT);                // :390-392
+        vy = (float)((double)vy + 0.5 * (double)af.y * DT);
+        vz = (float)((double)vz + 0.5 * (double)af.z * DT);
+        if ((double)fabsf(z) > 0.98) { z = (float)(0.97 / (double)z); vz = 0; }               // :404-413
+        if ((double)fabsf(y) > 0.98) vy = -vy;
+        if ((double)fabsf(x) > 0.98) vx = -vx;
+        pd.x = x; pd.y = y; pd.z = z;
+        vp.x = vx; vp.y = vy; vp.z = vz;
+        mx.x = solid; mx.y = fluid;
+    }
+    pd.w = bnd ? -dens : dens;
+    vp.w = press;
+    key = bin_id(d, pd.x, pd.y, pd.z);                                    // cell_calc, cu:547
+}
+
 __global__ void __launch_bounds__(256)
 k_update_unidyn(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B, int *__restrict__ keysB,
                 const float4 *__restrict__ sums, const float4 *__restrict__ sums2, const float4 *__restrict__ carry, float *__restrict__ vizb)
@@ -241,55 +296,8 @@ k_update_unidyn(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgS
     if (key < d.numcells) {
         float4 s = sums[i], s2 = sums2[i];
         if (carry) { float4 cy = carry[i]; s.x += cy.x; s.y += cy.y; s.z += cy.z; s.w += cy.w; }
-        const float diffx = s2.x, diffy = s2.y, diffz = s2.z;
-        float delfluid = s2.w;
-        const float delsolid = 0.f;
-        b3 = diffx * diffx + diffy * diffy + diffz * diffz;                  // cu:466
-        const bool bnd = pd.w < 0.f;
-        float solid = mx.x, fluid = mx.y;
-        const double DT = d.dt;
-        // set_dens cuh:183-185, calculate_pressure cuh:282-284 (double pow; RHO_0_SAND == RHO_0)
-        const float dens = (float)((double)(s.x + d.w0) / 23.0 * (double)(1 + (float)bnd * 1.5) + 9250);
-        const double eos = pow((double)(dens / 9550), 7.0) - 1;
-        const float press = (float)((double)((1 - solid) * 1000) * 1.0 * 9550 / 7.0 * eos + (double)(solid * 1000) * 1.0 * 9550 / 7.0 * eos);
-        dpi.x = s.y; dpi.y = s.z; dpi.z = s.w;                                // set_delpress cuh:302
-        if (!bnd) {
-            const float friction = fabsf(diffx) + fabsf(diffy) + fabsf(diffz);   // cuh:311
-            solid = (float)((double)solid + DT * (double)delsolid);           // :312-313
-            solid *= (solid >= 0.0);
-            if ((double)(fluid + delfluid) < 0.2) delfluid = 0;               // :315
-            fluid = (float)((double)fluid + DT * (double)delfluid);           // :316-317
-            fluid *= (fluid >= 0);
-            fluid *= 1 / (fluid + solid);                                     // :319-320
-            solid *= 1 / (fluid + solid);
-            float x = (float)((double)pd.x + DT * (double)vp.x + 0.5 * DT * DT * (double)af.x + (double)(0 * diffx));   // :328-330
-            float y = (float)((double)pd.y + DT * (double)vp.y + 0.5 * DT * DT * (double)af.y + (double)(0 * diffy));
-            float z = (float)((double)pd.z + DT * (double)vp.z + 0.5 * DT * DT * (double)af.z + (double)(0 * diffz));
-            float vx = vp.x, vy = vp.y, vz = vp.z;
-            if ((double)z < -0.89) { vx = 0; vy = 0; }                        // :332-341
-            // :351-353 — stress_accel == mixture_accel == 0 in scope; the y and z lines test the NEW xvel (sic)
-            const double fr = (double)friction * 0.0000002 * (double)solid;
-            double tx = (double)vx + DT * (double)af.x;
-            vx = (float)(((double)vx + 0.5 * DT * (double)af.x) - (tx > 0) * fr + (tx < 0) * fr);
-            tx = (double)vx + DT * (double)af.x;
-            vy = (float)(((double)vy + 0.5 * DT * (double)af.y) - (tx > 0) * fr + (tx < 0) * fr);
-            vz = (float)(((double)vz + 0.5 * DT * (double)af.z) - (tx > 0) * fr + (tx < 0) * fr);
-            af.x = (float)(-((220.0 - 70.0 * (double)solid) / (double)dens) * (double)dpi.x);     // :357-359
-            af.y = (float)(-((220.0 - 70.0 * (double)solid) / (double)dens) * (double)dpi.y);
-            af.z = (float)(d.gravity + ((-220.0 + 70.0 * (double)solid) / (double)dens) * (double)dpi.z);
-            vx = (float)((double)vx + 0.5 * (double)af.x * DT);                // :390-392
-            vy = (float)((double)vy + 0.5 * (double)af.y * DT);
-            vz = (float)((double)vz + 0.5 * (double)af.z * DT);
-            if ((double)fabsf(z) > 0.98) { z = (float)(0.97 / (double)z); vz = 0; }               // :404-413
-            if ((double)fabsf(y) > 0.98) vy = -vy;
-            if ((double)fabsf(x) > 0.98) vx = -vx;
-            pd.x = x; pd.y = y; pd.z = z;
-            vp.x = vx; vp.y = vy; vp.z = vz;
-            mx.x = solid; mx.y = fluid;
-        }
-        pd.w = bnd ? -dens : dens;
-        vp.w = press;
-        key = bin_id(d, pd.x, pd.y, pd.z);                                    // cell_calc, cu:547
+        b3 = s2.x * s2.x + s2.y * s2.y + s2.z * s2.z;                         // cu:466
+        unidyn_particle_update(d, pd, vp, af, dpi, mx, s, s2, key);
     }
     B.posd[i] = pd;
     B.velp[i] = vp;
@@ -419,4 +427,285 @@ cudaError_t fsg_launch_pack_aos_unidyn(unsigned char *aos, int64_t n, FsgState s
     if (n <= 0) return cudaSuccess;
     k_pack_aos_unidyn<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(aos, n, st, carry, keys, d);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage API for the unidyn model: one call per reference launch of solver-unidyn.cu:341-548, on caller-owned
+// DEVICE buffers in the reference's layout (340-byte unidyn Particle records, int tables).  The context (model
+// FSG_MODEL_UNIDYN) supplies constants and scratch memory.  Single-device form of the loop (x origin 0, buffer 0 —
+// what the shipped driver runs, solver-unidyn.cu:192-195).  The inter-kernel protocol is kept: mykernel marks the
+// split bins, sets subindex and ADDS the pair sums of the particles in unsplit bins onto the records' accumulators,
+// mykernel3 adds those of the split bins, mykernel2 exports / updates / zeroes / resets, cell_calc re-bins.
+// ------------------------------------------------------------------------------------------------
+#include <stdio.h>
+#define CUU(ctx, call)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            char b_[512];                                                                               \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            (ctx)->err = b_;                                                                            \
+            return e_ == cudaErrorMemoryAllocation ? FSG_E_NOMEM : FSG_E_CUDA;                          \
+        }                                                                                               \
+    } while (0)
+
+static int uni_stage_ok(fsg_ctx *c, int64_t n, const char *what)
+{
+    if (c->cfg.model != FSG_MODEL_UNIDYN) { c->err = std::string(what) + ": the context is not a unidyn context"; return FSG_E_STATE; }
+    if (n > c->cap) { c->err = std::string(what) + ": n exceeds the context capacity"; return FSG_E_INVALID; }
+    return FSG_OK;
+}
+
+// count_after_merge, FluidGPU-unidyn.cu:554-562: the first sorted slot whose bin id is outside the grid
+__global__ void k_stage_uni_count(const int *__restrict__ cells, int64_t n, int numcells, int *newsize)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > 0 && i < n && cells[i] >= numcells && cells[i - 1] < numcells) *newsize = (int)i;
+}
+extern "C" int fsg_stage_unidyn_count_after_merge(fsg_ctx *c, const int32_t *d_cells, int64_t n, int32_t *d_newsize)
+{
+    if (!c || n < 0 || !d_newsize || (n > 0 && !d_cells)) return FSG_E_INVALID;
+    if (n == 0) return FSG_OK;
+    CUU(c, cudaSetDevice(c->device));
+    k_stage_uni_count<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_cells, n, c->dev.numcells, d_newsize);
+    CUU(c, cudaGetLastError());
+    c->launches++;
+    return FSG_OK;
+}
+
+// findneighbours, FluidGPU-unidyn.cu:106-122 (x = id of the slab's first bin)
+__global__ void k_stage_uni_findneighbours(const int *__restrict__ cell, int *start, int *start_copy, int *end, int64_t n, int x, int numcells)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int key = cell[i] - x;
+    if (key < 0 || key >= numcells) return;       // the reference writes out of bounds here
+    if (i == 0 || cell[i - 1] != cell[i]) { start[key] = (int)i; start_copy[key] = (int)i; }
+    if (i == n - 1 || cell[i + 1] != cell[i]) end[key] = (int)i;
+}
+extern "C" int fsg_stage_unidyn_findneighbours(fsg_ctx *c, const int32_t *d_cells, int32_t *d_start, int32_t *d_start_copy, int32_t *d_end,
+                                               int64_t n, int32_t x)
+{
+    if (!c || n < 0 || (n > 0 && (!d_cells || !d_start || !d_start_copy || !d_end))) return FSG_E_INVALID;
+    if (n == 0) return FSG_OK;
+    CUU(c, cudaSetDevice(c->device));
+    k_stage_uni_findneighbours<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_cells, d_start, d_start_copy, d_end, n, x, c->dev.numcells);
+    CUU(c, cudaGetLastError());
+    c->launches++;
+    return FSG_OK;
+}
+
+// records -> the SoA streams the pair kernel reads + the list of occupied bins of one kind (which = 0: at most 6
+// particles, mykernel's bins; 1: more than 6, mykernel3's).  mark: also do mykernel's split marking (cu:181-191).
+__global__ void __launch_bounds__(256)
+k_stage_uni_unpack(FsgDev d, const unsigned char *__restrict__ aos_c, unsigned char *__restrict__ aos, const int *__restrict__ cell,
+                   const int *__restrict__ start, const int *__restrict__ end, int64_t n, FsgState st, int *binlist, int *nocc, int which,
+                   int *split, int *numsplit)
+{
+    using namespace aos_uni;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool head = false;
+    int key = -1;
+    if (i < n) {
+        const unsigned char *r = aos_c + i * FSG_AOS_STRIDE;
+        const bool bnd = r[BOUNDARY] != 0;
+        const float dens = uldf(r, DENS);
+        const float4 pd = make_float4(uldf(r, POS), uldf(r, POS + 4), uldf(r, POS + 8), bnd ? -dens : dens);
+        st.posd[i] = pd;
+        st.velp[i] = make_float4(uldf(r, VEL), uldf(r, VEL + 4), uldf(r, VEL + 8), uldf(r, PRESS));
+        st.mix[i] = make_float4(uldf(r, SOLID), uldf(r, FLUID), 0.f, 0.f);
+        key = cell[i];
+        if (key >= 0 && key < d.numcells) {
+            const int pop = end[key] - start[key] + 1;
+            const bool is_split = pop > 6;
+            const bool first = i == 0 || cell[i - 1] != key;
+            head = first && (is_split == (which == 1));
+            if (split && is_split) {
+                *reinterpret_cast<int *>(aos + i * FSG_AOS_STRIDE + SUBINDEX) = uni_subindex(d, pd.x, pd.y, pd.z);   // cu:182-184
+                if (first) { split[key] = key; atomicAdd(numsplit, 1); }                                              // cu:186-189
+            }
+        }
+    }
+    __shared__ int s_cnt[8], s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(FULL, head);
+    if (lane == 0) s_cnt[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { int cc = s_cnt[w]; s_cnt[w] = tot; tot += cc; }
+        s_base = tot ? atomicAdd(nocc, tot) : 0;
+    }
+    __syncthreads();
+    if (head) binlist[s_base + s_cnt[warp] + __popc(m & ((1u << lane) - 1))] = key;
+}
+
+// the atomicAdd targets of the pair loops (cu:358-366, 401): sums are ADDED to the accumulators of the particles
+// whose bin was in this launch's list
+__global__ void k_stage_uni_add_sums(unsigned char *__restrict__ aos, const int *__restrict__ cell, const int *__restrict__ start,
+                                     const int *__restrict__ end, const float4 *__restrict__ sums, const float4 *__restrict__ sums2,
+                                     int64_t n, int numcells, int which)
+{
+    using namespace aos_uni;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int key = cell[i];
+    if (key < 0 || key >= numcells) return;
+    if ((end[key] - start[key] + 1 > 6) != (which == 1)) return;
+    unsigned char *r = aos + i * FSG_AOS_STRIDE;
+    const float4 s = sums[i], s2 = sums2[i];
+    ustf(r, NEWDENS, uldf(r, NEWDENS) + s.x);
+    ustf(r, NDELP_X, uldf(r, NDELP_X) + s.y);
+    ustf(r, NDELP_Y, uldf(r, NDELP_Y) + s.z);
+    ustf(r, NDELP_Z, uldf(r, NDELP_Z) + s.w);
+    ustf(r, DIFFUSION, uldf(r, DIFFUSION) + s2.x);
+    ustf(r, DIFFUSION + 4, uldf(r, DIFFUSION + 4) + s2.y);
+    ustf(r, DIFFUSION + 8, uldf(r, DIFFUSION + 8) + s2.z);
+    ustf(r, DELFLUID, uldf(r, DELFLUID) + s2.w);
+}
+
+static int uni_stage_pairs(fsg_ctx *c, void *d_particles, const int32_t *d_cells, const int32_t *d_start, const int32_t *d_end,
+                           int32_t *d_split, int32_t *d_numsplit, int64_t n, int which)
+{
+    CUU(c, cudaSetDevice(c->device));
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_pair_unidyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
+        cudaFuncSetAttribute(k_pair_unidyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
+        attr_done = true;
+    }
+    int *binlist = c->binlist[0], *nocc = c->counters + 7, *work = c->counters + 2;
+    CUU(c, cudaMemsetAsync(nocc, 0, sizeof(int), c->stream));
+    CUU(c, cudaMemsetAsync(work, 0, sizeof(int), c->stream));
+    k_stage_uni_unpack<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->dev, (const unsigned char *)d_particles, (unsigned char *)d_particles,
+                                                                         d_cells, d_start, d_end, n, c->A, binlist, nocc, which, d_split, d_numsplit);
+    CUU(c, cudaGetLastError());
+    UniArgs a;
+    a.d = c->dev;
+    a.n = (int)n;
+    a.start = d_start;
+    a.end = d_end;
+    a.binlist = binlist;
+    a.nocc = nocc;
+    a.work = work;
+    a.A = c->A;
+    a.sums = c->sums;
+    a.sums2 = c->sums2;
+    a.stats = c->dstats;
+    int64_t blocks = (n + UNI_WARPS - 1) / UNI_WARPS;
+    const int64_t maxb = (int64_t)c->sm_count * 2;
+    if (blocks > maxb) blocks = maxb;
+    k_pair_unidyn<false><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, c->stream>>>(a);
+    CUU(c, cudaGetLastError());
+    k_stage_uni_add_sums<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((unsigned char *)d_particles, d_cells, d_start, d_end, c->sums,
+                                                                           c->sums2, n, c->dev.numcells, which);
+    CUU(c, cudaGetLastError());
+    c->launches += 3;
+    return FSG_OK;
+}
+
+extern "C" int fsg_stage_unidyn_mykernel(fsg_ctx *c, void *d_particles, const int32_t *d_cells, const int32_t *d_start, const int32_t *d_end,
+                                         int32_t *d_split, int32_t *d_numsplit, int64_t n)
+{
+    if (!c || n < 0 || (n > 0 && (!d_particles || !d_cells || !d_start || !d_end || !d_split || !d_numsplit))) return FSG_E_INVALID;
+    int rc = uni_stage_ok(c, n, "fsg_stage_unidyn_mykernel");
+    if (rc != FSG_OK || n == 0) return rc;
+    return uni_stage_pairs(c, d_particles, d_cells, d_start, d_end, d_split, d_numsplit, n, 0);
+}
+extern "C" int fsg_stage_unidyn_mykernel3(fsg_ctx *c, void *d_particles, const int32_t *d_cells, const int32_t *d_start, const int32_t *d_end,
+                                          int64_t n)
+{
+    if (!c || n < 0 || (n > 0 && (!d_particles || !d_cells || !d_start || !d_end))) return FSG_E_INVALID;
+    int rc = uni_stage_ok(c, n, "fsg_stage_unidyn_mykernel3");
+    if (rc != FSG_OK || n == 0) return rc;
+    return uni_stage_pairs(c, d_particles, d_cells, d_start, d_end, nullptr, nullptr, n, 1);
+}
+
+// mykernel2 (cu:451-497) on the records: export of the pre-update state, Particle::update(t), stale cells[], accumulators
+// zeroed, tables / split / numsplit reset.  The new bin id is NOT stored here — that is cell_calc's job (cu:544-551).
+__global__ void __launch_bounds__(256)
+k_stage_uni_mykernel2(FsgDev d, unsigned char *__restrict__ aos, int *__restrict__ cells, int *start_copy, int *start, int *end, int *split,
+                      int *numsplit, int64_t n, int x, float *spts, float *a3, float *b3)
+{
+    using namespace aos_uni;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        unsigned char *r = aos + i * FSG_AOS_STRIDE;
+        const bool bnd = r[BOUNDARY] != 0;
+        const int cellnumber = *reinterpret_cast<const int *>(r + CELL);
+        const float dens0 = uldf(r, DENS);
+        float4 pd = make_float4(uldf(r, POS), uldf(r, POS + 4), uldf(r, POS + 8), bnd ? -dens0 : dens0);
+        const float4 s = make_float4(uldf(r, NEWDENS), uldf(r, NDELP_X), uldf(r, NDELP_Y), uldf(r, NDELP_Z));
+        const float4 s2 = make_float4(uldf(r, DIFFUSION), uldf(r, DIFFUSION + 4), uldf(r, DIFFUSION + 8), uldf(r, DELFLUID));
+        if (cellnumber >= 0 && cellnumber < x) {                                         // cu:459-466 (lb = 0, hb = x)
+            if (spts) { spts[3 * i] = pd.x; spts[3 * i + 1] = pd.y; spts[3 * i + 2] = pd.z; }
+            if (a3) a3[i] = uldf(r, MASS);
+            if (b3) b3[i] = s2.x * s2.x + s2.y * s2.y + s2.z * s2.z;
+        }
+        float4 vp = make_float4(uldf(r, VEL), uldf(r, VEL + 4), uldf(r, VEL + 8), uldf(r, PRESS));
+        float4 af = make_float4(uldf(r, ACC), uldf(r, ACC + 4), uldf(r, ACC + 8), 0.f);
+        float4 dpi = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 mx = make_float4(uldf(r, SOLID), uldf(r, FLUID), 0.f, 0.f);
+        int key;
+        unidyn_particle_update(d, pd, vp, af, dpi, mx, s, s2, key);                      // cu:469
+        ustf(r, POS, pd.x); ustf(r, POS + 4, pd.y); ustf(r, POS + 8, pd.z);
+        ustf(r, VEL, vp.x); ustf(r, VEL + 4, vp.y); ustf(r, VEL + 8, vp.z);
+        ustf(r, ACC, af.x); ustf(r, ACC + 4, af.y); ustf(r, ACC + 8, af.z);
+        ustf(r, DENS, fabsf(pd.w));
+        ustf(r, PRESS, vp.w);
+        ustf(r, DELP_X, dpi.x); ustf(r, DELP_Y, dpi.y); ustf(r, DELP_Z, dpi.z);
+        ustf(r, SOLID, mx.x);
+        ustf(r, FLUID, mx.y);
+        for (int q = 0; q < 9; q++) ustf(r, 256 + 4 * q, (float)(d.dt * (double)uldf(r, 220 + 4 * q)));   // stress_tensor = DT * stress_rate, cuh:304-308
+        r[FLAG] = 1;                                                                     // cuh:422
+        cells[i] = cellnumber;                                                           // cu:474 (stale; cell_calc follows)
+        ustf(r, NEWDENS, 0.f); ustf(r, NDELP_X, 0.f); ustf(r, NDELP_Y, 0.f); ustf(r, NDELP_Z, 0.f);      // cu:475-478
+        for (int o = 124; o < 184; o += 4) ustf(r, o, 0.f);                              // drift velocities, vel_grad  cu:479,481
+        for (int o = 292; o < 316; o += 4) ustf(r, o, 0.f);                              // stress_accel, mixture_accel  cu:480,482
+        ustf(r, DELSOLID, 0.f); ustf(r, DELFLUID, 0.f);                                  // cu:483
+        ustf(r, DIFFUSION, 0.f); ustf(r, DIFFUSION + 4, 0.f); ustf(r, DIFFUSION + 8, 0.f);
+    }
+    if (i < x) { start[i] = -1; start_copy[i] = -1; end[i] = -1; split[i] = -1; }        // cu:486-491
+    if (i == 0) numsplit[0] = 0;                                                         // cu:493
+}
+extern "C" int fsg_stage_unidyn_mykernel2(fsg_ctx *c, void *d_particles, int32_t *d_cells, int32_t *d_start_copy, int32_t *d_start, int32_t *d_end,
+                                          int32_t *d_split, int32_t *d_numsplit, int64_t n, int32_t x, int32_t t, float *spts, float *a3, float *b3)
+{
+    (void)t;      // Particle::update(int t) never reads t (its Runge-Kutta branch is commented out, cuh:361-387)
+    if (!c || n < 0 || x < 0 || !d_start_copy || !d_start || !d_end || !d_split || !d_numsplit || (n > 0 && (!d_particles || !d_cells)))
+        return FSG_E_INVALID;
+    int rc = uni_stage_ok(c, n, "fsg_stage_unidyn_mykernel2");
+    if (rc != FSG_OK) return rc;
+    CUU(c, cudaSetDevice(c->device));
+    const int64_t threads = n > x ? n : x;
+    if (threads == 0) return FSG_OK;
+    k_stage_uni_mykernel2<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->dev, (unsigned char *)d_particles, d_cells, d_start_copy,
+                                                                                  d_start, d_end, d_split, d_numsplit, n, x, spts, a3, b3);
+    CUU(c, cudaGetLastError());
+    c->launches++;
+    return FSG_OK;
+}
+
+// cell_calc, cu:544-551
+__global__ void k_stage_uni_cell_calc(FsgDev d, unsigned char *__restrict__ aos, int *__restrict__ cells, int64_t n)
+{
+    using namespace aos_uni;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned char *r = aos + i * FSG_AOS_STRIDE;
+    const int key = bin_id(d, uldf(r, POS), uldf(r, POS + 4), uldf(r, POS + 8));
+    *reinterpret_cast<int *>(r + CELL) = key;
+    cells[i] = key;
+}
+extern "C" int fsg_stage_unidyn_cell_calc(fsg_ctx *c, void *d_particles, int32_t *d_cells, int64_t n)
+{
+    if (!c || n < 0 || (n > 0 && (!d_particles || !d_cells))) return FSG_E_INVALID;
+    int rc = uni_stage_ok(c, n, "fsg_stage_unidyn_cell_calc");
+    if (rc != FSG_OK || n == 0) return rc;
+    CUU(c, cudaSetDevice(c->device));
+    k_stage_uni_cell_calc<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->dev, (unsigned char *)d_particles, d_cells, n);
+    CUU(c, cudaGetLastError());
+    c->launches++;
+    return FSG_OK;
 }

@@ -246,6 +246,32 @@ FSG_API int  fsg_stage_mykernel(fsg_ctx *ctx, void *d_particles, const int32_t *
 FSG_API int  fsg_stage_mykernel2(fsg_ctx *ctx, void *d_particles, int32_t *d_cells, int32_t *d_start, int32_t *d_end,
                          int64_t n, float *spts, float *a3, float *b3);
 
+
+/* unidyn model (context created with FSG_MODEL_UNIDYN): the launches of the single-device loop solver-unidyn.cu:341-548
+ * on the reference's own buffers (340-byte unidyn Particle records).  Same scope as the context API: every non-boundary
+ * particle pure fluid with mass 1; the caller's thrust sorts (:331, :378) stay where they are
+ * (fsg_stage_sort does the first one for either model). */
+/* replaces count_after_merge<<<NUMCELLS,1024>>>(v_d, d_particleindex, dsz, newsize)   solver-unidyn.cu:341, FluidGPU-unidyn.cuh:544 */
+FSG_API int  fsg_stage_unidyn_count_after_merge(fsg_ctx *ctx, const int32_t *d_cells, int64_t n, int32_t *d_newsize);
+/* replaces findneighbours<<<NUMCELLS,1024>>>(v_d, d_start, d_start_copy, d_end, dsz, x)   solver-unidyn.cu:354, FluidGPU-unidyn.cuh:537 */
+FSG_API int  fsg_stage_unidyn_findneighbours(fsg_ctx *ctx, const int32_t *d_cells, int32_t *d_start, int32_t *d_start_copy,
+                                             int32_t *d_end, int64_t n, int32_t x);
+/* replaces mykernel<<<NUMCELLS,1024>>>(d_SPptr, pidx, v_d, d_start, d_end, d_split, dsz, x, dev, buffer, d_numsplit)
+ * solver-unidyn.cu:363, FluidGPU-unidyn.cuh:538: split marking + subindex + pair sums of the unsplit bins */
+FSG_API int  fsg_stage_unidyn_mykernel(fsg_ctx *ctx, void *d_particles, const int32_t *d_cells, const int32_t *d_start,
+                                       const int32_t *d_end, int32_t *d_split, int32_t *d_numsplit, int64_t n);
+/* replaces mykernel3<<<numsplit*8,1024>>>(same arguments)   solver-unidyn.cu:379, FluidGPU-unidyn.cuh:539: pair sums of the
+ * split bins (each particle sees the 8 bins of its octant); d_split is not needed (bins with more than 6 particles) */
+FSG_API int  fsg_stage_unidyn_mykernel3(fsg_ctx *ctx, void *d_particles, const int32_t *d_cells, const int32_t *d_start,
+                                        const int32_t *d_end, int64_t n);
+/* replaces mykernel2<<<NUMCELLS,1024>>>(d_SPptr, pidx, v_d, d_start_copy, d_start, d_end, d_split, d_numsplit, dsz, x, dev,
+ * buffer, t, spts, a3, b3)   solver-unidyn.cu:389, FluidGPU-unidyn.cuh:540 */
+FSG_API int  fsg_stage_unidyn_mykernel2(fsg_ctx *ctx, void *d_particles, int32_t *d_cells, int32_t *d_start_copy, int32_t *d_start,
+                                        int32_t *d_end, int32_t *d_split, int32_t *d_numsplit, int64_t n, int32_t x, int32_t t,
+                                        float *spts, float *a3, float *b3);
+/* replaces cell_calc<<<NUMCELLS,1024>>>(d_SPptr, pidx, v_d, dsz, dev)   solver-unidyn.cu:548, FluidGPU-unidyn.cuh:543 */
+FSG_API int  fsg_stage_unidyn_cell_calc(fsg_ctx *ctx, void *d_particles, int32_t *d_cells, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -616,6 +616,37 @@ def test_reference_style_driver_links_and_runs_against_libfsg(fsg, tmp_path):
             assert err <= bound, (k, f, err, bound)
 
 
+@pytest.mark.parametrize("name,steps", [("config2", (1, 2, 10)), ("unidyn_random", (1, 2, 3))])
+def test_reference_style_unidyn_driver_links_and_runs_against_libfsg(fsg, tmp_path, name, steps):
+    """oracle/_ref/compat_harness_unidyn = oracle/ref_harness_unidyn.cu (includes FluidGPU-unidyn.cuh, mirrors the single-device loop
+    of solver-unidyn.cu:313-573: count_after_merge / findneighbours / mykernel / mykernel3 / mykernel2 / cell_calc launched with
+    <<<>>>) linked with fsg_compat_unidyn.o + libfsg.so INSTEAD of the reference's FluidGPU-unidyn.o.  Its dumps must match the dumps
+    the same harness produced with the reference's own kernels (tests/golden/ref_config2_*, ref_unidyn_random_*)."""
+    import subprocess
+    from fluidsolvergpu_b200 import sections
+    exe = GOLD.parents[1] / "oracle" / "_ref" / "compat_harness_unidyn"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/compat_harness_unidyn is built where the reference headers are available")
+    scene = fsg.scenes.unidyn_default_scene() if name == "config2" else fsg.scenes.random_unidyn_scene(6000, 5)
+    inp, prefix = tmp_path / "in.bin", tmp_path / "compat"
+    sections.write_sections(inp, {k: scene[k] for k in ("pos", "vel", "acc", "dens", "press", "newdens", "index", "boundary", "solid", "fluid")})
+    out = subprocess.check_output([str(exe), "--in", str(inp), "--steps", str(max(steps)), "--dump", ",".join(map(str, steps)),
+                                   "--out", str(prefix)], timeout=180).decode()
+    assert '"impl"' in out
+    for k in steps:
+        got = sections.read_sections(f"{prefix}_step{k}.bin")
+        ref = dict(np.load(GOLD / f"ref_{name}_step{k}.npz"))
+        n = len(ref["index"])
+        if k == 1:
+            for f in ("cells_sorted", "start", "end", "split", "index", "cell", "subindex", "spts", "a3"):
+                assert np.array_equal(got[f], ref[f]), f
+            assert rel_l2(got["b3"], ref["b3"]) <= TOL
+        o, r = np.argsort(got["index"], kind="stable"), np.argsort(ref["index"], kind="stable")
+        for f in UFIELDS + ("diffusion",):
+            err = rel_l2(got[f].reshape(n, -1)[o], ref[f].reshape(n, -1)[r])
+            assert err <= 1e-5, (k, f, err)
+
+
 def test_slab_raw_round_trip_through_host_memory(fsg):
     """The end-to-end path of a slab context: download every slot, upload it again (fsg_slab_keep_foreign), go on.
     Must be bit-identical to a run that never left the device — including particles that had crossed a face and were

@@ -1,3 +1,2 @@
-N=${N:-2}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 10 --warmup 3 --e2e-steps 1 > gpurun_out/bench512_n${N}_v3.json 2> gpurun_out/bench512_n${N}_v3.err; echo "rc=$?"
-tail -2 gpurun_out/bench512_n${N}_v3.err; grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench512_n${N}_v3.json | head -2
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
