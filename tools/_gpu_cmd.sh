@@ -1,6 +1,7 @@
-O=gpurun_out
-timeout 900 python bench.py > $O/bench512_r1final.json 2> $O/bench512_r1final.err; echo "bench512 rc=$?"; tail -2 $O/bench512_r1final.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/benchref_r1final.json 2> $O/benchref_r1final.err; echo "benchref rc=$?"; cat $O/benchref_r1final.json | cut -c1-400
-CMD="python bench.py --grid 256 --steps 2 --warmup 3 --no-cpu --e2e-steps 1"
-$CMD > $O/plain_r1final.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_r1final.csv $CMD > $O/ncu_list_r1final.log 2>&1
-echo "ncu list rc=$?"
+N=${N:-2}; G=${G:-512}
+if [ "$N" = "1" ]; then
+timeout 900 python bench.py --grid $G --steps 10 --warmup 3 --e2e-steps 1 --no-cpu > gpurun_out/bench${G}_n${N}_v3.json 2> gpurun_out/bench${G}_n${N}_v3.err; echo "rc=$?"
+else
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --grid $G --steps 10 --warmup 3 --e2e-steps 1 > gpurun_out/bench${G}_n${N}_v3.json 2> gpurun_out/bench${G}_n${N}_v3.err; echo "rc=$?"
+fi
+tail -2 gpurun_out/bench${G}_n${N}_v3.err; grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench${G}_n${N}_v3.json | head -2
