@@ -221,6 +221,7 @@ k_pair_v3(V3Args va)
     int rs = 0, rp = 0, excl = 0;                             // lane r < 5: run r of the current bin (first slot, length, prefix)
     int C = 0, hn = 0, hs0 = 0, hnlim = 0, ig = 0, t0 = 0;
     bool have = false;
+    const int ghost_below = d.x0 * d.G2;                      // bins with a smaller id lie in the ghost layer x0 - 1
     // run r of home bin b: lane 0 -> bins [b, b+1]; lane 1 -> [b+G-1, b+G+1]; lanes 2..4 -> the three runs of layer ix+1
     auto prefetch = [&](int b) {
         pf_s0 = pf_s1 = pf_s2 = pf_e0 = pf_e1 = pf_e2 = -1;
@@ -254,7 +255,7 @@ k_pair_v3(V3Args va)
                 }
                 hs0 = __shfl_sync(FULL, pf_s1, 0);
                 hn = __shfl_sync(FULL, pf_e1, 0) - hs0 + 1;
-                const bool ghost = b / d.G2 < d.x0;             // ghost layer below the slab: only its pairs with layer x0
+                const bool ghost = b < ghost_below;             // ghost layer below the slab: only its pairs with layer x0
                 if (ghost && lane < 2) rp = 0;
                 hnlim = ghost ? 0 : hn;
                 grab++;
