@@ -75,6 +75,7 @@ SIGNATURES = {
     "fsg_slab_check": (C.c_int, [P, C.POINTER(C.c_int64 * 9)]),
     "fsg_slab_keep_foreign": (C.c_int, [P, C.c_int]),
     "fsg_slab_message_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "fsg_slab_message_bytes_model": (C.c_int64, [C.c_int, C.c_int64, C.c_int64]),
     "fsg_slab_alloc_messages": (C.c_int, [P, C.c_int64, C.c_int64]),
     "fsg_slab_inbox_handle": (C.c_int, [P, C.c_int, C.c_int, P]),
     "fsg_slab_open_peer": (C.c_int, [P, C.c_int, C.c_int, P]),

@@ -244,10 +244,6 @@ extern "C" int fsg_create(const fsg_config *cfg, fsg_ctx **out)
                        "and a one-layer ghost band, i.e. cellsize >= 2h";
         return FSG_E_UNSUPPORTED;
     }
-    if (cfg->model == FSG_MODEL_UNIDYN && cfg->world > 1) {
-        g_create_err = "fsg_create: slab decomposition is implemented for the base model only";
-        return FSG_E_UNSUPPORTED;
-    }
     int ndev = fsg_device_count();
     if (ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
         g_create_err = "fsg_create: no usable CUDA device (libfsg has no CPU path)";

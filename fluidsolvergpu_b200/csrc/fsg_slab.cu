@@ -80,30 +80,35 @@ k_slab_count(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ k
 
 // Fixed-layout message (device memory), the same size on every rank so that nothing on the host depends
 // on how many particles cross a face this step:
-//   [header 64 B: int64 m, int64 g][posd cap_m][velp cap_m][accf cap_m][dpi cap_m][posd cap_g][velp cap_g][tail 64 B: int64 stamp]
+//   [header 64 B: int64 m, int64 g][posd cap_m][velp cap_m][accf cap_m][dpi cap_m]{mix cap_m}[posd cap_g][velp cap_g]{mix cap_g}[tail 64 B: int64 stamp]
+// ({..}: unidyn model only — the volume fractions, FluidGPU-unidyn.cuh:180-181, which the pair terms of a neighbour read).
 // The stamp (exchange sequence number) is copied AFTER the rest of the message, so a receiver that sees it
 // has the whole message.
 struct SlabMsg {
     long long *hdr;
-    float4 *m_posd, *m_velp, *m_accf, *m_dpi, *g_posd, *g_velp;
+    float4 *m_posd, *m_velp, *m_accf, *m_dpi, *m_mix, *g_posd, *g_velp, *g_mix;
 };
-__host__ __device__ inline SlabMsg slab_msg(void *base, int64_t cap_m, int64_t cap_g)
+__host__ __device__ inline int64_t slab_body_float4(bool mix, int64_t cap_m, int64_t cap_g) { return (mix ? 5 : 4) * cap_m + (mix ? 3 : 2) * cap_g; }
+__host__ __device__ inline SlabMsg slab_msg(void *base, int64_t cap_m, int64_t cap_g, bool mix)
 {
     SlabMsg r;
     r.hdr = (long long *)base;
     float4 *p = (float4 *)((char *)base + 64);
     r.m_posd = p; r.m_velp = p + cap_m; r.m_accf = p + 2 * cap_m; r.m_dpi = p + 3 * cap_m;
-    r.g_posd = p + 4 * cap_m; r.g_velp = p + 4 * cap_m + cap_g;
+    r.m_mix = mix ? p + 4 * cap_m : nullptr;
+    float4 *g = p + (mix ? 5 : 4) * cap_m;
+    r.g_posd = g; r.g_velp = g + cap_g;
+    r.g_mix = mix ? g + 2 * cap_g : nullptr;
     return r;
 }
 
 // off = exclusive scan of cnt (length 4*nw + 1): totals of the four categories -> message headers (clamped to
 // the message capacities; an overflow is flagged, the excess is not sent) and the diagnostics array
 __global__ void k_slab_headers(const int *__restrict__ off, int64_t nw, void *to_left, void *to_right, int64_t cap_m, int64_t cap_g,
-                               int *overflow, long long *diag, long long stamp)
+                               int *overflow, long long *diag, long long stamp, bool mix)
 {
     if (threadIdx.x != 0) return;
-    const int64_t tail = (64 + (4 * cap_m + 2 * cap_g) * 16) / 8;
+    const int64_t tail = (64 + slab_body_float4(mix, cap_m, cap_g) * 16) / 8;
     if (to_left) ((long long *)to_left)[tail] = stamp;
     if (to_right) ((long long *)to_right)[tail] = stamp;
     long long t[4];
@@ -131,23 +136,33 @@ k_slab_scatter(FsgDev d, int rank, int world, int64_t n, const int *__restrict__
         pos[k] = (w < nw ? off[k * nw + w] - off[k * nw] : 0) + __popc(m & lt);
     }
     if (!c) return;
-    float4 pd = B.posd[i], vp = B.velp[i];
+    const bool mix = B.mix != nullptr;
+    float4 pd = B.posd[i], vp = B.velp[i], mx = mix ? B.mix[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     if (c & 5) {
         // migrant: full state goes to the neighbour.  The slot is NOT freed here: a particle moves less
         // than one bin per step, so it lands in the neighbour's outermost layer, where this slab still
         // needs it as a candidate for one more step.  Its bin is outside [x0, x1), so it is treated as
         // a ghost (never a home particle) and k_update drops it.
-        SlabMsg M = slab_msg((c & 1) ? to_left : to_right, cap_m, cap_g);
+        SlabMsg M = slab_msg((c & 1) ? to_left : to_right, cap_m, cap_g, mix);
         int q = (c & 1) ? pos[0] : pos[2];
         if (q < cap_m) {
             M.m_posd[q] = pd;
             M.m_velp[q] = vp;
             M.m_accf[q] = B.accf[i];
             M.m_dpi[q] = B.dpi[i];
+            if (mix) M.m_mix[q] = mx;
         }
     }
-    if ((c & 2) && pos[1] < cap_g) { SlabMsg M = slab_msg(to_left, cap_m, cap_g); M.g_posd[pos[1]] = pd; M.g_velp[pos[1]] = vp; }
-    if ((c & 8) && pos[3] < cap_g) { SlabMsg M = slab_msg(to_right, cap_m, cap_g); M.g_posd[pos[3]] = pd; M.g_velp[pos[3]] = vp; }
+    if ((c & 2) && pos[1] < cap_g) {
+        SlabMsg M = slab_msg(to_left, cap_m, cap_g, mix);
+        M.g_posd[pos[1]] = pd; M.g_velp[pos[1]] = vp;
+        if (mix) M.g_mix[pos[1]] = mx;
+    }
+    if ((c & 8) && pos[3] < cap_g) {
+        SlabMsg M = slab_msg(to_right, cap_m, cap_g, mix);
+        M.g_posd[pos[3]] = pd; M.g_velp[pos[3]] = vp;
+        if (mix) M.g_mix[pos[3]] = mx;
+    }
 }
 
 // Appends both received messages behind the slots in use (*n_used, a device-side count: nothing here needs
@@ -166,13 +181,15 @@ k_slab_unpack(FsgDev d, const void *from_left, const void *from_right, int64_t c
     const long long nl = from_left ? hl[0] + hl[1] : 0;
     if (t == 0) { diag[4] = from_left ? hl[0] : 0; diag[5] = from_left ? hl[1] : 0; diag[6] = from_right ? hr[0] : 0; diag[7] = from_right ? hr[1] : 0; }
     if (!msg) return;
-    SlabMsg M = slab_msg(const_cast<void *>(msg), cap_m, cap_g);
+    const bool mix = B.mix != nullptr;
+    SlabMsg M = slab_msg(const_cast<void *>(msg), cap_m, cap_g, mix);
     const long long m = M.hdr[0], g = M.hdr[1];
     int64_t u = t - (side ? per : 0);
     if (u >= m + g) return;
     int64_t i = (int64_t)*n_used + (side ? nl : 0) + u;
     if (i >= cap) { atomicOr(overflow, 2); return; }
     float4 pd, vp, af, dp;
+    if (mix) B.mix[i] = u < m ? M.m_mix[u] : M.g_mix[u - m];
     if (u < m) { pd = M.m_posd[u]; vp = M.m_velp[u]; af = M.m_accf[u]; dp = M.m_dpi[u]; }
     else {
         pd = M.g_posd[u - m]; vp = M.g_velp[u - m];
@@ -195,7 +212,12 @@ k_slab_unpack(FsgDev d, const void *from_left, const void *from_right, int64_t c
         }                                                                                               \
     } while (0)
 
-extern "C" int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g) { return 64 + (4 * cap_m + 2 * cap_g) * (int64_t)sizeof(float4) + 64; }
+extern "C" int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g) { return 64 + slab_body_float4(false, cap_m, cap_g) * (int64_t)sizeof(float4) + 64; }
+extern "C" int64_t fsg_slab_message_bytes_model(int model, int64_t cap_m, int64_t cap_g)
+{
+    return 64 + slab_body_float4(model == FSG_MODEL_UNIDYN, cap_m, cap_g) * (int64_t)sizeof(float4) + 64;
+}
+static size_t slab_bytes(const fsg_ctx *c, int64_t cap_m, int64_t cap_g) { return (size_t)fsg_slab_message_bytes_model(c->cfg.model, cap_m, cap_g); }
 
 // Waits (on the device) until both neighbours' messages number `expected` have landed in this rank's inboxes:
 // the stamp is the last thing a sender copies.  One thread, bounded: a missing neighbour raises flag 4.
@@ -239,7 +261,7 @@ static int slab_pack_on(fsg_ctx *c, void *d_to_left, void *d_to_right, int64_t c
     CUS(c, cudaGetLastError());
     CUS(c, fsg_scan_exclusive(c->scan_tmp, c->scan_tmp_bytes, cnt, off, 4 * nw + 1, st));
     k_slab_headers<<<1, 32, 0, st>>>(off, nw, c->cfg.rank > 0 ? d_to_left : nullptr, c->cfg.rank < c->cfg.world - 1 ? d_to_right : nullptr,
-                                     cap_m, cap_g, c->counters + 9, diag, stamp);
+                                     cap_m, cap_g, c->counters + 9, diag, stamp, c->B.mix != nullptr);
     CUS(c, cudaGetLastError());
     k_slab_scatter<<<blocks, 256, 0, st>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, region, c->B, off, nw, d_to_left, d_to_right,
                                            cap_m, cap_g);
@@ -326,7 +348,7 @@ extern "C" int fsg_slab_alloc_messages(fsg_ctx *c, int64_t cap_m, int64_t cap_g)
     CUS(c, cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 2; k++) { cudaFree(c->outbox[k]); c->outbox[k] = nullptr; }
     for (int k = 0; k < 4; k++) { cudaFree(c->inbox[k]); c->inbox[k] = nullptr; }
-    const size_t bytes = (size_t)fsg_slab_message_bytes(cap_m, cap_g);
+    const size_t bytes = slab_bytes(c, cap_m, cap_g);
     for (int k = 0; k < 2; k++) { CUS(c, cudaMalloc(&c->outbox[k], bytes)); CUS(c, cudaMemsetAsync(c->outbox[k], 0, bytes, c->stream)); }
     for (int k = 0; k < 4; k++) { CUS(c, cudaMalloc(&c->inbox[k], bytes)); CUS(c, cudaMemsetAsync(c->inbox[k], 0, bytes, c->stream)); }
     CUS(c, cudaStreamSynchronize(c->stream));
@@ -374,7 +396,7 @@ static int slab_send_on(fsg_ctx *c, const int *region, cudaStream_t st)
     }
     int rc = slab_pack_on(c, c->outbox[0], c->outbox[1], c->msg_cap_m, c->msg_cap_g, region, seq, st);
     if (rc != FSG_OK) return rc;
-    const size_t bytes = (size_t)fsg_slab_message_bytes(c->msg_cap_m, c->msg_cap_g), body = bytes - 64;
+    const size_t bytes = slab_bytes(c, c->msg_cap_m, c->msg_cap_g), body = bytes - 64;
     for (int side = 0; side < 2; side++) {
         if (side == 0 ? !left : !right) continue;
         char *dst = (char *)c->peer_inbox[2 * side + par], *src = (char *)c->outbox[side];
@@ -414,7 +436,7 @@ extern "C" int fsg_slab_unpack_recv(fsg_ctx *c)
     const int par = (int)(seq & 1);
     const bool left = c->cfg.rank > 0, right = c->cfg.rank < c->cfg.world - 1;
     if (c->overlap) CUS(c, cudaStreamWaitEvent(c->stream, c->ev_sent, 0));   // my own pack (other stream) reads the slots unpack writes
-    const size_t tail = ((size_t)fsg_slab_message_bytes(c->msg_cap_m, c->msg_cap_g) - 64);
+    const size_t tail = (slab_bytes(c, c->msg_cap_m, c->msg_cap_g) - 64);
     k_slab_wait<<<1, 32, 0, c->stream>>>(left ? (const long long *)((char *)c->inbox[par] + tail) : nullptr,
                                          right ? (const long long *)((char *)c->inbox[2 + par] + tail) : nullptr, seq, c->counters + 9);
     CUS(c, cudaGetLastError());
@@ -444,6 +466,7 @@ extern "C" int fsg_slab_set_overlap(fsg_ctx *c, int on)
     if (!c) return FSG_E_INVALID;
     if (c->cfg.world <= 1) { c->err = "fsg_slab_set_overlap: not a slab context (world == 1)"; return FSG_E_STATE; }
     if (on && !c->outbox[0]) { c->err = "fsg_slab_set_overlap: needs the peer-memory exchange (fsg_slab_alloc_messages)"; return FSG_E_STATE; }
+    if (on && c->cfg.model != FSG_MODEL_BASE) { c->err = "fsg_slab_set_overlap: base model only"; return FSG_E_UNSUPPORTED; }
     CUS(c, cudaSetDevice(c->device));
     CUS(c, cudaStreamSynchronize(c->stream));
     if (on && !c->comm) {

@@ -286,7 +286,8 @@ __device__ __forceinline__ void unidyn_particle_update(const FsgDev &d, float4 &
 
 __global__ void __launch_bounds__(256)
 k_update_unidyn(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B, int *__restrict__ keysB,
-                const float4 *__restrict__ sums, const float4 *__restrict__ sums2, const float4 *__restrict__ carry, float *__restrict__ vizb)
+                const float4 *__restrict__ sums, const float4 *__restrict__ sums2, const float4 *__restrict__ carry, float *__restrict__ vizb,
+                int *violation)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -294,10 +295,18 @@ k_update_unidyn(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgS
     int key = keysA[i];
     float b3 = 0.f;
     if (key < d.numcells) {
+        const int ix = key / d.G2;
+        if (ix < d.x0 || ix >= d.x1) {      // slab contexts: ghost copy of a neighbour slab's particle — drop it
+            keysB[i] = d.dead;
+            vizb[i] = 0.f;
+            return;
+        }
         float4 s = sums[i], s2 = sums2[i];
         if (carry) { float4 cy = carry[i]; s.x += cy.x; s.y += cy.y; s.z += cy.z; s.w += cy.w; }
         b3 = s2.x * s2.x + s2.y * s2.y + s2.z * s2.z;                         // cu:466
         unidyn_particle_update(d, pd, vp, af, dpi, mx, s, s2, key);
+        // the one-layer ghost band assumes less than one bin layer per step
+        if (violation && key < d.numcells && abs(key / d.G2 - ix) > 1) atomicOr(violation, 1);
     }
     B.posd[i] = pd;
     B.velp[i] = vp;
@@ -347,7 +356,7 @@ cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, c
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_update_unidyn<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->dev, (int)n, c->keysA, c->A, c->B, c->keysB, c->sums, c->sums2, carry,
-                                                              c->vizb);
+                                                              c->vizb, c->cfg.world > 1 ? c->counters + 6 : nullptr);
     *launches += 2;
     return cudaGetLastError();
 }

@@ -110,9 +110,11 @@ def slab_config(base: FsgConfig, rank: int, world: int, cuts, capacity: int, dev
     return cfg
 
 
-def message_bytes(cap_m: int, cap_g: int) -> int:
-    """Bytes of one slab message with room for cap_m migrants and cap_g ghosts (fsg_slab_message_bytes)."""
-    return 64 + (4 * cap_m + 2 * cap_g) * 16 + 64
+def message_bytes(cap_m: int, cap_g: int, model: int = 0) -> int:
+    """Bytes of one slab message with room for cap_m migrants and cap_g ghosts (fsg_slab_message_bytes_model): the unidyn
+    model (1) also carries the volume fractions."""
+    mix = model == 1
+    return 64 + ((5 if mix else 4) * cap_m + (3 if mix else 2) * cap_g) * 16 + 64
 
 
 def message_caps(hist, cuts, slack: float = 1.2, floor: int = 4096) -> tuple[int, int]:
@@ -173,7 +175,7 @@ class SlabSolver(FluidSolver):
         self.exchange = exchange
         self.tdev = torch.device("cuda", cfg.device)
         self.cap_m, self.cap_g = int(cap_m), int(cap_g)
-        self.msg_bytes = message_bytes(self.cap_m, self.cap_g)
+        self.msg_bytes = message_bytes(self.cap_m, self.cap_g, cfg.model)
         with torch.cuda.device(self.tdev):
             self.to_left, self.to_right, self.from_left, self.from_right = (
                 torch.zeros(self.msg_bytes, dtype=torch.uint8, device=self.tdev) for _ in range(4))

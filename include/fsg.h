@@ -214,7 +214,9 @@ FSG_API int  fsg_slab_check(fsg_ctx *ctx, int64_t info[9]);
  * 1 the upload returns what fsg_download_soa gave — all `capacity` slots, `cell` == grid^3 + 1 marking the empty ones —
  * and nothing is filtered by position (particles that have just crossed a face migrate at the next pack). */
 FSG_API int  fsg_slab_keep_foreign(fsg_ctx *ctx, int on);
-FSG_API int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g);
+FSG_API int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g);                 /* base model */
+/* unidyn messages also carry the volume fractions (16 bytes more per migrant and per ghost) */
+FSG_API int64_t fsg_slab_message_bytes_model(int model, int64_t cap_m, int64_t cap_g);
 /* Peer-memory variant (one process per GPU on one node): the library owns the message buffers, the
  * neighbours' inboxes are mapped through CUDA IPC and fsg_slab_pack_send copies the packed messages straight
  * into them over NVLink (copy engines).  The caller exchanges the 64-byte handles once

@@ -559,6 +559,47 @@ def test_unidyn_random_scenes(fsg, seed, n, bf):
             unidyn_resync_step(fsg, s)
 
 
+@pytest.mark.parametrize("mode", ["messages", "peer"])
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("fast", [False, True])
+def test_unidyn_slabs_match_single_device(fsg, world, mode, fast):
+    """The N-slab hand-off for the model the reference wrote it for (solver-unidyn.cu:396-470): W x-slabs of the unidyn model with
+    migration + one-layer ghost exchange (messages carry the volume fractions too) against ONE context on the same scene,
+    resynchronised every step: positions and every integer result bit-exact, everything that depends on the pair sums within 1e-5."""
+    if fast:      # a common drift carries particles across the slab faces (no boundary particles: fluid streaming past them at
+        #           speed blows up under the boundary viscosity, FluidGPU-unidyn.cu:307, and leaves the one-layer ghost band)
+        state = fsg.scenes.random_unidyn_scene(6000, 11, boundary_frac=0.0)
+        state["vel"][:, 0] += np.float32(4.0)
+    else:
+        state = fsg.scenes.random_unidyn_scene(6000, 12, boundary_frac=0.1)
+    n = state["pos"].shape[0]
+    cfg = fsg.FluidSolver.unidyn_config(capacity=n)
+    cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), world)
+    moved = 0
+    with fsg.SlabGroup(cfg, world, cuts, capacity=2 * n + 64, peer=mode == "peer") as g, fsg.FluidSolver(cfg) as s:
+        g.upload(state)
+        for k in range(6 if fast else 3):
+            cur = fsg.by_index(g.download())
+            assert cur["index"].shape[0] == n and np.array_equal(cur["index"], np.arange(n)), "particles lost or duplicated"
+            s.upload({f: cur[f] for f in cur if f != "cell"})
+            g.step(1)
+            s.step(1)
+            moved += sum(c["sent"][0] + c["sent"][2] for c in g.check())
+            a, b = fsg.by_index(g.download()), fsg.by_index(s.download())
+            assert np.array_equal(a["index"], b["index"])
+            for f in ("pos", "cell", "boundary"):
+                assert np.array_equal(a[f], b[f]), (f, k)
+            for f in ("vel", "acc", "dens", "press", "delpress", "fluid", "solid"):
+                err = rel_l2(a[f], b[f])
+                assert err <= TOL, (f, k, err)
+        for r, sl in enumerate(g.slabs):
+            own = sl.download()
+            ix = own["cell"][own["cell"] < cfg.grid ** 3] // (cfg.grid ** 2)
+            assert ix.size == 0 or (ix.min() >= cuts[r][0] - 1 and ix.max() <= cuts[r][1])
+    if fast:
+        assert moved > 0, "the scene was meant to exercise migration"
+
+
 def test_unidyn_aos_and_scope(fsg):
     import aos
     state = fsg.scenes.random_unidyn_scene(1500, 9)

@@ -33,6 +33,9 @@ def test_plume_layer_hist_matches_scene(fsg):
     assert hist.sum() == state["pos"].shape[0]
     assert np.array_equal(hist, fsg.slab.layer_hist_from_positions(cfg, state["pos"]))
     assert fsg.slab.message_bytes(3, 5) == fsg._lib.load().fsg_slab_message_bytes(3, 5) == 64 + (4 * 3 + 2 * 5) * 16 + 64
+    # unidyn messages carry the volume fractions too
+    assert fsg.slab.message_bytes(3, 5, 1) == fsg._lib.load().fsg_slab_message_bytes_model(1, 3, 5) == 64 + (5 * 3 + 3 * 5) * 16 + 64
+    assert fsg._lib.load().fsg_slab_message_bytes_model(0, 3, 5) == fsg.slab.message_bytes(3, 5)
     cap_m, cap_g = fsg.slab.message_caps(hist, fsg.slab_cuts(hist, 3))
     assert cap_g >= hist.max() and cap_m >= 4096
 
