@@ -195,8 +195,9 @@ __device__ __forceinline__ void v3_batch(const float4 *__restrict__ hp, const fl
     }
 }
 
+// (the variant that evaluates the boundary factors needs a few more registers: one resident block less instead of spills)
 template <bool HASB>
-__global__ void __launch_bounds__(V3_WARPS * 32, V3_BPS)
+__global__ void __launch_bounds__(V3_WARPS * 32, HASB ? V3_BPS - 1 : V3_BPS)
 k_pair_v3(V3Args va)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -436,7 +437,7 @@ cudaError_t fsg_launch_pair_v3(const PairArgs &a, float4 *sums, bool has_boundar
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float4) * (size_t)a.n, s);
     if (e != cudaSuccess) return e;
     int64_t blocks = ((int64_t)a.n + V3_WARPS - 1) / V3_WARPS;      // upper bound on useful warps: one per occupied bin
-    int64_t maxb = (int64_t)sm_count * V3_BPS;
+    int64_t maxb = (int64_t)sm_count * (has_boundary ? V3_BPS - 1 : V3_BPS);
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
     if (has_boundary) k_pair_v3<true><<<(unsigned)blocks, V3_WARPS * 32, smem, s>>>(va);

@@ -1,6 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
-timeout 300 python bench.py --no-cpu > gpurun_out/bench512_e2e2.json 2> gpurun_out/bench512_e2e2.err; echo "rc=$?"; tail -2 gpurun_out/bench512_e2e2.err
-python - <<'PY'
-import json
-j=json.load(open("gpurun_out/bench512_e2e2.json")); print(j["ms_per_step"], j["e2e"])
-PY
+timeout 900 python tools/ref_gpu_compare.py > gpurun_out/ref_gpu_compare2.json 2> gpurun_out/ref_gpu_compare2.err; echo "rc=$?"; tail -3 gpurun_out/ref_gpu_compare2.err; python -c "
+import json; j=json.load(open('gpurun_out/ref_gpu_compare2.json'))
+for k,v in j.items(): print(k, v.get('libfsg_ms_per_step'), v.get('reference_gpu_ms_per_step'), v.get('speedup'), str(v.get('reference_detail'))[:200])"
