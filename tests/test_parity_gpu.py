@@ -786,3 +786,52 @@ def test_gather_kernel_is_deterministic_on_the_plume(fsg):
             outs.append(s.download())
     for f in FIELDS + ("index", "cell"):
         assert np.array_equal(outs[0][f], outs[1][f]), f
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[2] at its full size (256^3 bins, 8.5 M particles): beyond what the oracle finishes in seconds, so the
+# checks are size-independent properties of the step
+# ---------------------------------------------------------------------------------------------
+def test_full_size_plume_256_properties(fsg):
+    cfg = fsg.scenes.plume_config(256)
+    cfg.capacity = fsg.scenes.plume_count(cfg)
+    outs = {}
+    for mode in (0, 1):                    # symmetric and gather pair kernels from the same device-generated scene
+        cfg.pair_mode = mode
+        with fsg.FluidSolver(cfg) as s:
+            n = s.scene_plume()
+            assert n == cfg.capacity
+            s.step(2)
+            got = s.download(("pos", "vel", "dens", "press", "delpress", "index", "cell"))
+            cells, start, end = s.tables()
+            st = s.stats()
+        assert st["n_live"] == n and st["steps"] == 2
+        # every particle is still there exactly once
+        assert np.array_equal(np.sort(got["index"]), np.arange(n, dtype=np.int32))
+        # the key array the pair kernel saw is sorted and start/end are findneighbours of it (FluidGPU.cu:106-117)
+        assert np.all(np.diff(cells.astype(np.int64)) >= 0)
+        heads = np.flatnonzero(np.r_[True, cells[1:] != cells[:-1]])
+        tails = np.flatnonzero(np.r_[cells[1:] != cells[:-1], True])
+        assert np.array_equal(start[cells[heads]], heads) and np.array_equal(end[cells[tails]], tails)
+        assert int((start >= 0).sum()) == heads.size == st["occupied_bins"]
+        # bin ids are the reference expression of the particle's own position (FluidGPU.cu:419)
+        own = oracle_py.cell_ids(oracle_py.params_from_cfg(cfg), got["pos"])
+        assert np.array_equal(got["cell"], own)
+        # Newton's third law: without boundary particles the pair term (P_i/rho_i^2 + P_j/rho_j^2 + s_ij) grad W_ij is antisymmetric,
+        # so the pressure-gradient sums cancel over the whole scene (FluidGPU.cu:258-260, 277-279)
+        dp = got["delpress"].astype(np.float64)
+        assert np.abs(dp.sum(0)).max() <= 1e-5 * np.abs(dp).sum(0).max(), (dp.sum(0), np.abs(dp).sum(0))
+        # set_dens (FluidGPU.cuh:165-167): dens = (sum + W(0)) / 23 + 9250 with a non-negative sum of kernel values;
+        # calculate_pressure (FluidGPU.cuh:256-257): the Tait equation of that density
+        w0 = 1.0 / 3.14159 / 0.06 ** 3
+        assert got["dens"].min() >= np.float32(9250 + w0 / 23.0) * (1 - 1e-6)
+        x = (got["dens"] / np.float32(9550)).astype(np.float32).astype(np.float64)
+        assert rel_l2(got["press"], 1000.0 * 9550.0 / 7.0 * (x ** 7 - 1.0)) <= 1e-4
+        outs[mode] = fsg.by_index(got)
+    # the two kernels differ only in the order of their float additions (positions after two steps do not depend on any sum yet)
+    for f in ("pos", "cell"):
+        assert np.array_equal(outs[0][f], outs[1][f]), f
+    for f in ("vel", "dens", "press", "delpress"):
+        err = rel_l2(outs[0][f], outs[1][f])
+        # (the Tait pressure amplifies a density difference by 7 rho^7 / (rho^7 - rho_0^7), large near the rest density)
+        assert err <= (1e-5 if f == "press" else 2e-6), (f, err)
