@@ -44,37 +44,48 @@ __device__ __forceinline__ int slab_category(const FsgDev &d, int key, int rank,
 
 // After the first step the particles are in bin-sorted order, and only slots within two layers of a face that has
 // a neighbour can have become migrants or ghosts (a particle moves less than one bin per step): the sorted slots
-// [0, region[0]) and [region[1], n), found by k_reorder.  Everything in between is skipped without being read —
-// which is also what lets overlap mode pack while the interior particles are still being updated.
-__device__ __forceinline__ bool slab_in_region(const int *__restrict__ region, int64_t i)
+// [0, region[0]) and [region[1], n_keep), found by k_reorder (n_keep: the slots in use; dead slots sort last).  The pack
+// kernels are launched over THAT index space only — compact index t -> slot t (head) or region[1] + t - region[0] (tail) —
+// with a fixed-size grid that strides over it: nothing is launched, read or written for the slots in between, which is
+// also what lets overlap mode pack while the interior particles are still being updated.
+struct SlabRegion {
+    int64_t r0, r1, total;            // head = [0, r0), tail = [r1, r1 + total - r0)
+};
+__device__ __forceinline__ SlabRegion slab_region(const int *__restrict__ region, const int *__restrict__ n_keep, int64_t n)
 {
-    return !region || i < region[0] || i >= region[1];
+    SlabRegion R;
+    if (!region) { R.r0 = n; R.r1 = n; R.total = n; return R; }      // before the first step: every slot
+    const int64_t keep = min((int64_t)*n_keep, n);
+    R.r0 = min((int64_t)region[0], keep);
+    R.r1 = max(min((int64_t)region[1], keep), R.r0);
+    R.total = R.r0 + (keep - R.r1);
+    return R;
 }
+__device__ __forceinline__ int64_t slab_slot(const SlabRegion &R, int64_t t) { return t < R.r0 ? t : R.r1 + (t - R.r0); }
 
-// counts per warp: cnt[cat * nw + warp]
+// counts per warp of the compact index space: cnt[cat * nw + warp] (cnt is cleared by the caller; only non-zero counts are written)
 __global__ void __launch_bounds__(256)
-k_slab_count(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ keys, const int *__restrict__ region, int *__restrict__ cnt,
-             int64_t nw, int *violation)
+k_slab_count(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ keys, const int *__restrict__ region,
+             const int *__restrict__ n_keep, int *__restrict__ cnt, int64_t nw, int *violation)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int c = 0;
-    if (i < n && slab_in_region(region, i)) {
-        int key = keys[i];
-        c = slab_category(d, key, rank, world);
-        // a particle that moved more than one bin layer in a step has left the one-layer ghost band
-        if (key < d.numcells && (key / d.G2 < d.x0 - 1 || key / d.G2 > d.x1)) atomicOr(violation, 1);
-    }
-    int64_t w = i >> 5;
-    int lane = threadIdx.x & 31;
-    if (i == 0) cnt[4 * nw] = 0;
-    if (!__any_sync(FULL, c != 0)) {              // the common case (interior warps): four zeros, no ballots
-        if (lane < 4 && w < nw) cnt[lane * nw + w] = 0;
-        return;
-    }
+    const SlabRegion R = slab_region(region, n_keep, n);
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5, nwc = (R.total + 31) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwc; w += warps) {
+        const int64_t t = w * 32 + lane;
+        int c = 0;
+        if (t < R.total) {
+            const int key = keys[slab_slot(R, t)];
+            c = slab_category(d, key, rank, world);
+            // a particle that moved more than one bin layer in a step has left the one-layer ghost band
+            if (key < d.numcells && (key / d.G2 < d.x0 - 1 || key / d.G2 > d.x1)) atomicOr(violation, 1);
+        }
+        if (!__any_sync(FULL, c != 0)) continue;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        unsigned m = __ballot_sync(FULL, (c >> k) & 1);
-        if (lane == 0 && w < nw) cnt[k * nw + w] = __popc(m);
+        for (int k = 0; k < 4; k++) {
+            unsigned m = __ballot_sync(FULL, (c >> k) & 1);
+            if (lane == 0 && m) cnt[k * nw + w] = __popc(m);
+        }
     }
 }
 
@@ -120,48 +131,53 @@ __global__ void k_slab_headers(const int *__restrict__ off, int64_t nw, void *to
 }
 
 __global__ void __launch_bounds__(256)
-k_slab_scatter(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ keys, const int *__restrict__ region, FsgState B,
-               const int *__restrict__ off, int64_t nw, void *to_left, void *to_right, int64_t cap_m, int64_t cap_g)
+k_slab_scatter(FsgDev d, int rank, int world, int64_t n, const int *__restrict__ keys, const int *__restrict__ region,
+               const int *__restrict__ n_keep, FsgState B, const int *__restrict__ off, int64_t nw, void *to_left, void *to_right,
+               int64_t cap_m, int64_t cap_g)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int c = (i < n && slab_in_region(region, i)) ? slab_category(d, keys[i], rank, world) : 0;
-    if (!__any_sync(FULL, c != 0)) return;
-    int64_t w = i >> 5;
-    int lane = threadIdx.x & 31;
-    unsigned lt = (1u << lane) - 1u;
-    int pos[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        unsigned m = __ballot_sync(FULL, (c >> k) & 1);
-        pos[k] = (w < nw ? off[k * nw + w] - off[k * nw] : 0) + __popc(m & lt);
-    }
-    if (!c) return;
+    const SlabRegion R = slab_region(region, n_keep, n);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const bool mix = B.mix != nullptr;
-    float4 pd = B.posd[i], vp = B.velp[i], mx = mix ? B.mix[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c & 5) {
-        // migrant: full state goes to the neighbour.  The slot is NOT freed here: a particle moves less
-        // than one bin per step, so it lands in the neighbour's outermost layer, where this slab still
-        // needs it as a candidate for one more step.  Its bin is outside [x0, x1), so it is treated as
-        // a ghost (never a home particle) and k_update drops it.
-        SlabMsg M = slab_msg((c & 1) ? to_left : to_right, cap_m, cap_g, mix);
-        int q = (c & 1) ? pos[0] : pos[2];
-        if (q < cap_m) {
-            M.m_posd[q] = pd;
-            M.m_velp[q] = vp;
-            M.m_accf[q] = B.accf[i];
-            M.m_dpi[q] = B.dpi[i];
-            if (mix) M.m_mix[q] = mx;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5, nwc = (R.total + 31) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwc; w += warps) {
+        const int64_t t = w * 32 + lane;
+        const int64_t i = t < R.total ? slab_slot(R, t) : 0;
+        const int c = t < R.total ? slab_category(d, keys[i], rank, world) : 0;
+        if (!__any_sync(FULL, c != 0)) continue;
+        int pos[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned m = __ballot_sync(FULL, (c >> k) & 1);
+            pos[k] = off[k * nw + w] - off[k * nw] + __popc(m & lt);
         }
-    }
-    if ((c & 2) && pos[1] < cap_g) {
-        SlabMsg M = slab_msg(to_left, cap_m, cap_g, mix);
-        M.g_posd[pos[1]] = pd; M.g_velp[pos[1]] = vp;
-        if (mix) M.g_mix[pos[1]] = mx;
-    }
-    if ((c & 8) && pos[3] < cap_g) {
-        SlabMsg M = slab_msg(to_right, cap_m, cap_g, mix);
-        M.g_posd[pos[3]] = pd; M.g_velp[pos[3]] = vp;
-        if (mix) M.g_mix[pos[3]] = mx;
+        if (!c) continue;
+        float4 pd = B.posd[i], vp = B.velp[i], mx = mix ? B.mix[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c & 5) {
+            // migrant: full state goes to the neighbour.  The slot is NOT freed here: a particle moves less
+            // than one bin per step, so it lands in the neighbour's outermost layer, where this slab still
+            // needs it as a candidate for one more step.  Its bin is outside [x0, x1), so it is treated as
+            // a ghost (never a home particle) and k_update drops it.
+            SlabMsg M = slab_msg((c & 1) ? to_left : to_right, cap_m, cap_g, mix);
+            int q = (c & 1) ? pos[0] : pos[2];
+            if (q < cap_m) {
+                M.m_posd[q] = pd;
+                M.m_velp[q] = vp;
+                M.m_accf[q] = B.accf[i];
+                M.m_dpi[q] = B.dpi[i];
+                if (mix) M.m_mix[q] = mx;
+            }
+        }
+        if ((c & 2) && pos[1] < cap_g) {
+            SlabMsg M = slab_msg(to_left, cap_m, cap_g, mix);
+            M.g_posd[pos[1]] = pd; M.g_velp[pos[1]] = vp;
+            if (mix) M.g_mix[pos[1]] = mx;
+        }
+        if ((c & 8) && pos[3] < cap_g) {
+            SlabMsg M = slab_msg(to_right, cap_m, cap_g, mix);
+            M.g_posd[pos[3]] = pd; M.g_velp[pos[3]] = vp;
+            if (mix) M.g_mix[pos[3]] = mx;
+        }
     }
 }
 
@@ -256,14 +272,19 @@ static int slab_pack_on(fsg_ctx *c, void *d_to_left, void *d_to_right, int64_t c
     }
     int *cnt = c->slab_cnt, *off = c->slab_cnt + (4 * c->slab_warps + 8);
     long long *diag = reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
-    const unsigned blocks = (unsigned)((nw * 32 + 255) / 256);
-    k_slab_count<<<blocks, 256, 0, st>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, region, cnt, nw, c->counters + 6);
+    // a fixed-size grid strides over the compact index space (its length is only known on the device)
+    int64_t want = (nw * 32 + 255) / 256;
+    const int64_t cap_blocks = (int64_t)c->sm_count * 16;
+    const unsigned blocks = (unsigned)(want < cap_blocks ? (want > 0 ? want : 1) : cap_blocks);
+    const int *n_keep = c->counters + 5;
+    CUS(c, cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(4 * nw + 1), st));
+    k_slab_count<<<blocks, 256, 0, st>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, region, n_keep, cnt, nw, c->counters + 6);
     CUS(c, cudaGetLastError());
     CUS(c, fsg_scan_exclusive(c->scan_tmp, c->scan_tmp_bytes, cnt, off, 4 * nw + 1, st));
     k_slab_headers<<<1, 32, 0, st>>>(off, nw, c->cfg.rank > 0 ? d_to_left : nullptr, c->cfg.rank < c->cfg.world - 1 ? d_to_right : nullptr,
                                      cap_m, cap_g, c->counters + 9, diag, stamp, c->B.mix != nullptr);
     CUS(c, cudaGetLastError());
-    k_slab_scatter<<<blocks, 256, 0, st>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, region, c->B, off, nw, d_to_left, d_to_right,
+    k_slab_scatter<<<blocks, 256, 0, st>>>(c->dev, c->cfg.rank, c->cfg.world, n, c->keysB, region, n_keep, c->B, off, nw, d_to_left, d_to_right,
                                            cap_m, cap_g);
     CUS(c, cudaGetLastError());
     c->launches += 3;

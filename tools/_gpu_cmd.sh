@@ -1,1 +1,8 @@
-timeout 300 python tools/slab_profile.py 256 > gpurun_out/slabprof_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/slabprof.csv python tools/slab_profile.py 256 > gpurun_out/slabprof_ncu.log 2>&1; echo rc=$?; tail -1 gpurun_out/slabprof_plain.log | cut -c1-200
+N=${N:-2}; G=${G:-512}
+timeout 600 python -m pytest tests -m gpu -q -x -k "slab" 2>&1 | tail -2
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --grid $G --steps 10 --warmup 3 --e2e-steps 1 > gpurun_out/bench${G}_n${N}_v3d.json 2> gpurun_out/bench${G}_n${N}_v3d.err; echo "rc=$?"
+python - <<PY
+import json
+t=open("gpurun_out/bench${G}_n${N}_v3d.json").read(); j=json.loads(t[t.index('{'):])
+print(j["ms_per_step"], {k:[round(x,3) for x in v] for k,v in j["per_rank"].items() if k.startswith("ms_")})
+PY
