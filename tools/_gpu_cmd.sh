@@ -1,5 +1,4 @@
 N=${N:-2}; G=${G:-512}
-timeout 600 python -m pytest tests -m gpu -q -x -k "slab" 2>&1 | tail -2
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --grid $G --steps 10 --warmup 3 --e2e-steps 1 > gpurun_out/bench${G}_n${N}_v3d.json 2> gpurun_out/bench${G}_n${N}_v3d.err; echo "rc=$?"
 python - <<PY
 import json
