@@ -355,7 +355,7 @@ extern "C" int fsg_upload_aos(fsg_ctx *c, const void *particles, int64_t n)
         int64_t m = n - o < chunk ? n - o : chunk;
         CU(c, cudaMemcpyAsync(c->stage, (const unsigned char *)particles + o * FSG_AOS_STRIDE, (size_t)m * FSG_AOS_STRIDE,
                               cudaMemcpyHostToDevice, c->stream));
-        FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o};
+        FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o, nullptr};
         if (c->cfg.model == FSG_MODEL_UNIDYN) {
             st.mix = c->B.mix + o;
             CU(c, fsg_launch_unpack_aos_unidyn((const unsigned char *)c->stage, m, st, c->carryB + o, c->counters + 8, c->stream));
@@ -376,7 +376,7 @@ extern "C" int fsg_download_aos(fsg_ctx *c, void *particles, int64_t n)
     if (rc != FSG_OK) return rc;
     for (int64_t o = 0; o < n; o += chunk) {
         int64_t m = n - o < chunk ? n - o : chunk;
-        FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o};
+        FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o, nullptr};
         if (c->cfg.model == FSG_MODEL_UNIDYN) {
             st.mix = c->B.mix + o;
             CU(c, fsg_launch_pack_aos_unidyn((unsigned char *)c->stage, m, st, c->carry_live ? c->carryB + o : nullptr, c->keysB + o, c->dev,

@@ -312,7 +312,6 @@ k_pair_v3(V3Args va)
         if (lane == 5) bulk_g2s(&S.hp[0], a.A.posd + sub.hs, (unsigned)sub.gcount * 16u, &W.full[stage]);
     };
 
-    const unsigned lt_mask = (1u << lane) - 1u;
     const float w_outer = d.w_c * 0.25f;
     const float inv_h = d.inv_h;
     const f32x2 ninvh = pk2(-inv_h, -inv_h);

@@ -507,7 +507,7 @@ extern "C" int fsg_stage_unidyn_findneighbours(fsg_ctx *c, const int32_t *d_cell
 // records -> the SoA streams the pair kernel reads + the list of occupied bins of one kind (which = 0: at most 6
 // particles, mykernel's bins; 1: more than 6, mykernel3's).  mark: also do mykernel's split marking (cu:181-191).
 __global__ void __launch_bounds__(256)
-k_stage_uni_unpack(FsgDev d, const unsigned char *__restrict__ aos_c, unsigned char *__restrict__ aos, const int *__restrict__ cell,
+k_stage_uni_unpack(FsgDev d, const unsigned char *aos_c, unsigned char *aos, const int *__restrict__ cell,
                    const int *__restrict__ start, const int *__restrict__ end, int64_t n, FsgState st, int *binlist, int *nocc, int which,
                    int *split, int *numsplit)
 {
