@@ -1,7 +1,6 @@
-N=${N:-2}; G=${G:-512}
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --grid $G --steps 10 --warmup 3 --e2e-steps 1 > gpurun_out/bench${G}_n${N}_v3d.json 2> gpurun_out/bench${G}_n${N}_v3d.err; echo "rc=$?"
-python - <<PY
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
+timeout 300 python bench.py --no-cpu --e2e-steps 1 --steps 5 > gpurun_out/bench512_last.json 2> gpurun_out/bench512_last.err; echo "rc=$?"
+python - <<'PY'
 import json
-t=open("gpurun_out/bench${G}_n${N}_v3d.json").read(); j=json.loads(t[t.index('{'):])
-print(j["ms_per_step"], {k:[round(x,3) for x in v] for k,v in j["per_rank"].items() if k.startswith("ms_")})
+j=json.load(open("gpurun_out/bench512_last.json")); print(j["ms_per_step"], j["phases_ms"], j["e2e"]["ms_per_step"])
 PY
