@@ -1,6 +1,9 @@
 // fsg_api.cu — the extern "C" boundary of libfsg (include/fsg.h): context lifetime, host<->device
 // movement and the step schedule.  No torch types, no exceptions across the boundary, no CPU path.
 #include "fsg_internal.cuh"
+#ifndef FSG_SORT_MERGE_MIN_CAP
+#define FSG_SORT_MERGE_MIN_CAP (1 << 20)
+#endif
 #include <stdlib.h>
 
 #include <math.h>
@@ -150,6 +153,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     cudaFree(c->start); cudaFree(c->end);
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
     cudaFree(c->counters); cudaFree(c->dstats); cudaFree(c->sort_tmp);
+    cudaFree(c->ns_a); cudaFree(c->ns_b); cudaFree(c->ns_c); cudaFree(c->ns_tmp); cudaFree(c->ns_flags);
     cudaFree(c->slab_cnt); cudaFree(c->scan_tmp);
     if (c->comm) cudaStreamSynchronize(c->comm);
     for (int k = 0; k < 4; k++) if (c->peer_inbox[k] && !c->peer_local) cudaIpcCloseMemHandle(c->peer_inbox[k]);
@@ -253,6 +257,7 @@ extern "C" int fsg_create(const fsg_config *cfg, fsg_ctx **out)
     if (!c) return FSG_E_NOMEM;
     c->cfg = *cfg;
     c->device = cfg->device;
+    c->ns_mode = -1;
     fsg_derive_constants(*cfg, c->dev);
     fsg_update_pair_mode(c);
     int rc = create_impl(c);
@@ -300,6 +305,7 @@ static int after_upload(fsg_ctx *c, int64_t n, const int *slot_state = nullptr)
         c->tables_dirty = false;
     }
     c->n = n;
+    c->keys_prev_valid = false;
     c->sent_ahead = false;
     if (c->comm) CU(c, cudaStreamSynchronize(c->comm));
     if (c->cfg.world > 1) {
@@ -584,6 +590,35 @@ extern "C" int fsg_get_phase_ms(fsg_ctx *c, double ms[4], int64_t *steps)
     return FSG_OK;
 }
 
+// The nearly-sorted path of the key sort (fsg_sort.cu): single-device contexts; its
+// buffers (two composite-key arrays of `cap` entries + one for the movers) are allocated on first use.
+static bool nearly_sorted_enabled(fsg_ctx *c)
+{
+    if (c->ns_mode < 0) {
+        // FSG_SORT_MERGE = 1 / 0 forces it on / off; by default it is used where the sort costs more than the two
+        // device-to-host reads the path needs per step (contexts of a million particles and more)
+        const char *e = getenv("FSG_SORT_MERGE");
+        const bool on = e ? atoi(e) != 0 : c->cap >= FSG_SORT_MERGE_MIN_CAP;
+        c->ns_mode = on && c->cfg.world == 1 && c->cap >= 4096;
+        if (c->ns_mode) {
+            c->ns_movers_cap = c->cap / 8 + 1024;
+            c->ns_tmp_bytes = fsg_nsort_temp_bytes(c->cap, c->ns_movers_cap, c->sort_bits);
+            bool ok = cudaMalloc(&c->ns_a, sizeof(unsigned long long) * (size_t)c->cap) == cudaSuccess &&
+                      cudaMalloc(&c->ns_b, sizeof(unsigned long long) * (size_t)c->cap) == cudaSuccess &&
+                      cudaMalloc(&c->ns_c, sizeof(unsigned long long) * (size_t)c->ns_movers_cap) == cudaSuccess &&
+                      cudaMalloc(&c->ns_tmp, c->ns_tmp_bytes ? c->ns_tmp_bytes : 16) == cudaSuccess &&
+                      cudaMalloc(&c->ns_flags, 4 * sizeof(int)) == cudaSuccess;
+            if (!ok) {                  // no room: stay with the radix sort
+                cudaGetLastError();
+                cudaFree(c->ns_a); cudaFree(c->ns_b); cudaFree(c->ns_c); cudaFree(c->ns_tmp); cudaFree(c->ns_flags);
+                c->ns_a = c->ns_b = c->ns_c = nullptr; c->ns_tmp = nullptr; c->ns_flags = nullptr;
+                c->ns_mode = 0;
+            }
+        }
+    }
+    return c->ns_mode == 1;
+}
+
 // ---- the step: solver.cu:181-198 ----
 extern "C" int fsg_step(fsg_ctx *c, int nsteps)
 {
@@ -612,7 +647,14 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         if (c->cfg.collect_stats) CU(c, cudaMemsetAsync(c->dstats, 0, 4 * sizeof(unsigned long long), c->stream));
         if (prof) prof_mark(c);
         // thrust::sort_by_key, key half (solver.cu:181)
-        CU(c, fsg_sort_pairs(c->sort_tmp, c->sort_tmp_bytes, c->keysB, c->keysA, c->iota, c->perm, n, c->sort_bits, c->stream));
+        bool sorted = false;
+        if (c->keys_prev_valid && nearly_sorted_enabled(c)) {
+            // after a step only the particles that changed bin are out of place: partition / sort the movers / merge
+            CU(c, fsg_sort_nearly_sorted(c->ns_tmp, c->ns_tmp_bytes, c->keysB, c->keysA, c->keysA, c->perm, c->ns_a, c->ns_b, c->ns_c,
+                                         c->ns_movers_cap, c->ns_flags, n, c->sort_bits, c->stream, &sorted));
+            if (sorted) c->ns_used++; else c->ns_fallbacks++;
+        }
+        if (!sorted) CU(c, fsg_sort_pairs(c->sort_tmp, c->sort_tmp_bytes, c->keysB, c->keysA, c->iota, c->perm, n, c->sort_bits, c->stream));
         if (prof) prof_mark(c);
         // value half + findneighbours (solver.cu:181-182)
         CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA,
@@ -635,6 +677,7 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         c->carry_live = false;
         c->cur = nxt;
         c->tables_dirty = true;
+        c->keys_prev_valid = true;      // keysA = this step's sorted keys, keysB = the new keys of the same slots
         c->steps++;
     }
     return FSG_OK;

@@ -93,6 +93,15 @@ struct fsg_ctx {
     cudaEvent_t ev_boundary, ev_sent;
     int *binlistB;      // boundary home bins of the current step (overlap mode)
     void *sort_tmp;
+    // nearly-sorted path of the key sort (world == 1): composite-key buffers, scratch, device flags; allocated on first use
+    unsigned long long *ns_a, *ns_b, *ns_c;
+    void *ns_tmp;
+    size_t ns_tmp_bytes;
+    int64_t ns_movers_cap;
+    int *ns_flags;
+    int ns_mode;        // -1 not decided yet, 0 off, 1 on (FSG_SORT_MERGE)
+    bool keys_prev_valid;   // keysA holds the sorted keys of the step that produced B / keysB (same slot order)
+    int64_t ns_used, ns_fallbacks;
     void *stage;        // device staging area for host<->device conversion
     size_t stage_bytes;
     size_t sort_tmp_bytes;
@@ -115,6 +124,12 @@ size_t fsg_sort_int_temp_bytes(int64_t n);
 size_t fsg_sort_temp_bytes(int64_t n, int bits);
 cudaError_t fsg_sort_pairs(void *tmp, size_t tmp_bytes, const int *keys_in, int *keys_out, const int *vals_in,
                            int *vals_out, int64_t n, int bits, cudaStream_t s);
+// the same sort for an almost sorted key array (partition stayers | movers, sort the movers, merge); verified on the device,
+// *done == false means "use fsg_sort_pairs" (see fsg_sort.cu)
+size_t fsg_nsort_temp_bytes(int64_t n, int64_t movers_cap, int bits);
+cudaError_t fsg_sort_nearly_sorted(void *tmp, size_t tmp_bytes, const int *keys_new, const int *keys_prev, int *keys_out, int *vals_out,
+                                   unsigned long long *buf_a, unsigned long long *buf_b, unsigned long long *buf_c, int64_t movers_cap,
+                                   int *dflags, int64_t n, int bits, cudaStream_t s, bool *done);
 
 // fsg_base_kernels.cu
 cudaError_t fsg_launch_iota(int *p, int64_t n, cudaStream_t s);

@@ -60,6 +60,7 @@ extern "C" int fsg_stage_sort(fsg_ctx *c, int32_t *d_cells, void *d_particles, i
     if (rc != FSG_OK) return rc;
     unsigned char *tmp_rec = (unsigned char *)c->stage;
     void *tmp_sort = tmp_rec + ((rec + 255) & ~(size_t)255);
+    c->keys_prev_valid = false;       // keysA / perm are used as scratch here
     // stable LSD radix sort of (key, slot): the permutation thrust::sort_by_key applies to the records
     CUG(c, fsg_sort_pairs_int(tmp_sort, tb, d_cells, c->keysA, c->iota, c->perm, n, c->stream));
     CUG(c, cudaMemcpyAsync(d_cells, c->keysA, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));

@@ -835,3 +835,37 @@ def test_full_size_plume_256_properties(fsg):
         err = rel_l2(outs[0][f], outs[1][f])
         # (the Tait pressure amplifies a density difference by 7 rho^7 / (rho^7 - rho_0^7), large near the rest density)
         assert err <= (1e-5 if f == "press" else 2e-6), (f, err)
+
+
+def test_nearly_sorted_key_sort_gives_the_radix_sort_result(fsg, monkeypatch):
+    """fsg_sort.cu: after the first step the key sort is partition (particles that kept their bin | movers) + radix sort of the
+    movers + merge, verified on the device, with the plain radix sort as fallback.  Same permutation, so with the deterministic
+    kernels the whole state must come out bit for bit the same (FSG_SORT_MERGE forces the path on / off; by default it is used
+    from a million particles up — the 256^3 test above runs it)."""
+    cases = []
+    cfg = fsg.FluidSolver.base_config()
+    cases.append((cfg, fsg.scenes.base_default_scene(), 12))                      # config 1, capped kernels
+    cfg = fsg.scenes.plume_config(24)
+    cfg.pair_mode = 1
+    st = fsg.scenes.plume_scene(cfg)
+    st["vel"] = (st["vel"] * np.float32(40.0)).astype(np.float32)                 # fast enough for many bin changes per step
+    cases.append((cfg, st, 8))
+    cfg = fsg.scenes.plume_config(17)
+    cfg.origin = -1.02
+    cfg.pair_mode = 1
+    cases.append((cfg, fsg.scenes.random_base_scene(6000, 21, box=((-0.4, 0.4),) * 3, spacing=0.05, jitter=0.012, boundary_frac=0.2,
+                                                    vel_scale=3.0), 6))
+    for cfg, state, steps in cases:
+        cfg.capacity = state["pos"].shape[0]
+        outs = []
+        for mode in ("1", "0"):
+            monkeypatch.setenv("FSG_SORT_MERGE", mode)
+            with fsg.FluidSolver(cfg) as s:
+                s.upload(state)
+                s.step(steps)
+                outs.append((s.download(), s.tables()))
+        (a, ta), (b, tb) = outs
+        for f in FIELDS + ("index", "cell", "boundary"):
+            assert np.array_equal(a[f], b[f]), f
+        for x, y in zip(ta, tb):
+            assert np.array_equal(x, y)
