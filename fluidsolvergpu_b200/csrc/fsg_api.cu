@@ -650,8 +650,13 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         bool sorted = false;
         if (c->keys_prev_valid && nearly_sorted_enabled(c)) {
             // after a step only the particles that changed bin are out of place: partition / sort the movers / merge
-            CU(c, fsg_sort_nearly_sorted(c->ns_tmp, c->ns_tmp_bytes, c->keysB, c->keysA, c->keysA, c->perm, c->ns_a, c->ns_b, c->ns_c,
-                                         c->ns_movers_cap, c->ns_flags, n, c->sort_bits, c->stream, &sorted));
+            cudaError_t ne = fsg_sort_nearly_sorted(c->ns_tmp, c->ns_tmp_bytes, c->keysB, c->keysA, c->keysA, c->perm, c->ns_a, c->ns_b, c->ns_c,
+                                                    c->ns_movers_cap, c->ns_flags, n, c->sort_bits, c->stream, &sorted);
+            if (ne != cudaSuccess) {        // a library call refused (size limits ...): not fatal, the radix sort does the job from here on
+                cudaGetLastError();
+                c->ns_mode = 0;
+                sorted = false;
+            }
             if (sorted) c->ns_used++; else c->ns_fallbacks++;
         }
         if (!sorted) CU(c, fsg_sort_pairs(c->sort_tmp, c->sort_tmp_bytes, c->keysB, c->keysA, c->iota, c->perm, n, c->sort_bits, c->stream));
