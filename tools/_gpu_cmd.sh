@@ -1,1 +1,1 @@
-timeout 300 python -m pytest tests -m gpu -q -x -k "nearly_sorted or full_size or config1_first" > gpurun_out/ns_test.log 2>&1; grep -E "^E  " gpurun_out/ns_test.log | cut -c1-250 | head -6; tail -2 gpurun_out/ns_test.log
+timeout 300 python -m pytest tests -m gpu -q > gpurun_out/final_test.log 2>&1; grep -E "^E  " gpurun_out/final_test.log | cut -c1-250 | head -6; tail -2 gpurun_out/final_test.log
