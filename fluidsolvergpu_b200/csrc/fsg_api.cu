@@ -164,6 +164,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     for (int k = 0; k < 2; k++) cudaFree(c->outbox[k]);
     for (int k = 0; k < 4; k++) cudaFree(c->inbox[k]);
     cudaFree(c->stage);
+    if (c->host_flag) cudaFreeHost((void *)c->host_flag);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -307,6 +308,7 @@ static int after_upload(fsg_ctx *c, int64_t n, const int *slot_state = nullptr)
     c->n = n;
     c->keys_prev_valid = false;
     c->sent_ahead = false;
+    if (c->host_flag) *c->host_flag = 0;      // a fresh state: a previous exchange time-out no longer applies
     if (c->comm) CU(c, cudaStreamSynchronize(c->comm));
     if (c->cfg.world > 1) {
         // a slab context always works on all `cap` slots (nothing on the host depends on how many are in use):
@@ -628,6 +630,7 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         c->err = "fsg_step: a slab context advances one step per pack / exchange / unpack round";
         return FSG_E_STATE;
     }
+    if (c->cfg.world > 1) { int rc = fsg_slab_sticky_error(c); if (rc != FSG_OK) return rc; }
     const int64_t n = c->n;
     if (n <= 0) { c->steps += nsteps; return FSG_OK; }
     for (int t = 0; t < nsteps; t++) {

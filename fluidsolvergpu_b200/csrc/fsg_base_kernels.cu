@@ -100,7 +100,9 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
 {
     if (n <= 0) return cudaSuccess;
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    int dev = 0, sms = 0;                                           // grid-stride kernel: 8 blocks per SM of the current device
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 1;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     k_reset_tables<<<(unsigned)blocks, 256, 0, s>>>(binlist, nocc, keysA, start, end);
     return cudaGetLastError();
 }
@@ -444,13 +446,12 @@ cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binli
     if (blocks < 1) blocks = 1;
     const bool stats = c->cfg.collect_stats != 0;
     const size_t smem = PAIR_SMEM;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static FsgAttrOnce attr_once;
+    if (attr_once.need()) {
         cudaFuncSetAttribute(k_pair_update<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pair_update<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pair_update<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pair_update<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
     }
     // Uncapped configuration (every particle of the 27 bins is visited): the pipelined pair-sum kernel
     // + the streaming update kernel (fsg_pair_v2.cu).  pair_fp64 == 3 keeps the fused kernel instead.

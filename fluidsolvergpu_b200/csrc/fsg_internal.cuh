@@ -85,6 +85,9 @@ struct fsg_ctx {
     void *peer_inbox[4];// the neighbours' inboxes mapped through CUDA IPC: [0..1] left neighbour's from-right, [2..3] right neighbour's from-left
     int64_t msg_cap_m, msg_cap_g;
     long long seq_send, seq_recv;   // exchange sequence numbers (stamps at the tail of every message)
+    volatile int *host_flag;        // pinned, device-mapped: raised by k_slab_wait when a neighbour's message never arrived (sticky)
+    int *host_flag_dev;
+    unsigned long long slab_timeout_ns;
     bool keep_foreign;  // slab contexts: uploads are not filtered by position (fsg_slab_keep_foreign)
     bool peer_local;    // peer_inbox holds plain pointers of this process (fsg_slab_set_peer), not IPC mappings
     bool overlap;       // pack + copies of the NEXT step's messages run on `comm` behind the boundary bins, beside the interior bins
@@ -145,6 +148,7 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
                                int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, cudaStream_t s);
+int fsg_slab_sticky_error(fsg_ctx *c); // fsg_slab.cu: FSG_E_STATE once a device-side wait for a neighbour has timed out
 int fsg_slab_send_next(fsg_ctx *c);   // fsg_slab.cu: pack + copies of the next step's messages on c->comm (overlap mode)
 cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work,
                                    const float4 *carry, int *launches, cudaStream_t s);
@@ -166,4 +170,19 @@ cudaError_t fsg_launch_pack_aos_unidyn(unsigned char *aos, int64_t n, FsgState s
                                        cudaStream_t s);
 
 void fsg_derive_constants(const fsg_config &cfg, FsgDev &d);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: a process that creates contexts on
+// several devices has to opt every kernel in on each of them.  One FsgAttrOnce per launcher; `need()` is true the first time
+// the CURRENT device is seen (lock-free, any thread).
+#include <atomic>
+struct FsgAttrOnce {
+    std::atomic<unsigned long long> seen[4];       // bit per device ordinal, 256 devices
+    bool need()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 256) return true;
+        const unsigned long long bit = 1ull << (dev & 63);
+        return (seen[dev >> 6].fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+    }
+};
 void fsg_update_pair_mode(fsg_ctx *c);     // sets c->dev.sym from the configuration and the overlap / stats switches

@@ -237,12 +237,11 @@ k_pair_update_fast(PairArgs a)
 
 cudaError_t fsg_launch_pair_fast(const PairArgs &a, bool stats, int sm_count, cudaStream_t s)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static FsgAttrOnce attr_once;
+    if (attr_once.need()) {
         cudaFuncSetAttribute(k_pair_update_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM);
         cudaFuncSetAttribute(k_pair_update_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM);
         cudaFuncSetAttribute(k_pair_update_fast<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM);
-        attr_done = true;
     }
     int64_t blocks = ((int64_t)a.n + FAST_WARPS - 1) / FAST_WARPS;
     int64_t maxb = (int64_t)sm_count * 4;      // persistent: 4 resident blocks (16 warps) per SM

@@ -466,14 +466,13 @@ k_update(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B,
 template <int CW, bool PK>
 static cudaError_t launch_pair_v2_cw(const V2Args &va, bool stats, bool has_boundary, int sm_count, int blocks_per_sm, cudaStream_t s)
 {
-    static bool attr_done = false;
+    static FsgAttrOnce attr_once;
     const int smem = (int)sizeof(V2Smem<CW>);
-    if (!attr_done) {
+    if (attr_once.need()) {
         cudaFuncSetAttribute(k_pair_v2<false, false, CW, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_pair_v2<false, true, CW, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_pair_v2<true, false, CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_pair_v2<true, true, CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_done = true;
     }
     int per_sm = CW == 4 ? V2_BPS4 : CW == 6 ? 5 : 4;
     if (blocks_per_sm > 0 && blocks_per_sm < per_sm) per_sm = blocks_per_sm;

@@ -426,12 +426,11 @@ cudaError_t fsg_launch_pair_v3(const PairArgs &a, float4 *sums, bool has_boundar
     V3Args va;
     va.a = a;
     va.sums = sums;
-    static bool attr_done = false;
+    static FsgAttrOnce attr_once;
     const int smem = (int)sizeof(V3Warp) * V3_WARPS;
-    if (!attr_done) {
+    if (attr_once.need()) {
         cudaFuncSetAttribute(k_pair_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_pair_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_done = true;
     }
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float4) * (size_t)a.n, s);
     if (e != cudaSuccess) return e;

@@ -14,6 +14,7 @@
 
 #include <cub/device/device_scan.cuh>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 size_t fsg_scan_temp_bytes(int64_t n)
@@ -197,6 +198,7 @@ k_slab_unpack(FsgDev d, const void *from_left, const void *from_right, int64_t c
     const long long nl = from_left ? hl[0] + hl[1] : 0;
     if (t == 0) { diag[4] = from_left ? hl[0] : 0; diag[5] = from_left ? hl[1] : 0; diag[6] = from_right ? hr[0] : 0; diag[7] = from_right ? hr[1] : 0; }
     if (!msg) return;
+    if (*overflow & 4) return;        // the wait for this message timed out: what the inbox holds is two steps old
     const bool mix = B.mix != nullptr;
     SlabMsg M = slab_msg(const_cast<void *>(msg), cap_m, cap_g, mix);
     const long long m = M.hdr[0], g = M.hdr[1];
@@ -236,15 +238,30 @@ extern "C" int64_t fsg_slab_message_bytes_model(int model, int64_t cap_m, int64_
 static size_t slab_bytes(const fsg_ctx *c, int64_t cap_m, int64_t cap_g) { return (size_t)fsg_slab_message_bytes_model(c->cfg.model, cap_m, cap_g); }
 
 // Waits (on the device) until both neighbours' messages number `expected` have landed in this rank's inboxes:
-// the stamp is the last thing a sender copies.  One thread, bounded: a missing neighbour raises flag 4.
-__global__ void k_slab_wait(const volatile long long *tail_left, const volatile long long *tail_right, long long expected, int *flags)
+// the stamp is the last thing a sender copies.  One thread; bounded by WALL-CLOCK time (%globaltimer, nanoseconds;
+// fsg_ctx::slab_timeout_ns, FSG_SLAB_TIMEOUT_MS in the environment, default 30 s — rank skew under a profiler's
+// kernel replay or a first-touch IPC mapping is seconds, not microseconds).  A missing neighbour raises flag 4 in the
+// device-side flags (k_slab_unpack then appends NOTHING: the stale message of two steps ago is not integrated) and in
+// the host-mapped flag word, which makes every following fsg_slab_* / fsg_step call return FSG_E_STATE.
+__device__ __forceinline__ unsigned long long fsg_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void k_slab_wait(const volatile long long *tail_left, const volatile long long *tail_right, long long expected, int *flags,
+                            volatile int *host_flag, unsigned long long timeout_ns)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const long long t0 = clock64();
+    const unsigned long long t0 = fsg_globaltimer();
     for (;;) {
         bool ok = (!tail_left || *tail_left >= expected) && (!tail_right || *tail_right >= expected);
         if (ok) break;
-        if (clock64() - t0 > 6000000000ll) { atomicOr(flags, 4); break; }     // ~3 s
+        if (fsg_globaltimer() - t0 > timeout_ns) {
+            atomicOr(flags, 4);
+            if (host_flag) *host_flag = 4;
+            break;
+        }
         __nanosleep(200);
     }
     __threadfence_system();
@@ -375,6 +392,14 @@ extern "C" int fsg_slab_alloc_messages(fsg_ctx *c, int64_t cap_m, int64_t cap_g)
     CUS(c, cudaStreamSynchronize(c->stream));
     c->msg_cap_m = cap_m;
     c->msg_cap_g = cap_g;
+    if (!c->host_flag) {              // host-visible flag word the device-side wait raises on a timeout
+        CUS(c, cudaHostAlloc((void **)&c->host_flag, 64, cudaHostAllocMapped));
+        *c->host_flag = 0;
+        CUS(c, cudaHostGetDevicePointer((void **)&c->host_flag_dev, (void *)c->host_flag, 0));
+    }
+    const char *te = getenv("FSG_SLAB_TIMEOUT_MS");
+    const double tms = te ? atof(te) : 30000.0;
+    c->slab_timeout_ns = (unsigned long long)((tms > 1.0 ? tms : 1.0) * 1e6);
     return FSG_OK;
 }
 
@@ -427,9 +452,21 @@ static int slab_send_on(fsg_ctx *c, const int *region, cudaStream_t st)
     return FSG_OK;
 }
 
+// A wait that timed out (k_slab_wait) is sticky: the state has been integrated without its neighbours.
+int fsg_slab_sticky_error(fsg_ctx *c)
+{
+    if (c->host_flag && *c->host_flag) {
+        c->err = "slab exchange: timed out waiting for a neighbour's message; the state of this context is no longer valid "
+                 "(upload again; FSG_SLAB_TIMEOUT_MS sets the limit)";
+        return FSG_E_STATE;
+    }
+    return FSG_OK;
+}
+
 extern "C" int fsg_slab_pack_send(fsg_ctx *c)
 {
     if (!c) return FSG_E_INVALID;
+    if (int rc = fsg_slab_sticky_error(c)) return rc;
     if (c->sent_ahead) { c->sent_ahead = false; return FSG_OK; }      // fsg_step already issued this exchange (overlap mode)
     // (before the first step the particles are in upload order: every slot is looked at)
     return slab_send_on(c, c->steps > 0 ? c->counters + 12 : nullptr, c->stream);
@@ -452,6 +489,7 @@ extern "C" int fsg_slab_unpack_recv(fsg_ctx *c)
 {
     if (!c) return FSG_E_INVALID;
     if (!c->inbox[0]) { c->err = "fsg_slab_unpack_recv: call fsg_slab_alloc_messages first"; return FSG_E_STATE; }
+    if (int rc = fsg_slab_sticky_error(c)) return rc;
     CUS(c, cudaSetDevice(c->device));
     const long long seq = ++c->seq_recv;
     const int par = (int)(seq & 1);
@@ -459,7 +497,8 @@ extern "C" int fsg_slab_unpack_recv(fsg_ctx *c)
     if (c->overlap) CUS(c, cudaStreamWaitEvent(c->stream, c->ev_sent, 0));   // my own pack (other stream) reads the slots unpack writes
     const size_t tail = (slab_bytes(c, c->msg_cap_m, c->msg_cap_g) - 64);
     k_slab_wait<<<1, 32, 0, c->stream>>>(left ? (const long long *)((char *)c->inbox[par] + tail) : nullptr,
-                                         right ? (const long long *)((char *)c->inbox[2 + par] + tail) : nullptr, seq, c->counters + 9);
+                                         right ? (const long long *)((char *)c->inbox[2 + par] + tail) : nullptr, seq, c->counters + 9,
+                                         c->host_flag_dev, c->slab_timeout_ns);
     CUS(c, cudaGetLastError());
     c->launches++;
     return fsg_slab_unpack(c, c->inbox[par], c->inbox[2 + par], c->msg_cap_m, c->msg_cap_g);

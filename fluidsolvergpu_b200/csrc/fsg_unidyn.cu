@@ -330,11 +330,10 @@ cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, c
                               int *launches, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static FsgAttrOnce attr_once;
+    if (attr_once.need()) {
         cudaFuncSetAttribute(k_pair_unidyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
         cudaFuncSetAttribute(k_pair_unidyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
-        attr_done = true;
     }
     UniArgs a;
     a.d = c->dev;
@@ -578,11 +577,10 @@ static int uni_stage_pairs(fsg_ctx *c, void *d_particles, const int32_t *d_cells
                            int32_t *d_split, int32_t *d_numsplit, int64_t n, int which)
 {
     CUU(c, cudaSetDevice(c->device));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static FsgAttrOnce attr_once;
+    if (attr_once.need()) {
         cudaFuncSetAttribute(k_pair_unidyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
         cudaFuncSetAttribute(k_pair_unidyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
-        attr_done = true;
     }
     int *binlist = c->binlist[0], *nocc = c->counters + 7, *work = c->counters + 2;
     CUU(c, cudaMemsetAsync(nocc, 0, sizeof(int), c->stream));

@@ -377,3 +377,87 @@ class SlabGroup:
     def download(self) -> dict:
         parts = [s.download() for s in self.slabs]
         return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+
+# ---------------------------------------------------------------------------------------------
+# N slab processes against one context, through the real transport (bench.py `slab_parity`, tests/test_multi_gpu.py)
+# ---------------------------------------------------------------------------------------------
+def parity_against_single(grid: int, rank: int, world: int, device: int, exchange: str = "peer", steps: int = 4, pair_mode: int = 0,
+                          spacing: float = 0.05, jitter: float = 0.005, seed: int = 20261018, drift: float = 3.0) -> dict | None:
+    """Runs the plume scene at grid^3 bins on `world` slab PROCESSES (this is one of them; torch.distributed is initialised,
+    one GPU per rank) over the `exchange` transport ('peer': CUDA-IPC inboxes + device-side stamps, 'nccl': send/recv) and,
+    on rank 0, on a single context.  Every step starts from identical bits (the single context is re-uploaded from the slabs'
+    gathered state, like tests/test_parity_gpu.py::test_slabs_match_single_device does in one process), so that positions,
+    velocities, bin ids and boundary flags must agree bit for bit and the pair sums to rounding.  A common drift along x
+    makes particles cross the slab faces (migration).  Returns the comparison record on rank 0, None elsewhere."""
+    import torch.distributed as dist
+    from . import scenes
+    from .solver import by_index
+
+    base = scenes.plume_config(grid)
+    base.pair_mode = pair_mode
+    base.device = device
+    state = scenes.plume_scene(base, spacing, jitter, seed)
+    state["vel"][:, 0] += np.float32(drift)
+    n = state["pos"].shape[0]
+    hist = layer_hist_from_positions(base, state["pos"])
+    cuts = slab_cuts(hist, world)
+    owned = [int(hist[a:b].sum()) for a, b in cuts]
+    cap = int(max(owned) * 1.1) + 3 * int(hist.max()) + 65536
+    cap_m, cap_g = message_caps(hist, cuts)
+    ex = DistExchange()
+    s = SlabSolver(slab_config(base, rank, world, cuts, cap, device), ex, cap_m, cap_g)
+    single = None
+    try:
+        if exchange == "peer":
+            s.setup_peer_exchange()
+        s.upload(state)                       # every rank is handed the whole scene and keeps its own slab
+        if rank == 0:
+            one = scenes.plume_config(grid, n)
+            one.pair_mode = pair_mode
+            one.device = device
+            single = FluidSolver(one)
+        rec = {"grid": grid, "particles": n, "world": world, "exchange": exchange, "pair_mode": pair_mode, "steps": steps,
+               "bit_exact": True, "cells_equal_frac": 1.0, "max_rel_l2": 0.0, "migrated": 0, "conserved": True}
+        ints = ("pos", "vel", "cell", "boundary")
+        flds = ("acc", "dens", "press", "delpress")
+
+        def gather():
+            mine = s.download()
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object(mine, parts, dst=0)
+            if rank != 0:
+                return None
+            return by_index({k: np.concatenate([p[k] for p in parts]) for k in parts[0]})
+
+        for _ in range(steps):
+            cur = gather()
+            if rank == 0:
+                rec["conserved"] &= bool(cur["index"].shape[0] == n and np.array_equal(cur["index"], np.arange(n)))
+                single.upload({f: v for f, v in cur.items() if f != "cell"})
+            s.step(1)
+            info = s.check()
+            rec["migrated"] += ex.global_sum([info["sent"][0] + info["sent"][2]], s.tdev)[0]
+            if rank == 0:
+                single.step(1)
+            a = gather()
+            if rank == 0:
+                b = by_index(single.download())
+                ok_n = a["index"].shape[0] == b["index"].shape[0] and np.array_equal(a["index"], b["index"])
+                rec["conserved"] &= bool(ok_n)
+                if not ok_n:
+                    rec["bit_exact"] = False
+                    break
+                for f in ints:
+                    same = np.array_equal(a[f].view(np.uint8) if a[f].dtype == np.uint8 else a[f], b[f])
+                    rec["bit_exact"] &= bool(same)
+                rec["cells_equal_frac"] = min(rec["cells_equal_frac"], float((a["cell"] == b["cell"]).mean()))
+                for f in flds:
+                    den = float(np.sqrt((b[f].astype(np.float64) ** 2).sum()))
+                    err = float(np.sqrt(((a[f].astype(np.float64) - b[f].astype(np.float64)) ** 2).sum()))
+                    rec["max_rel_l2"] = max(rec["max_rel_l2"], err / den if den > 0 else err)
+        return rec if rank == 0 else None
+    finally:
+        s.close()
+        if single is not None:
+            single.close()
