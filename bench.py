@@ -205,7 +205,8 @@ def slab_parity(fsg, dist, rank, world, local, exchange, steps=4, grid=128):
             out[name] = res
     if rank != 0:
         return None
-    out["ok"] = bool(all(out[k]["bit_exact"] and out[k]["conserved"] and out[k]["max_rel_l2"] <= 1e-5 for k in ("symmetric_kernel", "gather_kernel")))
+    out["ok"] = bool(all(out[k]["bit_exact"] and out[k]["conserved"] and out[k]["max_rel_l2"] <= 1e-5 and out[k]["migrated"] > 0
+                         for k in ("symmetric_kernel", "gather_kernel")))
     out["what"] = (f"plume {grid}^3 + x-drift, {steps} steps: {world} slab processes over the '{exchange}' transport vs one context, by index, "
                    "each step from identical bits; bit_exact = pos / vel / cell / boundary, max_rel_l2 = acc / dens / press / delpress")
     return out

@@ -153,7 +153,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     cudaFree(c->start); cudaFree(c->end);
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
     cudaFree(c->counters); cudaFree(c->dstats); cudaFree(c->sort_tmp);
-    cudaFree(c->ns_a); cudaFree(c->ns_b); cudaFree(c->ns_c); cudaFree(c->ns_tmp); cudaFree(c->ns_flags);
+    cudaFree(c->keysC); cudaFree(c->ns_ws);
     cudaFree(c->slab_cnt); cudaFree(c->scan_tmp);
     if (c->comm) cudaStreamSynchronize(c->comm);
     for (int k = 0; k < 4; k++) if (c->peer_inbox[k] && !c->peer_local) cudaIpcCloseMemHandle(c->peer_inbox[k]);
@@ -537,7 +537,13 @@ extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
     D2H(h->newdelpress, s.ndp, 12 * n); D2H(h->index, s.index, 4 * n); D2H(h->cell, s.cell, 4 * n); D2H(h->boundary, s.bnd, n);
     if (c->B.mix) { D2H(h->solid, s.solid, 4 * n); D2H(h->fluid, s.fluid, 4 * n); }
 #undef D2H
+    int order_bad = 0;
+    CU(c, cudaMemcpyAsync(&order_bad, c->counters + 14, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (order_bad) {
+        c->err = "the key sort left the bin ids out of order (found by k_reorder): the state of this context is not valid";
+        return FSG_E_STATE;
+    }
     return FSG_OK;
 }
 
@@ -592,28 +598,23 @@ extern "C" int fsg_get_phase_ms(fsg_ctx *c, double ms[4], int64_t *steps)
     return FSG_OK;
 }
 
-// The nearly-sorted path of the key sort (fsg_sort.cu): single-device contexts; its
-// buffers (two composite-key arrays of `cap` entries + one for the movers) are allocated on first use.
+// The nearly-sorted key sort (fsg_nsort.cu) — every step but the first after an upload, single-device and slab contexts alike; its
+// workspace (~17 B per slot) and the third key buffer are allocated on first use.
 static bool nearly_sorted_enabled(fsg_ctx *c)
 {
     if (c->ns_mode < 0) {
-        // FSG_SORT_MERGE = 1 / 0 forces it on / off; by default it is used where the sort costs more than the two
-        // device-to-host reads the path needs per step (contexts of a million particles and more)
+        // FSG_SORT_MERGE = 1 / 0 forces it on / off; by default it is used where the sort's memory traffic matters (contexts of a
+        // million slots and more) — below that its ~17 small launches cost more than the library sort's three
         const char *e = getenv("FSG_SORT_MERGE");
         const bool on = e ? atoi(e) != 0 : c->cap >= FSG_SORT_MERGE_MIN_CAP;
-        c->ns_mode = on && c->cfg.world == 1 && c->cap >= 4096;
+        c->ns_mode = on && c->cap >= 64;
         if (c->ns_mode) {
-            c->ns_movers_cap = c->cap / 8 + 1024;
-            c->ns_tmp_bytes = fsg_nsort_temp_bytes(c->cap, c->ns_movers_cap, c->sort_bits);
-            bool ok = cudaMalloc(&c->ns_a, sizeof(unsigned long long) * (size_t)c->cap) == cudaSuccess &&
-                      cudaMalloc(&c->ns_b, sizeof(unsigned long long) * (size_t)c->cap) == cudaSuccess &&
-                      cudaMalloc(&c->ns_c, sizeof(unsigned long long) * (size_t)c->ns_movers_cap) == cudaSuccess &&
-                      cudaMalloc(&c->ns_tmp, c->ns_tmp_bytes ? c->ns_tmp_bytes : 16) == cudaSuccess &&
-                      cudaMalloc(&c->ns_flags, 4 * sizeof(int)) == cudaSuccess;
+            c->ns_ws_bytes = fsg_nsort_bytes(c->cap);
+            bool ok = cudaMalloc(&c->keysC, sizeof(int) * (size_t)c->cap) == cudaSuccess && cudaMalloc(&c->ns_ws, c->ns_ws_bytes) == cudaSuccess;
             if (!ok) {                  // no room: stay with the radix sort
                 cudaGetLastError();
-                cudaFree(c->ns_a); cudaFree(c->ns_b); cudaFree(c->ns_c); cudaFree(c->ns_tmp); cudaFree(c->ns_flags);
-                c->ns_a = c->ns_b = c->ns_c = nullptr; c->ns_tmp = nullptr; c->ns_flags = nullptr;
+                cudaFree(c->keysC); cudaFree(c->ns_ws);
+                c->keysC = nullptr; c->ns_ws = nullptr;
                 c->ns_mode = 0;
             }
         }
@@ -650,25 +651,24 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         if (c->cfg.collect_stats) CU(c, cudaMemsetAsync(c->dstats, 0, 4 * sizeof(unsigned long long), c->stream));
         if (prof) prof_mark(c);
         // thrust::sort_by_key, key half (solver.cu:181)
-        bool sorted = false;
         if (c->keys_prev_valid && nearly_sorted_enabled(c)) {
-            // after a step only the particles that changed bin are out of place: partition / sort the movers / merge
-            cudaError_t ne = fsg_sort_nearly_sorted(c->ns_tmp, c->ns_tmp_bytes, c->keysB, c->keysA, c->keysA, c->perm, c->ns_a, c->ns_b, c->ns_c,
-                                                    c->ns_movers_cap, c->ns_flags, n, c->sort_bits, c->stream, &sorted);
-            if (ne != cudaSuccess) {        // a library call refused (size limits ...): not fatal, the radix sort does the job from here on
-                cudaGetLastError();
-                c->ns_mode = 0;
-                sorted = false;
-            }
-            if (sorted) c->ns_used++; else c->ns_fallbacks++;
+            // after a step only the particles that changed bin (and, in a slab, the ghosts that came or went) are out of place:
+            // flag the movers, radix-sort them, merge by ranking — hand-written, nothing read back (fsg_nsort.cu)
+            int l = 0;
+            CU(c, fsg_nsort(c->ns_ws, c->keysB, c->keysA, c->keysC, c->perm, n, c->sort_bits, c->sm_count, c->stream, &l));
+            int *t = c->keysA; c->keysA = c->keysC; c->keysC = t;
+            c->launches += l;
+            c->ns_used++;
+        } else {
+            CU(c, fsg_sort_pairs(c->sort_tmp, c->sort_tmp_bytes, c->keysB, c->keysA, c->iota, c->perm, n, c->sort_bits, c->stream));
+            c->launches++;
         }
-        if (!sorted) CU(c, fsg_sort_pairs(c->sort_tmp, c->sort_tmp_bytes, c->keysB, c->keysA, c->iota, c->perm, n, c->sort_bits, c->stream));
         if (prof) prof_mark(c);
         // value half + findneighbours (solver.cu:181-182)
         CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA,
                                  c->start, c->end, c->binlist[nxt], c->counters + nxt, c->binlistB ? c->binlistB : c->binlist[nxt],
                                  c->counters + 10, c->counters + 3, c->counters + 5, c->cfg.world > 1 ? c->counters + 12 : nullptr,
-                                 c->stream));
+                                 c->counters + 14, c->stream));
         c->n_sorted = n;
         c->launches++;
         if (prof) prof_mark(c);
@@ -746,7 +746,7 @@ extern "C" int fsg_get_stats(fsg_ctx *c, fsg_stats *out)
 {
     if (!c || !out) return FSG_E_INVALID;
     CU(c, cudaSetDevice(c->device));
-    int cnt[4] = {0, 0, 0, 0};
+    int cnt[16] = {0};
     unsigned long long ds[4] = {0, 0, 0, 0};
     CU(c, cudaMemcpyAsync(cnt, c->counters, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(ds, c->dstats, sizeof ds, cudaMemcpyDeviceToHost, c->stream));
@@ -760,6 +760,10 @@ extern "C" int fsg_get_stats(fsg_ctx *c, fsg_stats *out)
     out->dropped = (int64_t)ds[2];
     out->steps = c->steps;
     out->kernel_launches = c->launches;
+    if (cnt[14]) {
+        c->err = "the key sort left the bin ids out of order (found by k_reorder): the state of this context is not valid";
+        return FSG_E_STATE;
+    }
     return FSG_OK;
 }
 

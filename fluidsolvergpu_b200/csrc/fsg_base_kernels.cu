@@ -115,7 +115,7 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
 __global__ void __launch_bounds__(256)
 k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restrict__ keysA, FsgState src,
           FsgState dst, const float4 *__restrict__ carry_src, float4 *__restrict__ carry_dst, int *start, int *end,
-          int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges)
+          int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag)
 {
     const int numcells = d.numcells;
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,6 +131,7 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
         if (src.mix) dst.mix[k] = src.mix[sidx];
         if (carry_src) carry_dst[k] = carry_src[sidx];
         int next = k + 1 < n ? keysA[k + 1] : d.dead;
+        if (k + 1 < n && next < key) atomicOr(order_flag, 1);          // the key sort's result, verified where it is consumed
         if (key < numcells) {
             int prev = k > 0 ? keysA[k - 1] : -1;
             if (key != prev) {
@@ -172,11 +173,12 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
 }
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, cudaStream_t s)
+                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag,
+                               cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     k_reorder<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst,
-                                                          start, end, binlist, nocc, binlistB, noccB, nlive, nkeep, ranges);
+                                                          start, end, binlist, nocc, binlistB, noccB, nlive, nkeep, ranges, order_flag);
     return cudaGetLastError();
 }
 

@@ -74,7 +74,8 @@ struct fsg_ctx {
     int *perm, *iota;
     int *start, *end;   // dense bin tables, -1 = empty  (FluidGPU.cu:106-117)
     int *binlist[2];    // ids of the occupied home bins (unordered), ping-pong
-    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live, [4] any-boundary flag, [5] n_keep, [12..13] pack ranges
+    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live, [4] any-boundary flag, [5] n_keep, [12..13] pack ranges,
+                        // [14] the sorted key array was found out of order by k_reorder (never expected; reported by fsg_get_stats / downloads)
     unsigned long long *dstats;   // [0] tested, [1] in range, [2] dropped
     int *slab_cnt;      // slab pack: per-warp counts of the 4 message categories, then their exclusive scan
     void *scan_tmp;
@@ -96,15 +97,13 @@ struct fsg_ctx {
     cudaEvent_t ev_boundary, ev_sent;
     int *binlistB;      // boundary home bins of the current step (overlap mode)
     void *sort_tmp;
-    // nearly-sorted path of the key sort (world == 1): composite-key buffers, scratch, device flags; allocated on first use
-    unsigned long long *ns_a, *ns_b, *ns_c;
-    void *ns_tmp;
-    size_t ns_tmp_bytes;
-    int64_t ns_movers_cap;
-    int *ns_flags;
+    // nearly-sorted key sort (fsg_nsort.cu): third key buffer (the sort reads keysB + keysA and writes keysC, then A <-> C), workspace
+    int *keysC;
+    void *ns_ws;
+    size_t ns_ws_bytes;
     int ns_mode;        // -1 not decided yet, 0 off, 1 on (FSG_SORT_MERGE)
     bool keys_prev_valid;   // keysA holds the sorted keys of the step that produced B / keysB (same slot order)
-    int64_t ns_used, ns_fallbacks;
+    int64_t ns_used;
     void *stage;        // device staging area for host<->device conversion
     size_t stage_bytes;
     size_t sort_tmp_bytes;
@@ -127,12 +126,11 @@ size_t fsg_sort_int_temp_bytes(int64_t n);
 size_t fsg_sort_temp_bytes(int64_t n, int bits);
 cudaError_t fsg_sort_pairs(void *tmp, size_t tmp_bytes, const int *keys_in, int *keys_out, const int *vals_in,
                            int *vals_out, int64_t n, int bits, cudaStream_t s);
-// the same sort for an almost sorted key array (partition stayers | movers, sort the movers, merge); verified on the device,
-// *done == false means "use fsg_sort_pairs" (see fsg_sort.cu)
-size_t fsg_nsort_temp_bytes(int64_t n, int64_t movers_cap, int bits);
-cudaError_t fsg_sort_nearly_sorted(void *tmp, size_t tmp_bytes, const int *keys_new, const int *keys_prev, int *keys_out, int *vals_out,
-                                   unsigned long long *buf_a, unsigned long long *buf_b, unsigned long long *buf_c, int64_t movers_cap,
-                                   int *dflags, int64_t n, int bits, cudaStream_t s, bool *done);
+// fsg_nsort.cu — the same sort for an almost sorted key array (hand-written: flag movers / scan / radix sort of the movers / merge by
+// ranking), no host synchronisation.  keys_out / perm_out must not alias the inputs.
+size_t fsg_nsort_bytes(int64_t n);
+cudaError_t fsg_nsort(void *ws, const int *keys_new, const int *keys_prev, int *keys_out, int *perm_out, int64_t n, int bits, int sm_count,
+                      cudaStream_t s, int *launches);
 
 // fsg_base_kernels.cu
 cudaError_t fsg_launch_iota(int *p, int64_t n, cudaStream_t s);
@@ -147,7 +145,8 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
                                     int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, cudaStream_t s);
+                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag,
+                               cudaStream_t s);
 int fsg_slab_sticky_error(fsg_ctx *c); // fsg_slab.cu: FSG_E_STATE once a device-side wait for a neighbour has timed out
 int fsg_slab_send_next(fsg_ctx *c);   // fsg_slab.cu: pack + copies of the next step's messages on c->comm (overlap mode)
 cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work,

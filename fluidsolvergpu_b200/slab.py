@@ -383,13 +383,14 @@ class SlabGroup:
 # N slab processes against one context, through the real transport (bench.py `slab_parity`, tests/test_multi_gpu.py)
 # ---------------------------------------------------------------------------------------------
 def parity_against_single(grid: int, rank: int, world: int, device: int, exchange: str = "peer", steps: int = 4, pair_mode: int = 0,
-                          spacing: float = 0.05, jitter: float = 0.005, seed: int = 20261018, drift: float = 3.0) -> dict | None:
+                          spacing: float = 0.05, jitter: float = 0.005, seed: int = 20261018, drift: float = 25.0) -> dict | None:
     """Runs the plume scene at grid^3 bins on `world` slab PROCESSES (this is one of them; torch.distributed is initialised,
     one GPU per rank) over the `exchange` transport ('peer': CUDA-IPC inboxes + device-side stamps, 'nccl': send/recv) and,
     on rank 0, on a single context.  Every step starts from identical bits (the single context is re-uploaded from the slabs'
     gathered state, like tests/test_parity_gpu.py::test_slabs_match_single_device does in one process), so that positions,
     velocities, bin ids and boundary flags must agree bit for bit and the pair sums to rounding.  A common drift along x
-    makes particles cross the slab faces (migration).  Returns the comparison record on rank 0, None elsewhere."""
+    (drift * DT * steps >= one lattice spacing, so some lattice plane crosses every slab face; still far below one bin layer per
+    step) makes particles migrate.  Returns the comparison record on rank 0, None elsewhere."""
     import torch.distributed as dist
     from . import scenes
     from .solver import by_index
@@ -403,8 +404,9 @@ def parity_against_single(grid: int, rank: int, world: int, device: int, exchang
     hist = layer_hist_from_positions(base, state["pos"])
     cuts = slab_cuts(hist, world)
     owned = [int(hist[a:b].sum()) for a, b in cuts]
-    cap = int(max(owned) * 1.1) + 3 * int(hist.max()) + 65536
+    cap = max(int(max(owned) * 1.1) + 3 * int(hist.max()) + 65536, n + 64)      # (the upload hands every rank the whole scene)
     cap_m, cap_g = message_caps(hist, cuts)
+    cap_m = cap_g                     # with the drift whole lattice planes cross a face within one step
     ex = DistExchange()
     s = SlabSolver(slab_config(base, rank, world, cuts, cap, device), ex, cap_m, cap_g)
     single = None

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--grid", type=int, default=64)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
-    ap.add_argument("--drift", type=float, default=3.0)
+    ap.add_argument("--drift", type=float, default=25.0)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
