@@ -1,6 +1,6 @@
 // fsg_api.cu — the extern "C" boundary of libfsg (include/fsg.h): context lifetime, host<->device
 // movement and the step schedule.  No torch types, no exceptions across the boundary, no CPU path.
-#include "fsg_internal.cuh"
+#include "fsg_device.cuh"
 #ifndef FSG_SORT_MERGE_MIN_CAP
 #define FSG_SORT_MERGE_MIN_CAP (1 << 20)
 #endif
@@ -259,6 +259,7 @@ extern "C" int fsg_create(const fsg_config *cfg, fsg_ctx **out)
     c->cfg = *cfg;
     c->device = cfg->device;
     c->ns_mode = -1;
+    c->defer_mode = -1;
     fsg_derive_constants(*cfg, c->dev);
     fsg_update_pair_mode(c);
     int rc = create_impl(c);
@@ -307,6 +308,8 @@ static int after_upload(fsg_ctx *c, int64_t n, const int *slot_state = nullptr)
     }
     c->n = n;
     c->keys_prev_valid = false;
+    c->deferred = false;
+    c->carry_pending = false;
     c->sent_ahead = false;
     if (c->host_flag) *c->host_flag = 0;      // a fresh state: a previous exchange time-out no longer applies
     if (c->comm) CU(c, cudaStreamSynchronize(c->comm));
@@ -379,6 +382,7 @@ extern "C" int fsg_download_aos(fsg_ctx *c, void *particles, int64_t n)
 {
     if (!c || (!particles && n > 0) || n < 0 || n > c->n) return FSG_E_INVALID;
     CU(c, cudaSetDevice(c->device));
+    if (int rm = fsg_materialize(c)) return rm;
     const int64_t chunk = 1 << 20;
     int rc = ensure_stage(c, (size_t)(n < chunk ? n : chunk) * FSG_AOS_STRIDE + 16);
     if (rc != FSG_OK) return rc;
@@ -519,6 +523,7 @@ extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
     const int64_t n = c->n;
     h->n = n;
     CU(c, cudaSetDevice(c->device));
+    if (int rm = fsg_materialize(c)) return rm;
     SoaStage s;
     size_t bytes = soa_stage_layout(nullptr, n, h, s);
     int rc = ensure_stage(c, bytes);
@@ -622,6 +627,31 @@ static bool nearly_sorted_enabled(fsg_ctx *c)
     return c->ns_mode == 1;
 }
 
+// Deferred update: single-device base contexts running the pipelined fp32 pair kernels (they write `sums`); FSG_DEFER_UPDATE=0
+// keeps the separate k_update pass after every step.
+static bool defer_enabled(fsg_ctx *c)
+{
+    if (c->defer_mode < 0) {
+        const char *e = getenv("FSG_DEFER_UPDATE");
+        c->defer_mode = e ? atoi(e) != 0 : 1;
+    }
+    const fsg_config &f = c->cfg;
+    return c->defer_mode == 1 && f.world == 1 && f.model == FSG_MODEL_BASE && f.pair_fp64 == 0 && f.neighbour_cap == 0 && f.bin_cap == 0 &&
+           !c->overlap;
+}
+
+// Makes B / keysB the post-update state of the last step (what downloads, fsg_device_ptr and a slab pack read).
+int fsg_materialize(fsg_ctx *c)
+{
+    if (!c->deferred) return FSG_OK;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, fsg_launch_update(c->dev, c->n, c->keysA, c->A, c->B, c->keysB, c->sums, c->carry_pending ? c->carryA : nullptr, 0, nullptr, c->stream));
+    c->launches++;
+    c->deferred = false;
+    c->carry_pending = false;
+    return FSG_OK;
+}
+
 // ---- the step: solver.cu:181-198 ----
 extern "C" int fsg_step(fsg_ctx *c, int nsteps)
 {
@@ -664,11 +694,20 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
             c->launches++;
         }
         if (prof) prof_mark(c);
-        // value half + findneighbours (solver.cu:181-182)
-        CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA,
-                                 c->start, c->end, c->binlist[nxt], c->counters + nxt, c->binlistB ? c->binlistB : c->binlist[nxt],
-                                 c->counters + 10, c->counters + 3, c->counters + 5, c->cfg.world > 1 ? c->counters + 12 : nullptr,
-                                 c->counters + 14, c->stream));
+        // value half + findneighbours (solver.cu:181-182); with a deferred update also mykernel2's update of the PREVIOUS step
+        const bool defer = defer_enabled(c);
+        if (c->deferred) {
+            CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->A, c->B, c->carry_pending ? c->carryA : nullptr, nullptr, c->sums,
+                                     defer ? c->keysB : nullptr, c->start, c->end, c->binlist[nxt], c->counters + nxt, c->binlist[nxt],
+                                     c->counters + 10, c->counters + 3, c->counters + 5, nullptr, c->counters + 14, c->stream));
+            FsgState t = c->A; c->A = c->B; c->B = t;      // A: the sorted pre-update state of THIS step; B: scratch until materialised
+            c->carry_pending = false;
+            c->deferred = false;
+        } else
+            CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA, nullptr,
+                                     defer ? c->keysB : nullptr, c->start, c->end, c->binlist[nxt], c->counters + nxt,
+                                     c->binlistB ? c->binlistB : c->binlist[nxt], c->counters + 10, c->counters + 3, c->counters + 5,
+                                     c->cfg.world > 1 ? c->counters + 12 : nullptr, c->counters + 14, c->stream));
         c->n_sorted = n;
         c->launches++;
         if (prof) prof_mark(c);
@@ -677,7 +716,12 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         if (c->cfg.model == FSG_MODEL_UNIDYN)      // mykernel + mykernel3 + mykernel2 + cell_calc (solver-unidyn.cu:363-548)
             CU(c, fsg_launch_unidyn(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2, c->carry_live ? c->carryA : nullptr, &l,
                                     c->stream));
-        else
+        else if (defer) {
+            // pair sums only: the update they feed runs inside the next step's reorder (or in fsg_materialize)
+            CU(c, fsg_launch_pair_sums(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2, &l, c->stream));
+            c->deferred = true;
+            c->carry_pending = c->carry_live;
+        } else
             CU(c, fsg_launch_pair_update(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2,
                                          c->carry_live ? c->carryA : nullptr, &l, c->stream));
         c->launches += l;
@@ -799,6 +843,7 @@ extern "C" int fsg_scene_plume(fsg_ctx *c, double spacing, double jitter, uint64
 extern "C" int fsg_device_ptr(fsg_ctx *c, int which, void **ptr)
 {
     if (!c || !ptr) return FSG_E_INVALID;
+    if (int rm = fsg_materialize(c)) return rm;
     switch (which) {
     case 0: *ptr = c->B.posd; break;
     case 1: *ptr = c->B.velp; break;

@@ -112,9 +112,16 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
 // thrust::sort_by_key, solver.cu:181) + findneighbours (FluidGPU.cu:106-117) + the list of occupied
 // bins that k_pair_update walks.  Streaming, HBM-bound: 4+4 B keys/perm + 64 B in + 64 B out.
 // ------------------------------------------------------------------------------------------------
+// UPD: the source records are the sorted PRE-update state of the previous step: Particle::update (with that step's pair sums,
+// `sums_src`, + accumulators carried in from an upload) is applied on the way through — the deferred-update schedule of fsg_step,
+// which saves the separate update pass (read 80 B + write 72 B per particle) and one trip of the state through HBM.
+// keys_next != nullptr: the bin id each particle will have after ITS next update goes to keys_next[k] (predicted_key) — the next
+// step's sort input, produced before this step's pair kernel runs.
+template <bool UPD>
 __global__ void __launch_bounds__(256)
 k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restrict__ keysA, FsgState src,
-          FsgState dst, const float4 *__restrict__ carry_src, float4 *__restrict__ carry_dst, int *start, int *end,
+          FsgState dst, const float4 *__restrict__ carry_src, float4 *__restrict__ carry_dst, const float4 *__restrict__ sums_src,
+          int *__restrict__ keys_next, int *start, int *end,
           int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag)
 {
     const int numcells = d.numcells;
@@ -124,12 +131,24 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
         int sidx = perm[k];
         float4 a = src.posd[sidx], b = src.velp[sidx], c = src.accf[sidx], e = src.dpi[sidx];
         int key = keysA[k];
+        if (UPD) {
+            // particles that were parked BEFORE the update pass through unchanged, like k_update; one that leaves the grid in this
+            // update (key == numcells now, position still inside) gets it, and is parked from then on
+            if (key < numcells || bin_id(d, a.x, a.y, a.z) < numcells) {
+                float4 sm = sums_src[sidx];
+                if (carry_src) { const float4 cy = carry_src[sidx]; sm.x += cy.x; sm.y += cy.y; sm.z += cy.z; sm.w += cy.w; }
+                // (the bin id of the new position is `key`: it was predicted a step ago from the same bits, predicted_key; the three double
+                // divisions of a second bin_id would make this streaming kernel compute bound)
+                int unused;
+                particle_update<false>(d, a, b, c, e, sm.x, sm.y, sm.z, sm.w, unused);
+            }
+        } else if (carry_src) carry_dst[k] = carry_src[sidx];
         dst.posd[k] = a;
         dst.velp[k] = b;
         dst.accf[k] = c;
         dst.dpi[k] = e;
         if (src.mix) dst.mix[k] = src.mix[sidx];
-        if (carry_src) carry_dst[k] = carry_src[sidx];
+        if (keys_next) keys_next[k] = key < numcells ? predicted_key(d, a, b) : key;
         int next = k + 1 < n ? keysA[k + 1] : d.dead;
         if (k + 1 < n && next < key) atomicOr(order_flag, 1);          // the key sort's result, verified where it is consumed
         if (key < numcells) {
@@ -172,13 +191,18 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
     if (headB) binlistB[s_base[1] + s_cnt[1][warp] + __popc(mB & ((1u << lane) - 1))] = keysA[k];
 }
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
-                               FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag,
+                               FsgState dst, const float4 *carry_src, float4 *carry_dst, const float4 *sums_src, int *keys_next, int *start,
+                               int *end, int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag,
                                cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_reorder<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst,
-                                                          start, end, binlist, nocc, binlistB, noccB, nlive, nkeep, ranges, order_flag);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (sums_src)
+        k_reorder<true><<<blocks, 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst, sums_src, keys_next, start, end, binlist, nocc,
+                                               binlistB, noccB, nlive, nkeep, ranges, order_flag);
+    else
+        k_reorder<false><<<blocks, 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst, nullptr, keys_next, start, end, binlist, nocc,
+                                                binlistB, noccB, nlive, nkeep, ranges, order_flag);
     return cudaGetLastError();
 }
 
@@ -419,6 +443,36 @@ __global__ void k_copy_parked_dyn(const int *nlive, int64_t n, FsgState A, FsgSt
         B.dpi[i] = A.dpi[i];
         keysB[i] = numcells;
     }
+}
+
+static PairArgs pair_args(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work, const float4 *carry)
+{
+    PairArgs a;
+    a.d = c->dev;
+    a.n = (int)n;
+    a.keysA = c->keysA;
+    a.start = c->start;
+    a.end = c->end;
+    a.binlist = binlist;
+    a.nocc = nocc;
+    a.work = work;
+    a.A = c->A;
+    a.B = c->B;
+    a.keysB = c->keysB;
+    a.carry = carry;
+    a.stats = c->dstats;
+    a.sums = nullptr;
+    return a;
+}
+
+// the pair sums of the uncapped fp32 configuration into c->sums, nothing else (deferred-update schedule)
+cudaError_t fsg_launch_pair_sums(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work, int *launches, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    const PairArgs a = pair_args(c, n, binlist, nocc, work, nullptr);
+    *launches += 1;
+    if (c->dev.sym) return fsg_launch_pair_v3(a, c->sums, c->has_boundary, c->sm_count, s);
+    return fsg_launch_pair_v2(a, c->sums, c->cfg.collect_stats != 0, c->has_boundary, c->sm_count, 0, s);
 }
 
 cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work,

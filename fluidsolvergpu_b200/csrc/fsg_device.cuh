@@ -31,6 +31,7 @@ __device__ __forceinline__ float dist2(float rx, float ry, float rz)
 // Particle::update (FluidGPU.cuh:270-304) + the tail of mykernel2 (FluidGPU.cu:419-425) for one
 // particle.  Follows the reference's promotions expression by expression — it runs once per
 // particle, so the double arithmetic is free next to the pair loop.
+template <bool WITH_KEY = true>
 __device__ __forceinline__ void particle_update(const FsgDev &d, float4 &pd, float4 &vp, float4 &af, float4 &dpi,
                                                 float newdens, float ndx, float ndy, float ndz, int &key)
 {
@@ -63,7 +64,20 @@ __device__ __forceinline__ void particle_update(const FsgDev &d, float4 &pd, flo
     }
     pd.w = bnd ? -dens : dens;
     vp.w = press;
-    key = bin_id(d, pd.x, pd.y, pd.z);   // FluidGPU.cu:419
+    if (WITH_KEY) key = bin_id(d, pd.x, pd.y, pd.z);   // FluidGPU.cu:419
+}
+
+// The bin id a particle will have AFTER its next Particle::update: the new position is pos + DT*vel of the state the pair sums are
+// taken over (FluidGPU.cuh:286-288: the position step uses the velocity from before the update, and no pair sum) — so the NEXT
+// step's sort keys exist before this step's pair kernel has even started.  Same expressions, same bits as particle_update.
+__device__ __forceinline__ int predicted_key(const FsgDev &d, const float4 &pd, const float4 &vp)
+{
+    if (pd.w < 0.f) return bin_id(d, pd.x, pd.y, pd.z);                  // boundary particles do not move (cuh:285)
+    const double DT = d.dt;
+    const float x = (float)((double)pd.x + DT * (double)vp.x);
+    const float y = (float)((double)pd.y + DT * (double)vp.y);
+    const float z = (float)((double)pd.z + DT * (double)vp.z);
+    return bin_id(d, x, y, z);
 }
 
 struct PairArgs {
@@ -88,6 +102,8 @@ cudaError_t fsg_launch_pair_v2(const PairArgs &a, float4 *sums, bool stats, bool
                                cudaStream_t s);
 // fsg_pair_v3.cu — symmetric pair sums (each pair of particles in different bins is evaluated once); clears `sums` first
 cudaError_t fsg_launch_pair_v3(const PairArgs &a, float4 *sums, bool has_boundary, int sm_count, cudaStream_t s);
+// pair sums only (no update launch): the deferred-update schedule of fsg_step applies them in the next step's reorder
+cudaError_t fsg_launch_pair_sums(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work, int *launches, cudaStream_t s);
 // part: 0 every slot, 1 the slab's boundary slots (boundary bins, ghosts, parked, dead), 2 the interior slots
 cudaError_t fsg_launch_update(const FsgDev &d, int64_t n, const int *keysA, FsgState A, FsgState B, int *keysB,
                               const float4 *sums, const float4 *carry, int part, int *violation, cudaStream_t s);

@@ -64,6 +64,12 @@ struct fsg_ctx {
     FsgState A, B;      // A: sorted pre-update state of the last step; B: post-update state
     float4 *carryB, *carryA;   // accumulators carried into the first step after upload (newdens, newdelpress xyz)
     bool carry_live;
+    // Deferred update (single-device base contexts, uncapped fp32 pair kernels): after a step the post-update state B is NOT
+    // materialised — the state is (A, sums [, carryA]) and keysB already holds the bin ids after the update (predicted_key);
+    // the next step's reorder applies the update while it gathers.  fsg_materialize() runs k_update when somebody needs B.
+    bool deferred;          // B is stale: (A, sums) is the state
+    bool carry_pending;     // carryA still has to be added to the sums of the deferred update (first step after an upload)
+    int defer_mode;         // -1 not decided, 0 off, 1 on (FSG_DEFER_UPDATE)
     float4 *sums;              // pair sums of the current step (newdens, newdelpress xyz), sorted order
     float4 *sums2;             // unidyn: (diffusion xyz, delfluid)
     float *vizb;               // unidyn: |diffusion|^2 of the last step (mykernel2's b3, FluidGPU-unidyn.cu:466)
@@ -144,8 +150,8 @@ cudaError_t fsg_scan_exclusive(void *tmp, size_t tmp_bytes, const int *in, int *
 cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const int *keysA, int *start, int *end,
                                     int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
-                               FsgState dst, const float4 *carry_src, float4 *carry_dst, int *start, int *end,
-                               int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag,
+                               FsgState dst, const float4 *carry_src, float4 *carry_dst, const float4 *sums_src, int *keys_next, int *start,
+                               int *end, int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag,
                                cudaStream_t s);
 int fsg_slab_sticky_error(fsg_ctx *c); // fsg_slab.cu: FSG_E_STATE once a device-side wait for a neighbour has timed out
 int fsg_slab_send_next(fsg_ctx *c);   // fsg_slab.cu: pack + copies of the next step's messages on c->comm (overlap mode)
@@ -168,6 +174,7 @@ cudaError_t fsg_launch_unpack_aos_unidyn(const unsigned char *aos, int64_t n, Fs
 cudaError_t fsg_launch_pack_aos_unidyn(unsigned char *aos, int64_t n, FsgState st, const float4 *carry, const int *keys, const FsgDev &d,
                                        cudaStream_t s);
 
+int fsg_materialize(fsg_ctx *c);           // fsg_api.cu: makes B / keysB the post-update state (no-op unless the update is deferred)
 void fsg_derive_constants(const fsg_config &cfg, FsgDev &d);
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: a process that creates contexts on

@@ -9,7 +9,7 @@
 //   k_ns_count    movers per tile of 2048 slots                                   (8 B read per slot)
 //   k_ns_scan     exclusive scan of the tile counts, one block -> tile offsets, M = number of movers (device side)
 //   k_ns_compact  movers (key, slot) compacted IN SLOT ORDER + per 32-slot group: mover bit mask and mover prefix
-//   k_rs_*        stable LSD radix sort of the M movers by key, 8 bits a pass (histogram / scan / scatter); M is read
+//   k_rs_*        stable LSD radix sort of the M movers by key, 8 bits a pass (histogram / column scan / scatter); M is read
 //                 on the device: fixed grids stride over ceil(M / 2048) tiles, so nothing is launched "per mover count"
 //   k_ns_place    every element computes its own final position (a merge by ranking, no merge-path partition):
 //                   stayer at slot k :  k - movers_before_slot(k) + #{sorted movers < (key, k)}     (block-level search
@@ -29,11 +29,12 @@
 
 struct NsBufs {
     int *tile_cnt;            // [ntiles + 1] movers per tile -> exclusive offsets; [ntiles] = M
+    int *tile_lo;             // [ntiles + 1] sorted movers below the tile's first composite
     int *grp_off;             // [n / 32 + 1] movers before the 32-slot group
     unsigned *grp_mask;       // [n / 32 + 1] which slots of the group are movers
     int *mk[2], *ms[2];       // mover keys / slots, ping-pong for the radix passes
     int *hist;                // [mover tiles][256]
-    int *base;                // [256] digit bases of the current pass
+    int *base;                // [256] digit totals, [256] digit bases of the current pass
     int *M;                   // device-side mover count (== tile_cnt[ntiles])
 };
 
@@ -61,7 +62,7 @@ k_ns_count(const int *__restrict__ knew, const int *__restrict__ prev, int64_t n
     }
 }
 
-// exclusive scan of cnt[0..m) in place, cnt[m] = total; one block of 1024 threads
+// exclusive scan of cnt[0..m) in place, cnt[m] = total; one block of 1024 threads, 8 consecutive entries per thread and round
 __global__ void __launch_bounds__(1024)
 k_ns_scan(int *__restrict__ cnt, int64_t m, int *__restrict__ total_out)
 {
@@ -70,10 +71,12 @@ k_ns_scan(int *__restrict__ cnt, int64_t m, int *__restrict__ total_out)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
-    for (int64_t b = 0; b < m; b += 1024) {
-        const int64_t i = b + threadIdx.x;
-        const int v = i < m ? cnt[i] : 0;
-        int incl = v;
+    for (int64_t b = 0; b < m; b += 8192) {
+        const int64_t i0 = b + (int64_t)threadIdx.x * 8;
+        int v[8], sum = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) { v[r] = i0 + r < m ? cnt[i0 + r] : 0; sum += v[r]; }
+        int incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(FULL, incl, o);
@@ -92,7 +95,9 @@ k_ns_scan(int *__restrict__ cnt, int64_t m, int *__restrict__ total_out)
         }
         __syncthreads();
         const int run = s_run;
-        if (i < m) cnt[i] = run + s_w[warp] + incl - v;
+        int ex = run + s_w[warp] + incl - sum;
+#pragma unroll
+        for (int r = 0; r < 8; r++) { if (i0 + r < m) cnt[i0 + r] = ex; ex += v[r]; }
         __syncthreads();
         if (threadIdx.x == 1023) s_run = run + s_w[31] + incl;
         __syncthreads();
@@ -110,13 +115,21 @@ k_ns_compact(const int *__restrict__ knew, const int *__restrict__ prev, int64_t
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int key[8];
     unsigned bits = 0;
+    if (base + 8 <= n) {                                 // (the arrays are 256-byte aligned, base is a multiple of 8: two 16-byte loads each)
+        const int4 a0 = *reinterpret_cast<const int4 *>(knew + base), a1 = *reinterpret_cast<const int4 *>(knew + base + 4);
+        const int4 p0 = *reinterpret_cast<const int4 *>(prev + base), p1 = *reinterpret_cast<const int4 *>(prev + base + 4);
+        key[0] = a0.x; key[1] = a0.y; key[2] = a0.z; key[3] = a0.w; key[4] = a1.x; key[5] = a1.y; key[6] = a1.z; key[7] = a1.w;
+        bits = (a0.x != p0.x) | ((a0.y != p0.y) << 1) | ((a0.z != p0.z) << 2) | ((a0.w != p0.w) << 3) | ((a1.x != p1.x) << 4) |
+               ((a1.y != p1.y) << 5) | ((a1.z != p1.z) << 6) | ((a1.w != p1.w) << 7);
+    } else {
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int64_t k = base + r;
-        key[r] = 0;
-        if (k < n) {
-            key[r] = knew[k];
-            if (key[r] != prev[k]) bits |= 1u << r;
+        for (int r = 0; r < 8; r++) {
+            const int64_t k = base + r;
+            key[r] = 0;
+            if (k < n) {
+                key[r] = knew[k];
+                if (key[r] != prev[k]) bits |= 1u << r;
+            }
         }
     }
     const int mine = __popc(bits);
@@ -151,8 +164,9 @@ k_ns_compact(const int *__restrict__ knew, const int *__restrict__ prev, int64_t
 }
 
 // ---- stable LSD radix sort of the movers: 8 bits a pass, M read on the device ----
+// hist[d * tcap + t] = movers of digit d in mover tile t (digit-major, so that the scan of one digit over the tiles is contiguous)
 __global__ void __launch_bounds__(NS_THREADS)
-k_rs_hist(const int *__restrict__ mk, const int *__restrict__ Mp, int shift, int *__restrict__ hist)
+k_rs_hist(const int *__restrict__ mk, const int *__restrict__ Mp, int shift, int *__restrict__ hist, int64_t tcap)
 {
     __shared__ int s_h[256];
     const int M = *Mp;
@@ -167,39 +181,75 @@ k_rs_hist(const int *__restrict__ mk, const int *__restrict__ Mp, int shift, int
             if (i < M) atomicAdd(&s_h[((unsigned)mk[i] >> shift) & 255u], 1);
         }
         __syncthreads();
-        hist[(int64_t)t * 256 + threadIdx.x] = s_h[threadIdx.x];
+        hist[(int64_t)threadIdx.x * tcap + t] = s_h[threadIdx.x];
         __syncthreads();
     }
 }
 
-// hist[t][d] -> movers of digit d in tiles before t; base[d] -> movers of smaller digits.  One block, thread = digit.
+// block d: exclusive scan of hist[d][0 .. ntiles) in place (movers of digit d in the tiles before t), total[d] = their number
 __global__ void __launch_bounds__(256)
-k_rs_scan(int *__restrict__ hist, const int *__restrict__ Mp, int *__restrict__ base)
+k_rs_colscan(int *__restrict__ hist, const int *__restrict__ Mp, int64_t tcap, int *__restrict__ total)
 {
+    __shared__ int s_w[8];
+    __shared__ int s_run;
     const int M = *Mp;
     const int ntiles = (M + NS_TILE - 1) / NS_TILE;
-    const int d = threadIdx.x;
-    int run = 0;
-    for (int t = 0; t < ntiles; t++) {
-        const int v = hist[(int64_t)t * 256 + d];
-        hist[(int64_t)t * 256 + d] = run;
-        run += v;
-    }
-    __shared__ int s[256];
-    s[d] = run;
+    int *col = hist + (int64_t)blockIdx.x * tcap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
-    if (d == 0) {
-        int acc = 0;
-        for (int q = 0; q < 256; q++) { const int v = s[q]; s[q] = acc; acc += v; }
+    for (int b = 0; b < ntiles; b += 1024) {
+        const int i0 = b + threadIdx.x * 4;
+        int v[4], sum = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) { v[r] = i0 + r < ntiles ? col[i0 + r] : 0; sum += v[r]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int wb = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) if (w < warp) wb += s_w[w];
+        const int run = s_run;
+        int ex = run + wb + incl - sum;
+#pragma unroll
+        for (int r = 0; r < 4; r++) { if (i0 + r < ntiles) col[i0 + r] = ex; ex += v[r]; }
+        __syncthreads();
+        if (threadIdx.x == 255) s_run = run + wb + incl;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) total[blockIdx.x] = s_run;
+}
+
+// base[d] = movers of smaller digits (exclusive scan of the 256 totals)
+__global__ void __launch_bounds__(256)
+k_rs_base(const int *__restrict__ total, int *__restrict__ base)
+{
+    __shared__ int s_w[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = total[threadIdx.x];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    base[d] = s[d];
+    int wb = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (w < warp) wb += s_w[w];
+    base[threadIdx.x] = wb + incl - v;
 }
 
 // warp w of a tile takes the 256 consecutive movers [256 w, 256 w + 256) in 8 rounds of 32: tile order = (warp, round, lane)
 __global__ void __launch_bounds__(NS_THREADS)
 k_rs_scatter(const int *__restrict__ mk, const int *__restrict__ ms, int *__restrict__ ok, int *__restrict__ os, const int *__restrict__ Mp,
-             int shift, const int *__restrict__ hist, const int *__restrict__ base)
+             int shift, const int *__restrict__ hist, int64_t tcap, const int *__restrict__ base)
 {
     __shared__ int s_cnt[NS_THREADS / 32][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -239,7 +289,7 @@ k_rs_scatter(const int *__restrict__ mk, const int *__restrict__ ms, int *__rest
             const int i = b + r * 32 + lane;
             if (i < M) {
                 const int d = (int)(((unsigned)key[r] >> shift) & 255u);
-                const int at = base[d] + hist[(int64_t)t * 256 + d] + s_cnt[warp][d] + lrank[r];
+                const int at = base[d] + hist[(int64_t)d * tcap + t] + s_cnt[warp][d] + lrank[r];
                 ok[at] = key[r];
                 os[at] = val[r];
             }
@@ -261,21 +311,28 @@ __device__ __forceinline__ int ns_lower_bound(const int *__restrict__ mk, const 
     return lo;
 }
 
+// tile_lo[t] = sorted movers below the first composite of tile t, (prev[2048 t], 2048 t); tile_lo[ntiles] = M.  One thread per
+// tile: the searches of all tiles run side by side instead of at the head of every placing block.
+__global__ void __launch_bounds__(NS_THREADS)
+k_ns_tile_bounds(const int *__restrict__ prev, int64_t ntiles, const int *__restrict__ mk, const int *__restrict__ ms, const int *__restrict__ Mp,
+                 int *__restrict__ tile_lo)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    const int M = *Mp;
+    tile_lo[t] = t == ntiles ? M : ns_lower_bound(mk, ms, 0, M, prev[t * NS_TILE], (int)(t * NS_TILE));
+}
+
 __global__ void __launch_bounds__(NS_THREADS)
 k_ns_place_stayers(const int *__restrict__ knew, const int *__restrict__ prev, int64_t n, const int *__restrict__ mk, const int *__restrict__ ms,
-                   const int *__restrict__ Mp, const int *__restrict__ grp_off, const unsigned *__restrict__ grp_mask, int *__restrict__ keys_out,
+                   const int *__restrict__ tile_lo, const int *__restrict__ grp_off, const unsigned *__restrict__ grp_mask, int *__restrict__ keys_out,
                    int *__restrict__ perm)
 {
     __shared__ int s_mk[NS_SM_MOVERS], s_ms[NS_SM_MOVERS];
-    __shared__ int s_lo, s_hi;
-    const int M = *Mp;
     const int64_t base = (int64_t)blockIdx.x * NS_TILE;
-    const int64_t last = min(base + NS_TILE, n) - 1;
-    // the tile's stayers have composites in [(prev[base], base), (prev[last], last)]: movers outside that range are either
-    // before all of them (counted by s_lo) or after all of them
-    if (threadIdx.x == 0) s_lo = ns_lower_bound(mk, ms, 0, M, prev[base], (int)base);
-    if (threadIdx.x == 32) s_hi = ns_lower_bound(mk, ms, 0, M, prev[last], (int)last + 1);
-    __syncthreads();
+    // the tile's stayers have composites in [(prev[base], base), first composite of the next tile): movers below that range are
+    // counted by tile_lo, movers above it are after all of them
+    const int s_lo = tile_lo[blockIdx.x], s_hi = tile_lo[blockIdx.x + 1];
     const int lo = s_lo, hi = s_hi, cnt = hi - lo;
     const bool in_smem = cnt <= NS_SM_MOVERS;
     if (in_smem)
@@ -333,8 +390,8 @@ size_t fsg_nsort_bytes(int64_t n)
 {
     const int64_t ntiles = (n + NS_TILE - 1) / NS_TILE;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return al(sizeof(int) * (ntiles + 2)) + 2 * al(sizeof(int) * (n / 32 + 2)) + 4 * al(sizeof(int) * (size_t)n) + al(sizeof(int) * (size_t)ntiles * 256) +
-           al(sizeof(int) * 256) + 256;
+    return 2 * al(sizeof(int) * (ntiles + 2)) + 2 * al(sizeof(int) * (n / 32 + 2)) + 4 * al(sizeof(int) * (size_t)n) + al(sizeof(int) * (size_t)ntiles * 256) +
+           al(sizeof(int) * 512) + 256;
 }
 
 static NsBufs ns_layout(void *ws, int64_t n)
@@ -344,11 +401,12 @@ static NsBufs ns_layout(void *ws, int64_t n)
     char *p = (char *)ws;
     NsBufs B;
     B.tile_cnt = (int *)p; p += al(sizeof(int) * (ntiles + 2));
+    B.tile_lo = (int *)p; p += al(sizeof(int) * (ntiles + 2));
     B.grp_off = (int *)p; p += al(sizeof(int) * (n / 32 + 2));
     B.grp_mask = (unsigned *)p; p += al(sizeof(int) * (n / 32 + 2));
     for (int k = 0; k < 2; k++) { B.mk[k] = (int *)p; p += al(sizeof(int) * (size_t)n); B.ms[k] = (int *)p; p += al(sizeof(int) * (size_t)n); }
     B.hist = (int *)p; p += al(sizeof(int) * (size_t)ntiles * 256);
-    B.base = (int *)p; p += al(sizeof(int) * 256);
+    B.base = (int *)p; p += al(sizeof(int) * 512);
     B.M = B.tile_cnt + ntiles;
     return B;
 }
@@ -368,15 +426,17 @@ cudaError_t fsg_nsort(void *ws, const int *keys_new, const int *keys_prev, int *
     if (g < 1) g = 1;
     int cur = 0, nl = 3;
     for (int shift = 0; shift < bits; shift += 8) {
-        k_rs_hist<<<(unsigned)g, NS_THREADS, 0, s>>>(B.mk[cur], B.M, shift, B.hist);
-        k_rs_scan<<<1, 256, 0, s>>>(B.hist, B.M, B.base);
-        k_rs_scatter<<<(unsigned)g, NS_THREADS, 0, s>>>(B.mk[cur], B.ms[cur], B.mk[cur ^ 1], B.ms[cur ^ 1], B.M, shift, B.hist, B.base);
+        k_rs_hist<<<(unsigned)g, NS_THREADS, 0, s>>>(B.mk[cur], B.M, shift, B.hist, ntiles);
+        k_rs_colscan<<<256, 256, 0, s>>>(B.hist, B.M, ntiles, B.base);
+        k_rs_base<<<1, 256, 0, s>>>(B.base, B.base + 256);
+        k_rs_scatter<<<(unsigned)g, NS_THREADS, 0, s>>>(B.mk[cur], B.ms[cur], B.mk[cur ^ 1], B.ms[cur ^ 1], B.M, shift, B.hist, ntiles, B.base + 256);
         cur ^= 1;
-        nl += 3;
+        nl += 4;
     }
-    k_ns_place_stayers<<<(unsigned)ntiles, NS_THREADS, 0, s>>>(keys_new, keys_prev, n, B.mk[cur], B.ms[cur], B.M, B.grp_off, B.grp_mask, keys_out,
+    k_ns_tile_bounds<<<(unsigned)((ntiles + 1 + NS_THREADS - 1) / NS_THREADS), NS_THREADS, 0, s>>>(keys_prev, ntiles, B.mk[cur], B.ms[cur], B.M, B.tile_lo);
+    k_ns_place_stayers<<<(unsigned)ntiles, NS_THREADS, 0, s>>>(keys_new, keys_prev, n, B.mk[cur], B.ms[cur], B.tile_lo, B.grp_off, B.grp_mask, keys_out,
                                                              perm_out);
     k_ns_place_movers<<<(unsigned)g, NS_THREADS, 0, s>>>(keys_prev, n, B.mk[cur], B.ms[cur], B.M, B.grp_off, B.grp_mask, keys_out, perm_out);
-    if (launches) *launches += nl + 2;
+    if (launches) *launches += nl + 3;
     return cudaGetLastError();
 }

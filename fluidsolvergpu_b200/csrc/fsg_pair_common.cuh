@@ -42,6 +42,14 @@ __device__ __forceinline__ float rsqrt_fast(float x)
     return r;
 }
 
+// fma with the result saturated to [0, 1] (NaN -> +0): clamp and NaN filter at no instruction cost
+__device__ __forceinline__ float fma_sat(float a, float b, float c)
+{
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // Packed FP32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): one instruction works on the two home particles of a pass.
 // A scalar operand duplicated into both halves costs nothing — ptxas encodes it as a broadcast (`R4.F32`).
 typedef unsigned long long f32x2;

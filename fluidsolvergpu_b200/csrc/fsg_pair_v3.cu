@@ -130,12 +130,14 @@ __device__ __forceinline__ void v3_drain_batch(const V3Near &d, const V3Warp &W,
 
 // One batch of up to four passes (two home particles each, packed) over the NCH 32-candidate chunks of the tile.  The chunk
 // loop is straight-line code per chunk count: the candidate accumulators cw[] stay in fixed registers across the passes and
-// the chunks overlap in the pipeline.  M0 / M1 collect the near marks of the batch: bit 8 * pass + chunk.
+// the chunks overlap in the pipeline.  M0 / M1 collect the near marks of the batch: bit 8 * pass + (NCH - 1 - chunk).
 template <int NCH, bool HASB>
 __device__ __forceinline__ void v3_batch(const float4 *__restrict__ hp, const float4 *__restrict__ sp, const int kb, const int gcount,
                                          const int lane, const f32x2 ninvh, f32x2 (&cw)[V3_CH], float &hrow, unsigned &M0, unsigned &M1)
 {
-    const f32x2 two = pk2(2.f, 2.f), one = pk2(1.f, 1.f);
+    const f32x2 one = pk2(1.f, 1.f), mhalf = pk2(-0.5f, -0.5f);
+    float nih0, nih1;
+    upk2(ninvh, nih0, nih1);                                 // -1 / (2h)
 #pragma unroll 1
     for (int pp = 0; pp < 4; pp++) {
         const int k0 = kb + 2 * pp;
@@ -143,13 +145,13 @@ __device__ __forceinline__ void v3_batch(const float4 *__restrict__ hp, const fl
         const bool has1 = k0 + 1 < gcount;
         const float4 pi0 = hp[k0];
         float4 pi1 = hp[has1 ? k0 + 1 : k0];
-        if (!has1) pi1.x = -1e30f;                           // nothing is in range of it
+        if (!has1) pi1.x = -1e15f;                           // nothing is in range of it
         const f32x2 nhx = pk2(-pi0.x, -pi1.x), nhy = pk2(-pi0.y, -pi1.y), nhz = pk2(-pi0.z, -pi1.z);
         // float(!b_i)*BDENSFACTOR (FluidGPU.cu:276) for the home side, the homes' boundary flags for the candidate side
         const f32x2 ci = pk2(pi0.w < 0.f ? 0.f : 1.5f, pi1.w < 0.f ? 0.f : 1.5f);
         const f32x2 bi = pk2(pi0.w < 0.f ? 1.f : 0.f, pi1.w < 0.f ? 1.f : 0.f);
         f32x2 wacc = pk2(0.f, 0.f);
-        unsigned m0 = 0, m1 = 0;
+        unsigned m0 = 0, m1 = 0;                             // bit (NCH - 1 - chunk) SET = the candidate is NOT within h
 #pragma unroll
         for (int k = 0; k < NCH; k++) {
             const float4 pj = sp[k * 32];
@@ -158,17 +160,19 @@ __device__ __forceinline__ void v3_batch(const float4 *__restrict__ hp, const fl
             float d2a, d2b;
             upk2(d2p, d2a, d2b);
             const f32x2 r = mul2(d2p, pk2(rsqrt_fast(d2a), rsqrt_fast(d2b)));
-            float ta, tb;
-            upk2(fma2(r, ninvh, two), ta, tb);
-            // (2 - r/h)^3 clamped at 0: zero beyond 2h (FluidGPU.cu:236) and for d2 == 0 / the padding (NaN -> 0).
-            // Pairs with r <= h also get this OUTER-branch value; the near-pair pass adds the difference to the
-            // inner branch (FluidGPU.cu:13).
-            ta = fmaxf(ta, 0.f);
-            tb = fmaxf(tb, 0.f);
-            if (ta >= 1.f) m0 |= 1u << k;                  // 2 - r/h >= 1  <=>  0 < r <= h
-            if (tb >= 1.f) m1 |= 1u << k;
-            const f32x2 tt = pk2(ta, tb);
-            const f32x2 t3 = mul2(mul2(tt, tt), tt);
+            float ra, rb;
+            upk2(r, ra, rb);
+            // u = 1 - r/(2h) saturated to [0, 1] by the FMA itself: 0 beyond 2h (FluidGPU.cu:236) and for d2 == 0 (r = 0 * inf = NaN
+            // -> +0, the particle itself); the padding sits 1e15 away.  (2 - r/h)^3 = 8 u^3 — the 8 is folded into w_outer.
+            // Pairs with r <= h also get this OUTER-branch value; the near-pair pass adds the difference to the inner
+            // branch (FluidGPU.cu:13).  No compare, no min/max: the sign of u - 1/2 is shifted into the near marks.
+            const float ua = fma_sat(ra, nih0, 1.f), ub = fma_sat(rb, nih1, 1.f);
+            const f32x2 uu = pk2(ua, ub);
+            float va, vb;
+            upk2(add2(uu, mhalf), va, vb);                  // < 0  <=>  r > h
+            m0 = __funnelshift_l(__float_as_uint(va), m0, 1);
+            m1 = __funnelshift_l(__float_as_uint(vb), m1, 1);
+            const f32x2 t3 = mul2(mul2(uu, uu), uu);
             if (HASB) {
                 const float bjf = pj.w < 0.f ? 1.f : 0.f, cjf = pj.w < 0.f ? 0.f : 1.5f;
                 wacc = fma2(t3, fma2(ci, pk2(bjf, bjf), one), wacc);
@@ -178,6 +182,8 @@ __device__ __forceinline__ void v3_batch(const float4 *__restrict__ hp, const fl
                 cw[k] = add2(cw[k], t3);
             }
         }
+        m0 = ~m0 & ((1u << NCH) - 1u);                       // bit (NCH - 1 - chunk) set = within h
+        m1 = ~m1 & ((1u << NCH) - 1u);
         M0 |= m0 << (8 * pp);
         M1 |= m1 << (8 * pp);
 #pragma unroll
@@ -302,7 +308,7 @@ k_pair_v3(V3Args va)
         // padding up to the chunk count the sweep runs (whole chunks, at least 4: the sweep has no variant below)
         const int cpad = max((sub.ct + 31) & ~31, 128);
 #pragma unroll 1
-        for (int c = sub.ct + lane; c < cpad; c += 32) S.sp[c] = make_float4(1e30f, 1e30f, 1e30f, 0.f);
+        for (int c = sub.ct + lane; c < cpad; c += 32) S.sp[c] = make_float4(1e15f, 1e15f, 1e15f, 0.f);      // (finite d2: no NaN in the sweep)
         // the stage was read through the generic proxy two items ago; order those reads before the async writes
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -312,9 +318,9 @@ k_pair_v3(V3Args va)
         if (lane == 5) bulk_g2s(&S.hp[0], a.A.posd + sub.hs, (unsigned)sub.gcount * 16u, &W.full[stage]);
     };
 
-    const float w_outer = d.w_c * 0.25f;
+    const float w_outer = d.w_c * 2.f;                         // w_c / 4 * 8: the sweep sums u^3 with u = (2 - r/h) / 2
     const float inv_h = d.inv_h;
-    const f32x2 ninvh = pk2(-inv_h, -inv_h);
+    const f32x2 ninvh = pk2(-0.5f * inv_h, -0.5f * inv_h);
     V3Near nc;
     nc.inv_h = d.inv_h; nc.w_c = d.w_c; nc.hf = d.hf; nc.dw_c = d.dw_c; nc.eps = d.eps; nc.visc_c = d.visc_c; nc.visc_q = d.visc_q;
     nc.ab = 1.f + (float)d.alpha_boundary;
@@ -393,11 +399,11 @@ k_pair_v3(V3Args va)
                 int at = qn + incl - mine;
                 for (unsigned m = a0; m; m &= m - 1) {
                     const int p = __ffs(m) - 1;
-                    W.q[at++] = ((unsigned)(kb + 2 * (p >> 3)) << 16) | (unsigned)((p & 7) * 32 + lane);
+                    W.q[at++] = ((unsigned)(kb + 2 * (p >> 3)) << 16) | (unsigned)((nch - 1 - (p & 7)) * 32 + lane);
                 }
                 for (unsigned m = a1; m; m &= m - 1) {
                     const int p = __ffs(m) - 1;
-                    W.q[at++] = ((unsigned)(kb + 2 * (p >> 3) + 1) << 16) | (unsigned)((p & 7) * 32 + lane);
+                    W.q[at++] = ((unsigned)(kb + 2 * (p >> 3) + 1) << 16) | (unsigned)((nch - 1 - (p & 7)) * 32 + lane);
                 }
                 qn += total;
             }

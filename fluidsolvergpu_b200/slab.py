@@ -404,7 +404,8 @@ def parity_against_single(grid: int, rank: int, world: int, device: int, exchang
     hist = layer_hist_from_positions(base, state["pos"])
     cuts = slab_cuts(hist, world)
     owned = [int(hist[a:b].sum()) for a, b in cuts]
-    cap = max(int(max(owned) * 1.1) + 3 * int(hist.max()) + 65536, n + 64)      # (the upload hands every rank the whole scene)
+    # (the upload hands every rank the whole scene: until the first sort trims the foreign slots, arrivals are appended behind all n)
+    cap = max(int(max(owned) * 1.1), n) + 4 * int(hist.max()) + 65536
     cap_m, cap_g = message_caps(hist, cuts)
     cap_m = cap_g                     # with the drift whole lattice planes cross a face within one step
     ex = DistExchange()

@@ -869,3 +869,48 @@ def test_nearly_sorted_key_sort_gives_the_radix_sort_result(fsg, monkeypatch):
             assert np.array_equal(a[f], b[f]), f
         for x, y in zip(ta, tb):
             assert np.array_equal(x, y)
+
+
+def test_deferred_update_gives_the_same_bits(fsg, monkeypatch):
+    """fsg_step's deferred-update schedule (single-device base contexts, uncapped fp32 kernels): Particle::update of step n runs inside
+    the reorder of step n + 1, the next step's bin ids are predicted before the pair kernel runs (predicted_key), and downloads
+    materialise the post-update state on demand.  With the deterministic gather kernel the whole state must be bit for bit what the
+    separate k_update pass gives (FSG_DEFER_UPDATE=0) — including particles that leave the bin grid (parked), boundary particles,
+    accumulators carried in by the upload, and downloads in the middle of a run."""
+    cases = []
+    cfg = fsg.scenes.plume_config(24)
+    cfg.pair_mode = 1
+    st = fsg.scenes.plume_scene(cfg)
+    st["vel"] = (st["vel"] * np.float32(40.0)).astype(np.float32)
+    st["vel"][::7, 0] += np.float32(900.0)                       # some particles leave the grid within a few steps
+    cases.append((cfg, st, (1, 2, 5, 9)))
+    cfg = fsg.scenes.plume_config(17)
+    cfg.origin = -1.02
+    cfg.pair_mode = 1
+    st = fsg.scenes.random_base_scene(6000, 21, box=((-0.4, 0.4),) * 3, spacing=0.05, jitter=0.012, boundary_frac=0.2, vel_scale=3.0)
+    st["newdens"] = np.full(st["pos"].shape[0], 7.0, np.float32)  # accumulators carried in by the upload (SURVEY.md B.1)
+    cases.append((cfg, st, (1, 3, 4)))
+    for cfg, state, marks in cases:
+        cfg.capacity = state["pos"].shape[0]
+        runs = []
+        for mode in ("1", "0"):
+            monkeypatch.setenv("FSG_DEFER_UPDATE", mode)
+            outs = []
+            with fsg.FluidSolver(cfg) as s:
+                s.upload(state)
+                done = 0
+                for k in marks:
+                    s.step(k - done)
+                    done = k
+                    outs.append((s.download(), s.tables(), s.export_viz(), s.stats()["n_live"]))
+            runs.append(outs)
+        parked = 0
+        for (a, ta, va, la), (b, tb, vb, lb) in zip(*runs):
+            for f in FIELDS + ("index", "cell", "boundary", "newdens", "newdelpress"):
+                assert np.array_equal(a[f], b[f]), f
+            for x, y in zip(ta + va, tb + vb):
+                assert np.array_equal(x, y)
+            assert la == lb
+            parked = max(parked, int((a["cell"] >= cfg.grid ** 3).sum()))
+        if cfg.grid == 24:
+            assert parked > 0, "the scene was meant to park particles outside the grid"
