@@ -131,6 +131,8 @@ __device__ __forceinline__ void v3_drain_batch(const V3Near &d, const V3Warp &W,
 // One batch of up to four passes (two home particles each, packed) over the NCH 32-candidate chunks of the tile.  The chunk
 // loop is straight-line code per chunk count: the candidate accumulators cw[] stay in fixed registers across the passes and
 // the chunks overlap in the pipeline.  M0 / M1 collect the near marks of the batch: bit 8 * pass + (NCH - 1 - chunk).
+template <bool HASB> __device__ __forceinline__ constexpr float V3_FIX() { return HASB ? 4194304.f : 8388608.f; }      // 2^22, 2^23
+
 template <int NCH, bool HASB>
 __device__ __forceinline__ void v3_batch(const float4 *__restrict__ hp, const float4 *__restrict__ sp, const int kb, const int gcount,
                                          const int lane, const f32x2 ninvh, f32x2 (&cw)[V3_CH], float &hrow, unsigned &M0, unsigned &M1)
@@ -186,17 +188,17 @@ __device__ __forceinline__ void v3_batch(const float4 *__restrict__ hp, const fl
         m1 = ~m1 & ((1u << NCH) - 1u);
         M0 |= m0 << (8 * pp);
         M1 |= m1 << (8 * pp);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            float w0, w1;
-            upk2(wacc, w0, w1);
-            wacc = add2(wacc, pk2(__shfl_xor_sync(FULL, w0, o), __shfl_xor_sync(FULL, w1, o)));
-        }
+        // Home side: the 32 lanes' partial sums of the two home particles are added with the warp-wide INTEGER reduction (one REDUX
+        // each instead of five shuffle + add rounds): fixed point with 23 (22 with boundary factors) fraction bits.  A pass adds at
+        // most 256 terms u^3 <= 1 (x 2.5 with boundary factors), so the 32-bit sum cannot overflow: 256 * 2^23 = 2^31,
+        // 640 * 2^22 < 2^32; the rounding (<= 6e-8 per lane and pass, absolute) is below the float rounding of sums of this size.
+        // The running total over passes and tiles stays a float.  Order independent: this side of the sums is deterministic.
         {
             float w0, w1;
-            upk2(wacc, w0, w1);
-            if (lane == k0) hrow += w0;
-            if (lane == k0 + 1) hrow += w1;
+            upk2(mul2(wacc, pk2(V3_FIX<HASB>(), V3_FIX<HASB>())), w0, w1);
+            const unsigned s0 = __reduce_add_sync(FULL, __float2uint_rn(w0)), s1 = __reduce_add_sync(FULL, __float2uint_rn(w1));
+            if (lane == k0) hrow += (float)s0;
+            if (lane == k0 + 1) hrow += (float)s1;
         }
     }
 }
@@ -324,7 +326,7 @@ k_pair_v3(V3Args va)
     V3Near nc;
     nc.inv_h = d.inv_h; nc.w_c = d.w_c; nc.hf = d.hf; nc.dw_c = d.dw_c; nc.eps = d.eps; nc.visc_c = d.visc_c; nc.visc_q = d.visc_q;
     nc.ab = 1.f + (float)d.alpha_boundary;
-    float hrow = 0.f;                                          // lane k: sum of outer-branch terms of home particle k of the group
+    float hrow = 0.f;                                          // lane k: sum of outer-branch terms of home particle k of the group (x 2^23 / 2^22)
 
     V3Sub cur, nxt;
     cur.hs = cur.gcount = cur.t0 = cur.ct = cur.flags = cur.hnlim = 0;
@@ -368,10 +370,25 @@ k_pair_v3(V3Args va)
             //      neighbourhood) goes through in 32 slices of one (pass, chunk) each — at most 64 marks. ----
             const bool last_batch = kb + 8 >= gcount;
             const int nsl = __reduce_add_sync(FULL, __popc(M0) + __popc(M1)) > V3_QCAP - 32 ? 32 : 1;
+            // processes queued pairs 32 at a time: whole batches only (`all` false: make room), or everything
+            auto drain = [&](const bool all) {
+                __syncwarp();
+                int qh = 0;
+                while (qn - qh >= 32 || (all && qh < qn)) {
+                    v3_drain_batch(nc, W, stage, cur.hs, cur.t0, cur.hnlim, a.A.velp, sums, qh, qn, lane);
+                    qh += 32;
+                }
+                const int left = max(qn - qh, 0);
+                unsigned ent = 0;
+                if (lane < left) ent = W.q[qh + lane];
+                __syncwarp();
+                if (lane < left) W.q[lane] = ent;
+                qn = left;
+                __syncwarp();
+            };
 #pragma unroll 1
-            for (int sl = 0; sl <= nsl; sl++) {
-                const bool fin = sl == nsl;                          // no append: only the queue check after the last slice
-                const unsigned smask = fin ? 0u : nsl == 1 ? 0xffffffffu : 1u << sl;
+            for (int sl = 0; sl < nsl; sl++) {
+                const unsigned smask = nsl == 1 ? 0xffffffffu : 1u << sl;
                 const unsigned a0 = M0 & smask, a1 = M1 & smask;
                 const int mine = __popc(a0) + __popc(a1);
                 int incl = mine;
@@ -381,21 +398,7 @@ k_pair_v3(V3Args va)
                     if (lane >= o) incl += t;
                 }
                 const int total = __shfl_sync(FULL, incl, 31);
-                if (fin ? (last_batch && qn > 0) : (qn + total > V3_QCAP)) {
-                    __syncwarp();
-                    int qh = 0;
-                    while (qn - qh >= 32 || (fin && qh < qn)) {
-                        v3_drain_batch(nc, W, stage, cur.hs, cur.t0, cur.hnlim, a.A.velp, sums, qh, qn, lane);
-                        qh += 32;
-                    }
-                    const int left = max(qn - qh, 0);
-                    unsigned ent = 0;
-                    if (lane < left) ent = W.q[qh + lane];
-                    __syncwarp();
-                    if (lane < left) W.q[lane] = ent;
-                    qn = left;
-                    __syncwarp();
-                }
+                if (qn + total > V3_QCAP) drain(false);
                 int at = qn + incl - mine;
                 for (unsigned m = a0; m; m &= m - 1) {
                     const int p = __ffs(m) - 1;
@@ -407,6 +410,7 @@ k_pair_v3(V3Args va)
                 }
                 qn += total;
             }
+            if (last_batch && qn > 0) drain(true);
         }
         // ---- candidate side of the sweep: one float reduction per candidate of the other bins ----
 #pragma unroll
@@ -420,7 +424,7 @@ k_pair_v3(V3Args va)
             }
         }
         // ---- home side of the sweep, once per group ----
-        if ((cur.flags & 2) && lane < gcount) red_add_f32(&sums[cur.hs + lane].x, hrow * w_outer);
+        if ((cur.flags & 2) && lane < gcount) red_add_f32(&sums[cur.hs + lane].x, hrow * (w_outer / V3_FIX<HASB>()));
         __syncwarp();
         if (!hnx) break;
         cur = nxt;

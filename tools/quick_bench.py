@@ -15,6 +15,7 @@ for G in [int(a) for a in sys.argv[1:]] or [64, 128, 256]:
         stream = torch.cuda.ExternalStream(s.stream())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         K = 10
+        s.set_profiling(True)
         with torch.cuda.stream(stream):
             e0.record(stream)
             s.step(K, sync=False)
@@ -22,6 +23,8 @@ for G in [int(a) for a in sys.argv[1:]] or [64, 128, 256]:
         s.sync()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / K
+        ph = s.phase_ms()
+        ph = {k: round(v / max(1, ph["steps"]), 4) for k, v in ph.items() if k != "steps"}
         print(json.dumps(dict(G=G, n=n, ms_per_step=ms, particle_steps_per_s=n / ms * 1e3, cell_updates_per_s=G**3 / ms * 1e3,
                               pairs_tested=st["pairs_tested"], pairs_in_range=st["pairs_in_range"], occupied=st["occupied_bins"],
-                              hbm_frac=272 * n / (ms * 1e-3) / 6544.7e9)))
+                              hbm_frac=272 * n / (ms * 1e-3) / 6544.7e9, phases=ph)))
