@@ -121,8 +121,10 @@ __device__ __forceinline__ void v3_drain_batch(const V3Near &d, const V3Warp &W,
         unsigned ent = W.q[e];
         const int k = (int)(ent >> 16), c = (int)(ent & 0xffffu);
         const int i = hs + k, j = v3_global_slot(W, stage, c);
+        const float *P = reinterpret_cast<const float *>(&S.hp[0]) + (k >> 1) * 8 + (k & 1);     // packed homes, see the main loop
+        const float4 pi = make_float4(-P[0], -P[2], -P[4], P[6]);
         float4 hv, cv;
-        v3_near_pair(d, S.hp[k], velp[i], S.sp[c], velp[j], hv, cv);
+        v3_near_pair(d, pi, velp[i], S.sp[c], velp[j], hv, cv);
         red_add_v4(sums + i, hv);
         if (t0 + c >= hnlim) red_add_v4(sums + j, cv);
     }
@@ -144,14 +146,11 @@ __device__ __forceinline__ void v3_batch(const float4 *__restrict__ hp, const fl
     for (int pp = 0; pp < 4; pp++) {
         const int k0 = kb + 2 * pp;
         if (k0 >= gcount) break;
-        const bool has1 = k0 + 1 < gcount;
-        const float4 pi0 = hp[k0];
-        float4 pi1 = hp[has1 ? k0 + 1 : k0];
-        if (!has1) pi1.x = -1e15f;                           // nothing is in range of it
-        const f32x2 nhx = pk2(-pi0.x, -pi1.x), nhy = pk2(-pi0.y, -pi1.y), nhz = pk2(-pi0.z, -pi1.z);
+        const float4 ha = hp[k0], hb = hp[k0 + 1];             // packed by the caller: (-x0, -x1, -y0, -y1), (-z0, -z1, w0, w1)
+        const f32x2 nhx = pk2(ha.x, ha.y), nhy = pk2(ha.z, ha.w), nhz = pk2(hb.x, hb.y);
         // float(!b_i)*BDENSFACTOR (FluidGPU.cu:276) for the home side, the homes' boundary flags for the candidate side
-        const f32x2 ci = pk2(pi0.w < 0.f ? 0.f : 1.5f, pi1.w < 0.f ? 0.f : 1.5f);
-        const f32x2 bi = pk2(pi0.w < 0.f ? 1.f : 0.f, pi1.w < 0.f ? 1.f : 0.f);
+        const f32x2 ci = pk2(hb.z < 0.f ? 0.f : 1.5f, hb.w < 0.f ? 0.f : 1.5f);
+        const f32x2 bi = pk2(hb.z < 0.f ? 1.f : 0.f, hb.w < 0.f ? 1.f : 0.f);
         f32x2 wacc = pk2(0.f, 0.f);
         unsigned m0 = 0, m1 = 0;                             // bit (NCH - 1 - chunk) SET = the candidate is NOT within h
 #pragma unroll
@@ -303,9 +302,15 @@ k_pair_v3(V3Args va)
         V3Stage &S = W.st[stage];
         const int lo = max(excl, sub.t0), hi = min(excl + rp, sub.t0 + sub.ct);
         const bool used = lane < 5 && rp > 0 && hi > lo;
-        if (lane < 8) {
-            W.run_lo[stage][lane] = used ? lo - sub.t0 : V3_TILE;
-            W.run_j[stage][lane] = used ? rs + (lo - excl) : 0;
+        // the runs this tile holds, COMPACTED (ascending tile slot): entry q = (first tile slot, global slot of it); unused entries
+        // hold V3_TILE, so "the last entry with run_lo <= c" is candidate c's run and the table can be walked monotonically
+        const unsigned um = __ballot_sync(FULL, used);
+        if (lane < 8) { W.run_lo[stage][lane] = V3_TILE; W.run_j[stage][lane] = 0; }
+        __syncwarp();
+        if (used) {
+            const int q = __popc(um & ((1u << lane) - 1u));
+            W.run_lo[stage][q] = lo - sub.t0;
+            W.run_j[stage][q] = rs + (lo - excl);
         }
         // padding up to the chunk count the sweep runs (whole chunks, at least 4: the sweep has no variant below)
         const int cpad = max((sub.ct + 31) & ~31, 128);
@@ -343,8 +348,19 @@ k_pair_v3(V3Args va)
         }
         mbar_wait(&W.full[stage], (n >> 1) & 1);
 
-        const V3Stage &S = W.st[stage];
+        V3Stage &S = W.st[stage];
         const int gcount = cur.gcount, ct = cur.ct;
+        {
+            // the home particles, re-packed in place the way a pass reads them: pass p (home particles 2p, 2p + 1) =
+            // {(-x0, -x1, -y0, -y1), (-z0, -z1, w0, w1)} — two 16-byte loads give the packed operands, no register shuffling per pass.
+            // A home particle that does not exist sits 1e15 away (nothing is in range of it).
+            float4 me = S.hp[lane];
+            __syncwarp();
+            if (lane >= gcount) me = make_float4(-1e15f, -1e15f, -1e15f, 0.f);
+            float *P = reinterpret_cast<float *>(&S.hp[0]) + (lane >> 1) * 8 + (lane & 1);
+            P[0] = -me.x; P[2] = -me.y; P[4] = -me.z; P[6] = me.w;
+            __syncwarp();
+        }
         const int nch = max((ct + 31) >> 5, 4);
         if (cur.flags & 1) hrow = 0.f;
         f32x2 cw[V3_CH];                                       // candidate of chunk k of this lane: its sum over the home particles
@@ -400,27 +416,34 @@ k_pair_v3(V3Args va)
                 const int total = __shfl_sync(FULL, incl, 31);
                 if (qn + total > V3_QCAP) drain(false);
                 int at = qn + incl - mine;
-                for (unsigned m = a0; m; m &= m - 1) {
-                    const int p = __ffs(m) - 1;
-                    W.q[at++] = ((unsigned)(kb + 2 * (p >> 3)) << 16) | (unsigned)((nch - 1 - (p & 7)) * 32 + lane);
-                }
-                for (unsigned m = a1; m; m &= m - 1) {
-                    const int p = __ffs(m) - 1;
-                    W.q[at++] = ((unsigned)(kb + 2 * (p >> 3) + 1) << 16) | (unsigned)((nch - 1 - (p & 7)) * 32 + lane);
+                // one loop over both halves' marks (bit 32 * half + 8 * pass + pos): its trip count is the largest number of marks
+                // any lane holds, not the sum of the two halves' maxima
+                for (unsigned long long m = (unsigned long long)a0 | ((unsigned long long)a1 << 32); m; m &= m - 1) {
+                    const int p = __ffsll((long long)m) - 1;
+                    W.q[at++] = ((unsigned)(kb + ((p >> 2) & 6) + (p >> 5)) << 16) | (unsigned)((nch - 1 - (p & 7)) * 32 + lane);
                 }
                 qn += total;
             }
             if (last_batch && qn > 0) drain(true);
         }
         // ---- candidate side of the sweep: one float reduction per candidate of the other bins ----
+        {
+            // this lane's candidates lane, lane + 32, ... ascend, and so do the runs of the table: walk it instead of searching per chunk
+            int fq = 0, fnext = W.run_lo[stage][1], fbase = W.run_j[stage][0] - W.run_lo[stage][0];
 #pragma unroll
-        for (int k = 0; k < V3_CH; k++) {
-            if (k < nch) {
-                const int c = k * 32 + lane;
-                float lo, hi;
-                upk2(cw[k], lo, hi);
-                const float v = lo + hi;
-                if (c < ct && cur.t0 + c >= cur.hnlim && v != 0.f) red_add_f32(&sums[v3_global_slot(W, stage, c)].x, v * w_outer);
+            for (int k = 0; k < V3_CH; k++) {
+                if (k < nch) {
+                    const int c = k * 32 + lane;
+                    while (c >= fnext) {                       // (entries 5..7 hold V3_TILE: the walk stops by itself)
+                        fq++;
+                        fbase = W.run_j[stage][fq] - W.run_lo[stage][fq];
+                        fnext = W.run_lo[stage][fq + 1];
+                    }
+                    float lo, hi;
+                    upk2(cw[k], lo, hi);
+                    const float v = lo + hi;
+                    if (c < ct && cur.t0 + c >= cur.hnlim && v != 0.f) red_add_f32(&sums[fbase + c].x, v * w_outer);
+                }
             }
         }
         // ---- home side of the sweep, once per group ----
