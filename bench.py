@@ -280,6 +280,44 @@ def reference_gpu_leg(fsg, torch, steps=100):
     return res
 
 
+def frame_output_leg(fsg, torch, grid=128, steps=60, every=20):
+    """Frame output beside the step loop: the plume at grid^3, `steps` steps with a legacy-VTK ASCII frame
+    (positions + 2 scalars, "%20.12e " per number: the reference's format, solver-unidyn.cu:472-493) every `every` steps — none,
+    synchronous (fsg_write_frame, the reference's way) and asynchronous (fsg_write_frame_async: export kernel + copy stream +
+    writer thread).  Wall clock per step including the final wait for the files."""
+    import shutil
+    import tempfile
+    cfg = fsg.scenes.plume_config(grid)
+    cfg.capacity = fsg.scenes.plume_count(cfg, SPACING)
+    out = {"grid": grid, "particles": int(cfg.capacity), "steps": steps, "frame_every": every}
+    tmp = tempfile.mkdtemp(prefix="fsg_frames_")
+    try:
+        for mode in ("none", "sync", "async"):
+            with fsg.FluidSolver(cfg) as s:
+                s.scene_plume(SPACING, JITTER, SEED)
+                s.step(3)
+                t0 = time.perf_counter()
+                loop_s = 0.0
+                for k in range(1, steps + 1):
+                    s.step(1, sync=False)
+                    if mode != "none" and k % every == 0:
+                        name = f"{tmp}/{mode}_{k}.vtk"
+                        (s.write_frame if mode == "sync" else s.write_frame_async)(name)
+                s.sync()
+                loop_s = time.perf_counter() - t0
+                if mode == "async":
+                    s.frame_wait()
+                total_s = time.perf_counter() - t0
+            out[mode] = {"ms_per_step_loop": loop_s / steps * 1e3, "ms_per_step_incl_final_wait": total_s / steps * 1e3}
+        f0 = next(pathlib.Path(tmp).glob("sync_*.vtk"))
+        out["frame_bytes"] = f0.stat().st_size
+        out["files_identical"] = all((pathlib.Path(tmp) / f"sync_{k}.vtk").stat().st_size == (pathlib.Path(tmp) / f"async_{k}.vtk").stat().st_size
+                                     for k in range(every, steps + 1, every))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def workload_config(grid, n, gpus):
     return {"workload": f"synthetic plume, {grid}^3 bins (CELLSIZE 0.12 = 2h, lattice spacing {SPACING}, jitter {JITTER}, seed {SEED}), "
                         f"base SPH step: key sort + reorder/bin tables + pair sums + EOS/integrate/re-bin",
@@ -501,6 +539,11 @@ def fsg_arm(args):
     if rank == 0 and world == 1 and not args.no_reference_gpu:
         refgpu = reference_gpu_leg(fsg, torch)
 
+    # ---- frame output beside the step loop (N = 1) ----
+    frames = None
+    if rank == 0 and world == 1 and not args.no_frames:
+        frames = frame_output_leg(fsg, torch)
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -529,6 +572,8 @@ def fsg_arm(args):
             line["grid1024"] = g1024
         if refgpu is not None:
             line["reference_gpu"] = refgpu
+        if frames is not None:
+            line["frame_output"] = frames
         print(json.dumps(line))
     if solver is not None:
         solver.close()
@@ -699,6 +744,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle-sampled parity check (N=1) / the slab-vs-single check (N>1)")
     ap.add_argument("--parity-bins", type=int, default=256)
+    ap.add_argument("--no-frames", action="store_true", help="skip the frame-output leg (N=1)")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref) beside libfsg")
     ap.add_argument("--grid1024-steps", type=int, default=5, help="steps of the short 1024^3 leg (0 = off)")
     ap.add_argument("--e2e-contexts", type=int, default=3,

@@ -70,6 +70,8 @@ SIGNATURES = {
     "fsg_device_ptr": (C.c_int, [P, C.c_int, C.POINTER(P)]),
     "fsg_write_point_mesh": (C.c_int, [C.c_char_p, C.c_int, C.c_int, P, C.c_int, P, P, P]),
     "fsg_write_frame": (C.c_int, [P, C.c_char_p, C.c_int]),
+    "fsg_write_frame_async": (C.c_int, [P, C.c_char_p, C.c_int]),
+    "fsg_frame_wait": (C.c_int, [P, C.POINTER(C.c_int64)]),
     "fsg_slab_pack": (C.c_int, [P, P, P, C.c_int64, C.c_int64]),
     "fsg_slab_unpack": (C.c_int, [P, P, P, C.c_int64, C.c_int64]),
     "fsg_slab_check": (C.c_int, [P, C.POINTER(C.c_int64 * 9)]),

@@ -145,6 +145,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
 {
     if (!c) return FSG_E_INVALID;
     cudaSetDevice(c->device);
+    fsg_frame_writer_destroy(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_state(c->A);
     free_state(c->B);

@@ -50,6 +50,8 @@ struct FsgState {
     float4 *mix;     // unidyn model only: (solid, fluid, -, -)   FluidGPU-unidyn.cuh:180-181
 };
 
+struct FsgFrameWriter;        // fsg_frame.cu: copy stream, pinned staging slots and the writer thread of the asynchronous frame output
+
 struct fsg_ctx {
     fsg_config cfg;
     FsgDev dev;
@@ -110,6 +112,7 @@ struct fsg_ctx {
     int ns_mode;        // -1 not decided yet, 0 off, 1 on (FSG_SORT_MERGE)
     bool keys_prev_valid;   // keysA holds the sorted keys of the step that produced B / keysB (same slot order)
     int64_t ns_used;
+    FsgFrameWriter *frame_writer;   // created by the first fsg_write_frame_async
     void *stage;        // device staging area for host<->device conversion
     size_t stage_bytes;
     size_t sort_tmp_bytes;
@@ -174,6 +177,7 @@ cudaError_t fsg_launch_unpack_aos_unidyn(const unsigned char *aos, int64_t n, Fs
 cudaError_t fsg_launch_pack_aos_unidyn(unsigned char *aos, int64_t n, FsgState st, const float4 *carry, const int *keys, const FsgDev &d,
                                        cudaStream_t s);
 
+void fsg_frame_writer_destroy(fsg_ctx *c);   // fsg_frame.cu: writes the pending frames, stops the writer thread, frees its buffers
 int fsg_materialize(fsg_ctx *c);           // fsg_api.cu: makes B / keysB the post-update state (no-op unless the update is deferred)
 void fsg_derive_constants(const fsg_config &cfg, FsgDev &d);
 

@@ -161,6 +161,16 @@ class FluidSolver:
         """The VTK frame the drivers write after a step (solver-unidyn.cu:472-493), byte-compatible with visit_writer."""
         self._check(self._lib.fsg_write_frame(self._ctx, str(filename).encode(), int(binary)), "fsg_write_frame")
 
+    def write_frame_async(self, filename: str, binary: bool = False):
+        """write_frame off the critical path: export kernel + copy stream + writer thread (fsg_write_frame_async)."""
+        self._check(self._lib.fsg_write_frame_async(self._ctx, str(filename).encode(), int(binary)), "fsg_write_frame_async")
+
+    def frame_wait(self) -> int:
+        """Blocks until every asynchronous frame is on disk; returns how many have been written since the context was created."""
+        n = C.c_int64(0)
+        self._check(self._lib.fsg_frame_wait(self._ctx, C.byref(n)), "fsg_frame_wait")
+        return n.value
+
     def tables(self):
         n = self.stats()["n"]
         cells = np.empty(n, np.int32)

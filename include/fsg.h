@@ -191,6 +191,12 @@ FSG_API int  fsg_device_ptr(fsg_ctx *ctx, int which, void **ptr);
 FSG_API int  fsg_write_point_mesh(const char *filename, int use_binary, int npts, const float *pts, int nvars, const int *vardim,
                                   const char *const *varnames, const float *const *vars);
 FSG_API int  fsg_write_frame(fsg_ctx *ctx, const char *filename, int use_binary);
+/* The same frame OFF the step loop's critical path (the reference dumps synchronously inside its time loop, solver-unidyn.cu:472-493):
+ * one small export kernel on the context's stream, the device-to-host copy on a second stream behind an event into one of two pinned
+ * staging slots, formatting and file I/O on a writer thread.  Returns at once; a third frame in flight waits for the oldest one.
+ * fsg_frame_wait blocks until every frame is on disk, gives the number written so far and returns (and clears) the first error. */
+FSG_API int  fsg_write_frame_async(fsg_ctx *ctx, const char *filename, int use_binary);
+FSG_API int  fsg_frame_wait(fsg_ctx *ctx, int64_t *frames_written);
 
 /* ---- slab decomposition along x (world > 1): the multi-device hand-off of solver-unidyn.cu:396-470 ----
  * Every step of a slab context is   fsg_slab_pack -> (caller moves the two messages to the x-neighbours,

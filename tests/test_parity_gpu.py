@@ -914,3 +914,25 @@ def test_deferred_update_gives_the_same_bits(fsg, monkeypatch):
             parked = max(parked, int((a["cell"] >= cfg.grid ** 3).sum()))
         if cfg.grid == 24:
             assert parked > 0, "the scene was meant to park particles outside the grid"
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_unidyn_bookkeeping_kernels_behave_like_the_reference(seed):
+    """find_idx / mem_shift / count_after_merge (FluidGPU-unidyn.cu:499-562): the same driver (oracle/ref_bookkeeping.cu, written
+    against FluidGPU-unidyn.cuh, launching the kernels with <<<>>> like solver-unidyn.cu:341,404-466) linked once against the
+    reference's own kernel object and once against fsg_compat_unidyn.o + libfsg.so must print the same thing: the owned / transfer
+    index ranges of both slabs, the live count before the parked tail, and the shifted Particle records byte for byte."""
+    import json
+    import subprocess
+    ref = GOLD.parents[1] / "oracle" / "_ref" / "ref_bookkeeping"
+    ours = GOLD.parents[1] / "oracle" / "_ref" / "compat_bookkeeping"
+    if not (ref.exists() and ours.exists()):
+        pytest.skip("oracle/_ref/*_bookkeeping are built where the reference sources are available")
+    a = subprocess.check_output([str(ref), str(seed)], timeout=120).decode().strip().splitlines()[-1]
+    b = subprocess.check_output([str(ours), str(seed)], timeout=120).decode().strip().splitlines()[-1]
+    ja, jb = json.loads(a), json.loads(b)
+    assert ja == jb, (ja, jb)
+    assert ja["mem_shift_as_expected"] and ja["mem_shift_zero_is_noop"] and ja["sizeof_particle"] == 340
+    assert 0 < ja["newsize"] < ja["npts"]
+    # both slabs found their ranges (nothing left at the preset)
+    assert all(v != -7 for v in ja["find_idx_dev0"][:2] + ja["find_idx_dev0"][3:]) and all(v != -7 for v in ja["find_idx_dev1"])
