@@ -40,3 +40,32 @@ def test_slab_processes_match_single_context(exchange):
         assert r["bit_exact"] and r["cells_equal_frac"] == 1.0, r
         assert r["max_rel_l2"] <= 1e-5, r
         assert r["migrated"] > 0, "the drift was meant to carry particles across the slab faces"
+
+
+def test_the_real_unidyn_driver_links_and_runs_against_libfsg(tmp_path):
+    """solver-unidyn.cu itself (its main(), scene, 100 of its 1450 steps, frames every 20 steps into anim-uni/) linked against
+    fsg_compat_unidyn.o + libfsg.so instead of FluidGPU-unidyn.o, beside the same driver with the reference's own kernels.  The
+    driver indexes per-device arrays for TWO devices whatever it then uses (solver-unidyn.cu:86,120,308-310), so it is only run
+    where two GPUs are visible.  The scene is smooth: frames agree to 1e-4 (the reference's own run-to-run noise is ~6e-6)."""
+    import numpy as np
+    import torch
+    from test_parity_gpu import _read_vtk_ascii, run_real_driver
+    if torch.cuda.device_count() < 2:
+        pytest.skip("solver-unidyn.cu is only memory-safe with two visible GPUs")
+    ref_exe, our_exe = ROOT / "oracle" / "_ref" / "solver_unidyn_ref", ROOT / "oracle" / "_ref" / "solver_unidyn_compat"
+    if not (ref_exe.exists() and our_exe.exists()):
+        pytest.skip("oracle/_ref/solver_unidyn_* are built where the reference sources are available")
+    for d in ("compat", "ref"):
+        (tmp_path / d / "anim-uni").mkdir(parents=True)
+    out = run_real_driver(our_exe, tmp_path / "compat")
+    assert "t= 99" in out and "libfsg compat" not in out
+    run_real_driver(ref_exe, tmp_path / "ref")
+    for t in (20, 40, 60, 80):
+        a, b = (tmp_path / d / "anim-uni" / f"anim_s_GPU0_{t}.vtk" for d in ("compat", "ref"))
+        assert a.exists() and b.exists(), t
+        (pa, ma, sa), (pb, mb, sb) = _read_vtk_ascii(a), _read_vtk_ascii(b)
+        assert pa.shape == pb.shape
+        oa, ob = np.lexsort(pa.T[::-1]), np.lexsort(pb.T[::-1])
+        err = float(np.sqrt(((pa[oa] - pb[ob]) ** 2).sum() / (pb ** 2).sum()))
+        assert err <= 1e-4, (t, err)
+        assert np.array_equal(ma, mb)
