@@ -69,6 +69,13 @@ int main(int argc, char **argv)
         const int nrec = 1000, left = 300, right = 811, shifts = 123;
         std::vector<unsigned char> rec((size_t)nrec * sizeof(Particle));
         for (size_t i = 0; i < rec.size(); i++) rec[i] = (unsigned char)(rand() & 0xff);
+        /* the reference moves records by Particle assignment: padding bytes (317-319, 338-339 of the unidyn record, FluidGPU-unidyn.cuh
+           offsets in SURVEY.md §8 a1) need not travel and bools are only defined for 0 / 1 — keep both out of the comparison */
+        static const int pad[] = {317, 318, 319, 338, 339}, bools[] = {316, 336, 337};
+        for (int r = 0; r < nrec; r++) {
+            for (int p : pad) rec[(size_t)r * sizeof(Particle) + p] = 0;
+            for (int b : bools) rec[(size_t)r * sizeof(Particle) + b] &= 1;
+        }
         Particle *d_p, *d_b;
         CK(cudaMalloc(&d_p, rec.size()));
         CK(cudaMalloc(&d_b, rec.size()));
@@ -78,6 +85,7 @@ int main(int argc, char **argv)
         CK(cudaDeviceSynchronize());
         std::vector<unsigned char> out(rec.size());
         CK(cudaMemcpy(out.data(), d_p, rec.size(), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < nrec; r++) for (int p : pad) out[(size_t)r * sizeof(Particle) + p] = 0;
         /* expectation independent of either implementation: [left - shifts, right - shifts] holds the old [left, right], the rest is untouched */
         std::vector<unsigned char> want(rec);
         memmove(&want[(size_t)(left - shifts) * sizeof(Particle)], &rec[(size_t)left * sizeof(Particle)], (size_t)(right - left + 1) * sizeof(Particle));
@@ -88,6 +96,7 @@ int main(int argc, char **argv)
         CK(cudaDeviceSynchronize());
         std::vector<unsigned char> out2(rec.size());
         CK(cudaMemcpy(out2.data(), d_p, rec.size(), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < nrec; r++) for (int p : pad) out2[(size_t)r * sizeof(Particle) + p] = 0;
         printf(", \"mem_shift_zero_is_noop\": %s", out2 == out ? "true" : "false");
     }
     printf("}\n");
