@@ -31,6 +31,7 @@ class FsgSoa(C.Structure):
         ("n", C.c_int64), ("pos", C.c_void_p), ("vel", C.c_void_p), ("acc", C.c_void_p), ("dens", C.c_void_p),
         ("press", C.c_void_p), ("delpress", C.c_void_p), ("newdens", C.c_void_p), ("newdelpress", C.c_void_p),
         ("index", C.c_void_p), ("cell", C.c_void_p), ("boundary", C.c_void_p), ("solid", C.c_void_p), ("fluid", C.c_void_p),
+        ("stress_tensor", C.c_void_p), ("stress_rate", C.c_void_p),
     ]
 
 

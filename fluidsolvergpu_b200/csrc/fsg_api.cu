@@ -137,8 +137,9 @@ extern "C" int fsg_config_default(fsg_config *cfg, int model)
 
 static void free_state(FsgState &s)
 {
-    cudaFree(s.posd); cudaFree(s.velp); cudaFree(s.accf); cudaFree(s.dpi); cudaFree(s.mix);
+    cudaFree(s.posd); cudaFree(s.velp); cudaFree(s.accf); cudaFree(s.dpi); cudaFree(s.mix); cudaFree(s.stress);
     s.posd = s.velp = s.accf = s.dpi = s.mix = nullptr;
+    s.stress = nullptr;
 }
 
 extern "C" int fsg_destroy(fsg_ctx *c)
@@ -149,7 +150,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_state(c->A);
     free_state(c->B);
-    cudaFree(c->carryA); cudaFree(c->carryB); cudaFree(c->sums); cudaFree(c->sums2); cudaFree(c->vizb);
+    cudaFree(c->carryA); cudaFree(c->carryB); cudaFree(c->sums); cudaFree(c->sums2); cudaFree(c->vizb); cudaFree(c->mixA); cudaFree(c->mixB);
     cudaFree(c->keysA); cudaFree(c->keysB); cudaFree(c->perm); cudaFree(c->iota);
     cudaFree(c->start); cudaFree(c->end);
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
@@ -179,7 +180,13 @@ static int alloc_state(fsg_ctx *c, FsgState &s, int64_t cap)
     CU(c, cudaMalloc(&s.velp, sizeof(float4) * cap));
     CU(c, cudaMalloc(&s.accf, sizeof(float4) * cap));
     CU(c, cudaMalloc(&s.dpi, sizeof(float4) * cap));
-    if (c->cfg.model == FSG_MODEL_UNIDYN) CU(c, cudaMalloc(&s.mix, sizeof(float4) * cap));
+    if (c->cfg.model == FSG_MODEL_UNIDYN) {
+        CU(c, cudaMalloc(&s.mix, sizeof(float4) * cap));
+        if (c->cfg.world == 1) {        // granular state (stress_tensor, stress_rate): carried by single-device contexts only
+            CU(c, cudaMalloc(&s.stress, sizeof(float) * 18 * cap));
+            CU(c, cudaMemsetAsync(s.stress, 0, sizeof(float) * 18 * cap, c->stream));
+        }
+    }
     return FSG_OK;
 }
 
@@ -204,6 +211,10 @@ static int create_impl(fsg_ctx *c)
         CU(c, cudaMalloc(&c->sums2, sizeof(float4) * cap));
         CU(c, cudaMalloc(&c->vizb, sizeof(float) * cap));
         CU(c, cudaMemsetAsync(c->vizb, 0, sizeof(float) * cap, c->stream));
+        if (cfg.world == 1) {
+            CU(c, cudaMalloc(&c->mixA, sizeof(float) * 18 * cap));
+            CU(c, cudaMalloc(&c->mixB, sizeof(float) * 8 * cap));
+        }
     }
     CU(c, cudaMalloc(&c->keysA, sizeof(int) * cap));
     CU(c, cudaMalloc(&c->keysB, sizeof(int) * cap));
@@ -335,11 +346,18 @@ static int after_upload(fsg_ctx *c, int64_t n, const int *slot_state = nullptr)
     c->has_boundary = flag[0] != 0;
     if (c->cfg.world > 1) c->n = c->cap;
     CU(c, cudaMemsetAsync(c->counters + 8, 0, sizeof(int), c->stream));
+    c->mixed = false;
     if (c->cfg.model == FSG_MODEL_UNIDYN && flag[4]) {
-        c->n = 0;
-        c->err = "upload: the unidyn path covers scenes whose non-boundary particles are pure fluid (solid == 0) with mass 1 "
-                 "(solver-unidyn.cu:127-184); mixed-phase / granular scenes are not built yet";
-        return FSG_E_UNSUPPORTED;
+        // bit 1: a particle with mass != 1 (merged / split particles are outside the built scope); bit 2: a non-boundary particle
+        // with solid != 0 — a mixed-phase / granular scene: the two-pass kernels of fsg_unidyn_mixed.cu, single-device contexts
+        if ((flag[4] & 1) || c->cfg.world > 1) {
+            c->n = 0;
+            c->err = (flag[4] & 1) ? "upload: the unidyn path needs mass == 1 for every particle (solver-unidyn.cu:127-184)"
+                                   : "upload: mixed-phase / granular unidyn scenes (a non-boundary particle with solid != 0) run on single-device "
+                                     "contexts only (the slab messages do not carry the granular stress state)";
+            return FSG_E_UNSUPPORTED;
+        }
+        c->mixed = true;
     }
     c->carry_live = true;
     c->steps = 0;
@@ -370,6 +388,7 @@ extern "C" int fsg_upload_aos(fsg_ctx *c, const void *particles, int64_t n)
         FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o, nullptr};
         if (c->cfg.model == FSG_MODEL_UNIDYN) {
             st.mix = c->B.mix + o;
+            st.stress = c->B.stress ? c->B.stress + 18 * o : nullptr;
             CU(c, fsg_launch_unpack_aos_unidyn((const unsigned char *)c->stage, m, st, c->carryB + o, c->counters + 8, c->stream));
         } else
             CU(c, fsg_launch_unpack_aos(c->cfg.model, (const unsigned char *)c->stage, m, st, c->carryB + o, c->stream));
@@ -392,6 +411,7 @@ extern "C" int fsg_download_aos(fsg_ctx *c, void *particles, int64_t n)
         FsgState st = {c->B.posd + o, c->B.velp + o, c->B.accf + o, c->B.dpi + o, nullptr};
         if (c->cfg.model == FSG_MODEL_UNIDYN) {
             st.mix = c->B.mix + o;
+            st.stress = c->B.stress ? c->B.stress + 18 * o : nullptr;
             CU(c, fsg_launch_pack_aos_unidyn((unsigned char *)c->stage, m, st, c->carry_live ? c->carryB + o : nullptr, c->keysB + o, c->dev,
                                              c->stream));
         } else
@@ -408,8 +428,8 @@ extern "C" int fsg_download_aos(fsg_ctx *c, void *particles, int64_t n)
 // ---- SoA host interface: raw arrays are copied into a staging area and (un)packed on the device ----
 __global__ void k_pack_soa(int64_t n, const float *pos, const float *vel, const float *acc, const float *dens,
                            const float *press, const float *delp, const float *nd, const float *ndp, const int *index,
-                           const unsigned char *bnd, const float *solid, const float *fluid, float gravity, FsgState st, float4 *carry,
-                           int *bad)
+                           const unsigned char *bnd, const float *solid, const float *fluid, const float *stress_tensor, const float *stress_rate,
+                           float gravity, FsgState st, float4 *carry, int *bad)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -425,13 +445,19 @@ __global__ void k_pack_soa(int64_t n, const float *pos, const float *vel, const 
     if (st.mix) {      // unidyn: solid / fluid default to 0/1 for fluid, 1/0 for boundary particles (solver-unidyn.cu:129-143)
         float so = solid ? solid[i] : (b ? 1.f : 0.f), fl = fluid ? fluid[i] : (b ? 0.f : 1.f);
         st.mix[i] = make_float4(so, fl, 0.f, 0.f);
-        if (!b && so != 0.f) atomicOr(bad, 1);
+        if (!b && so != 0.f) atomicOr(bad, 2);        // a mixed-phase / granular scene
+    }
+    if (st.stress) {
+        for (int k = 0; k < 9; k++) {
+            st.stress[i * 18 + k] = stress_tensor ? stress_tensor[9 * i + k] : 0.f;
+            st.stress[i * 18 + 9 + k] = stress_rate ? stress_rate[9 * i + k] : 0.f;
+        }
     }
 }
 
 __global__ void k_unpack_soa(int64_t n, FsgState st, const float4 *carry, const int *keys, float *pos, float *vel, float *acc,
                              float *dens, float *press, float *delp, float *nd, float *ndp, int *index, int *cell,
-                             unsigned char *bnd, float *solid, float *fluid)
+                             unsigned char *bnd, float *solid, float *fluid, float *stress_tensor, float *stress_rate)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -453,13 +479,17 @@ __global__ void k_unpack_soa(int64_t n, FsgState st, const float4 *carry, const 
         if (solid) solid[i] = mx.x;
         if (fluid) fluid[i] = mx.y;
     }
+    for (int k = 0; k < 9; k++) {
+        if (stress_tensor) stress_tensor[9 * i + k] = st.stress ? st.stress[i * 18 + k] : 0.f;
+        if (stress_rate) stress_rate[9 * i + k] = st.stress ? st.stress[i * 18 + 9 + k] : 0.f;
+    }
 }
 
 struct SoaStage {
     float *pos, *vel, *acc, *dens, *press, *delp, *nd, *ndp;
     int *index, *cell;
     unsigned char *bnd;
-    float *solid, *fluid;
+    float *solid, *fluid, *stress_tensor, *stress_rate;
 };
 static size_t soa_stage_layout(char *base, int64_t n, const fsg_soa *h, SoaStage &s)
 {
@@ -483,6 +513,8 @@ static size_t soa_stage_layout(char *base, int64_t n, const fsg_soa *h, SoaStage
     s.bnd = (unsigned char *)take(h->boundary, n);
     s.solid = (float *)take(h->solid, 4 * n);
     s.fluid = (float *)take(h->fluid, 4 * n);
+    s.stress_tensor = (float *)take(h->stress_tensor, 36 * n);
+    s.stress_rate = (float *)take(h->stress_rate, 36 * n);
     return o + 256;
 }
 
@@ -506,12 +538,13 @@ extern "C" int fsg_upload_soa(fsg_ctx *c, const fsg_soa *h)
     H2D(s.press, h->press, 4 * n); H2D(s.delp, h->delpress, 12 * n); H2D(s.nd, h->newdens, 4 * n);
     H2D(s.ndp, h->newdelpress, 12 * n); H2D(s.index, h->index, 4 * n); H2D(s.bnd, h->boundary, n);
     H2D(s.solid, h->solid, 4 * n); H2D(s.fluid, h->fluid, 4 * n);
+    H2D(s.stress_tensor, h->stress_tensor, 36 * n); H2D(s.stress_rate, h->stress_rate, 36 * n);
     if (hh.cell) CU(c, cudaMemcpyAsync(s.cell, h->cell, (size_t)(4 * n), cudaMemcpyHostToDevice, c->stream));
 #undef H2D
     if (n > 0) {
         k_pack_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, s.pos, s.vel, s.acc, s.dens, s.press, s.delp, s.nd,
-                                                                       s.ndp, s.index, s.bnd, s.solid, s.fluid, (float)c->cfg.gravity,
-                                                                       c->B, c->carryB, c->counters + 8);
+                                                                       s.ndp, s.index, s.bnd, s.solid, s.fluid, s.stress_tensor, s.stress_rate,
+                                                                       (float)c->cfg.gravity, c->B, c->carryB, c->counters + 8);
         CU(c, cudaGetLastError());
         c->launches++;
     }
@@ -533,7 +566,7 @@ extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
     if (n > 0) {
         k_unpack_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->B, c->carry_live ? c->carryB : nullptr, c->keysB,
                                                                          s.pos, s.vel, s.acc, s.dens, s.press, s.delp, s.nd,
-                                                                         s.ndp, s.index, s.cell, s.bnd, s.solid, s.fluid);
+                                                                         s.ndp, s.index, s.cell, s.bnd, s.solid, s.fluid, s.stress_tensor, s.stress_rate);
         CU(c, cudaGetLastError());
         c->launches++;
     }
@@ -542,6 +575,7 @@ extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
     D2H(h->press, s.press, 4 * n); D2H(h->delpress, s.delp, 12 * n); D2H(h->newdens, s.nd, 4 * n);
     D2H(h->newdelpress, s.ndp, 12 * n); D2H(h->index, s.index, 4 * n); D2H(h->cell, s.cell, 4 * n); D2H(h->boundary, s.bnd, n);
     if (c->B.mix) { D2H(h->solid, s.solid, 4 * n); D2H(h->fluid, s.fluid, 4 * n); }
+    D2H(h->stress_tensor, s.stress_tensor, 36 * n); D2H(h->stress_rate, s.stress_rate, 36 * n);
 #undef D2H
     int order_bad = 0;
     CU(c, cudaMemcpyAsync(&order_bad, c->counters + 14, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -148,6 +148,9 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
         dst.accf[k] = c;
         dst.dpi[k] = e;
         if (src.mix) dst.mix[k] = src.mix[sidx];
+        if (src.stress) {
+            for (int q = 0; q < 18; q++) dst.stress[(size_t)k * 18 + q] = src.stress[(size_t)sidx * 18 + q];
+        }
         if (keys_next) keys_next[k] = key < numcells ? predicted_key(d, a, b) : key;
         int next = k + 1 < n ? keysA[k + 1] : d.dead;
         if (k + 1 < n && next < key) atomicOr(order_flag, 1);          // the key sort's result, verified where it is consumed

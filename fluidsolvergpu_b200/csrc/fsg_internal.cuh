@@ -48,6 +48,7 @@ struct FsgDev {
 struct FsgState {
     float4 *posd, *velp, *accf, *dpi;
     float4 *mix;     // unidyn model only: (solid, fluid, -, -)   FluidGPU-unidyn.cuh:180-181
+    float *stress;   // unidyn model, single-device contexts: [n][18] stress_tensor[3][3] then stress_rate[3][3] (granular scenes)
 };
 
 struct FsgFrameWriter;        // fsg_frame.cu: copy stream, pinned staging slots and the writer thread of the asynchronous frame output
@@ -74,6 +75,8 @@ struct fsg_ctx {
     int defer_mode;         // -1 not decided, 0 off, 1 on (FSG_DEFER_UPDATE)
     float4 *sums;              // pair sums of the current step (newdens, newdelpress xyz), sorted order
     float4 *sums2;             // unidyn: (diffusion xyz, delfluid)
+    float *mixA, *mixB;        // unidyn, mixed-phase scenes: pass-A / pass-B pair sums per sorted slot (fsg_unidyn_mixed.cu)
+    bool mixed;                // the uploaded unidyn scene has a non-boundary particle with solid != 0
     float *vizb;               // unidyn: |diffusion|^2 of the last step (mykernel2's b3, FluidGPU-unidyn.cu:466)
     int upload_flags;          // host copy of the flags the upload kernels raise
     bool has_boundary;         // any Particle::boundary set in the uploaded scene

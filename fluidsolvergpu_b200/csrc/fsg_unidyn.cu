@@ -15,50 +15,7 @@
 // Gather form, one warp per home bin, in-range candidates compacted into a queue, no atomics.
 #include "fsg_device.cuh"
 
-#define UNI_WARPS 2
-#define UNI_TILE 1024                   // the reference's threads per block = neighbour particles per bin (solver-unidyn.cu:363)
-
-struct UniWarpSmem {
-    float4 sp[UNI_TILE];                // x, y, z, +-dens (sign = boundary)
-    float4 sv[UNI_TILE];                // vx, vy, vz, press / dens^2
-    float sf[UNI_TILE];                 // fluid
-    unsigned short q[UNI_TILE];
-    unsigned char tag[UNI_TILE];        // neighbour slot 0..26 of the candidate's bin
-};
-#define UNI_SMEM (sizeof(UniWarpSmem) * UNI_WARPS)
-
-struct UniArgs {
-    FsgDev d;
-    int n;
-    const int *start, *end, *binlist, *nocc;
-    int *work;
-    FsgState A;
-    float4 *sums, *sums2;               // (newdens, newdelpress xyz), (diffusion xyz, delfluid)
-    unsigned long long *stats;
-};
-
-// octant of a particle inside its bin, FluidGPU-unidyn.cu:182-184
-__device__ __forceinline__ int uni_subindex(const FsgDev &d, float x, float y, float z)
-{
-    float fx = x - d.origin, fy = y - d.origin, fz = z - d.origin;
-    const double cs = d.cellsize;
-    int sx = (int)((double)fx / cs) == (int)(((double)fx + cs / 2) / cs);
-    int sy = (int)((double)fy / cs) == (int)(((double)fy + cs / 2) / cs);
-    int sz = (int)((double)fz / cs) == (int)(((double)fz + cs / 2) / cs);
-    return 1 - sx + 2 - 2 * sy + 4 * sz;
-}
-// the 8 neighbour slots (of the 27) mykernel3 visits for an octant, :579-583
-__device__ __forceinline__ unsigned uni_octant_mask(int oct)
-{
-    const int ax = (oct & 1) ? 1 : -1, ay = (oct & 2) ? 1 : -1, az = (oct & 4) ? -1 : 1;
-    unsigned m = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int a = (k & 1) ? ax : 0, b = (k & 2) ? ay : 0, c = (k & 4) ? az : 0;
-        m |= 1u << ((a + 1) * 9 + (b + 1) * 3 + (c + 1));
-    }
-    return m;
-}
+#include "fsg_unidyn.cuh"
 
 template <bool STATS>
 __global__ void __launch_bounds__(UNI_WARPS * 32)
@@ -231,12 +188,48 @@ k_pair_unidyn(UniArgs a)
 // ------------------------------------------------------------------------------------------------
 // mykernel2's per-particle work after the export: Particle::update(t) (cuh:296-423) for one particle of a live bin,
 // then cell_calc's bin id (cu:547).  s = (newdens, newdelpress xyz), s2 = (diffusion xyz, delfluid).
+// The granular stress update of one particle, FluidGPU-unidyn.cu:410-446, with the COMPLETED vel_grad sums (race-free reading,
+// fsg_unidyn_mixed.cu).  st: stress_tensor[9] then stress_rate[9]; press: the pressure before this step's update.
+__device__ __forceinline__ void unidyn_stress_update(float *st, const float *vg, float solid, float press)
+{
+    if (!(solid != 0.f)) return;                                          // cu:411
+    float *sr = st + 9;
+    float strain[9];
+    float tr = 0, tr3 = 0, tr4 = 0, tr5 = 0;
+#pragma unroll
+    for (int pq = 0; pq < 9; pq++) strain[pq] = (float)(0.5 * (double)(vg[pq] + vg[3 * (pq % 3) + pq / 3]));                     // :419
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            tr3 = (float)((double)tr3 + 0.5 * (double)st[3 * p + q] * (double)st[3 * p + q]);                                   // :421
+            tr5 += strain[3 * p + q] * strain[3 * p + q];                                                                        // :423
+            tr4 += st[3 * p + q] * strain[3 * q + p];                                                                            // :424
+        }
+        tr += strain[3 * p + p];                                                                                                 // :426
+    }
+    const double tp = tan(1.23), root = sqrt(9 + 12 * pow(tp, 2));                                                               // PHI
+    const double yield = 3 * tp / root * (double)press * (double)(press > 0) + 1e9 / root;                                       // KC
+    const bool scale = yield < (double)tr3 && tr3 != 0;                                                                          // :435
+#pragma unroll
+    for (int pq = 0; pq < 9; pq++) {
+        if (scale) st[pq] = (float)((double)st[pq] * (yield / (double)tr3));                                                     // :436
+        // :438 (C1 = 1.5e1, C2 = 0e6, C3 = 5e1)
+        sr[pq] = (float)(3 * 1.5e1 * (double)press * ((double)strain[pq] - 1. / 3. * (double)tr * (double)(pq % 4 == 0)) +
+                         1.5e1 * 0e6 * ((double)tr4 + (double)(tr * press * (float)(press > 0))) / (pow((double)press, 2) + 1e8) * (double)st[pq] -
+                         1.5e1 * 5e1 * sqrt((double)tr5) * (double)st[pq]);
+    }
+}
+
+// mixed: (stress_accel xyz, mixture_accel xyz, delsolid) of the step, all zero for pure-fluid scenes
+struct UniMixedTerms { float sa[3], ma[3], delsolid; };
+
 __device__ __forceinline__ void unidyn_particle_update(const FsgDev &d, float4 &pd, float4 &vp, float4 &af, float4 &dpi, float4 &mx,
-                                                       const float4 s, const float4 s2, int &key)
+                                                       const float4 s, const float4 s2, int &key, const UniMixedTerms &mt)
 {
     const float diffx = s2.x, diffy = s2.y, diffz = s2.z;
     float delfluid = s2.w;
-    const float delsolid = 0.f;
+    const float delsolid = mt.delsolid;
     const bool bnd = pd.w < 0.f;
     float solid = mx.x, fluid = mx.y;
     const double DT = d.dt;
@@ -259,13 +252,14 @@ __device__ __forceinline__ void unidyn_particle_update(const FsgDev &d, float4 &
         float z = (float)((double)pd.z + DT * (double)vp.z + 0.5 * DT * DT * (double)af.z + (double)(0 * diffz));
         float vx = vp.x, vy = vp.y, vz = vp.z;
         if ((double)z < -0.89) { vx = 0; vy = 0; }                        // :332-341
-        // :351-353 — stress_accel == mixture_accel == 0 in scope; the y and z lines test the NEW xvel (sic)
+        // :351-353 — the y and z lines test the NEW xvel with xacc (sic), each with its own stress_accel / mixture_accel component
         const double fr = (double)friction * 0.0000002 * (double)solid;
-        double tx = (double)vx + DT * (double)af.x;
-        vx = (float)(((double)vx + 0.5 * DT * (double)af.x) - (tx > 0) * fr + (tx < 0) * fr);
-        tx = (double)vx + DT * (double)af.x;
-        vy = (float)(((double)vy + 0.5 * DT * (double)af.y) - (tx > 0) * fr + (tx < 0) * fr);
-        vz = (float)(((double)vz + 0.5 * DT * (double)af.z) - (tx > 0) * fr + (tx < 0) * fr);
+        double tx = (double)vx + DT * (double)af.x + DT * (double)mt.sa[0] + DT * DT * (double)mt.ma[0];
+        vx = (float)(((double)vx + 0.5 * DT * (double)af.x + DT * (double)mt.sa[0] + 5 * DT * DT * (double)mt.ma[0]) - (tx > 0) * fr + (tx < 0) * fr);
+        tx = (double)vx + DT * (double)af.x + DT * (double)mt.sa[1] + DT * DT * (double)mt.ma[1];
+        vy = (float)(((double)vy + 0.5 * DT * (double)af.y + DT * (double)mt.sa[1] + 5 * DT * DT * (double)mt.ma[1]) - (tx > 0) * fr + (tx < 0) * fr);
+        tx = (double)vx + DT * (double)af.x + DT * (double)mt.sa[2] + DT * DT * (double)mt.ma[2];
+        vz = (float)(((double)vz + 0.5 * DT * (double)af.z + DT * (double)mt.sa[2] + 5 * DT * DT * (double)mt.ma[2]) - (tx > 0) * fr + (tx < 0) * fr);
         af.x = (float)(-((220.0 - 70.0 * (double)solid) / (double)dens) * (double)dpi.x);     // :357-359
         af.y = (float)(-((220.0 - 70.0 * (double)solid) / (double)dens) * (double)dpi.y);
         af.z = (float)(d.gravity + ((-220.0 + 70.0 * (double)solid) / (double)dens) * (double)dpi.z);
@@ -287,13 +281,18 @@ __device__ __forceinline__ void unidyn_particle_update(const FsgDev &d, float4 &
 __global__ void __launch_bounds__(256)
 k_update_unidyn(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgState B, int *__restrict__ keysB,
                 const float4 *__restrict__ sums, const float4 *__restrict__ sums2, const float4 *__restrict__ carry, float *__restrict__ vizb,
-                int *violation)
+                int *violation, const float *__restrict__ mixA, const float *__restrict__ mixB)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 pd = A.posd[i], vp = A.velp[i], af = A.accf[i], dpi = A.dpi[i], mx = A.mix[i];
     int key = keysA[i];
     float b3 = 0.f;
+    float st[UNI_STRESS];
+    if (A.stress) {
+#pragma unroll
+        for (int k = 0; k < UNI_STRESS; k++) st[k] = A.stress[(size_t)i * UNI_STRESS + k];
+    }
     if (key < d.numcells) {
         const int ix = key / d.G2;
         if (ix < d.x0 || ix >= d.x1) {      // slab contexts: ghost copy of a neighbour slab's particle — drop it
@@ -304,7 +303,20 @@ k_update_unidyn(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgS
         float4 s = sums[i], s2 = sums2[i];
         if (carry) { float4 cy = carry[i]; s.x += cy.x; s.y += cy.y; s.z += cy.z; s.w += cy.w; }
         b3 = s2.x * s2.x + s2.y * s2.y + s2.z * s2.z;                         // cu:466
-        unidyn_particle_update(d, pd, vp, af, dpi, mx, s, s2, key);
+        UniMixedTerms mt = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0.f};
+        if (mixA) {                                                           // mixed-phase / granular scene (fsg_unidyn_mixed.cu)
+            const float *ma = mixA + (size_t)i * UNI_MIXA, *mb = mixB + (size_t)i * UNI_MIXB;
+            unidyn_stress_update(st, ma + 6, mx.x, vp.w);                     // cu:410-446, before mykernel2's update
+            mt.sa[0] = ma[15]; mt.sa[1] = ma[16]; mt.sa[2] = ma[17];
+            mt.ma[0] = mb[0]; mt.ma[1] = mb[1]; mt.ma[2] = mb[2];
+            mt.delsolid = mb[3];
+            s2.w = mb[4];                                                     // delfluid comes from pass B
+        }
+        if (A.stress) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) st[k] = (float)(d.dt * (double)st[9 + k]);     // stress_tensor = DT * stress_rate, cuh:304-308
+        }
+        unidyn_particle_update(d, pd, vp, af, dpi, mx, s, s2, key, mt);
         // the one-layer ghost band assumes less than one bin layer per step
         if (violation && key < d.numcells && abs(key / d.G2 - ix) > 1) atomicOr(violation, 1);
     }
@@ -313,6 +325,10 @@ k_update_unidyn(FsgDev d, int n, const int *__restrict__ keysA, FsgState A, FsgS
     B.accf[i] = af;
     B.dpi[i] = dpi;
     B.mix[i] = mx;
+    if (A.stress) {
+#pragma unroll
+        for (int k = 0; k < UNI_STRESS; k++) B.stress[(size_t)i * UNI_STRESS + k] = st[k];
+    }
     keysB[i] = key;
     vizb[i] = b3;
 }
@@ -347,15 +363,31 @@ cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, c
     a.sums = c->sums;
     a.sums2 = c->sums2;
     a.stats = c->dstats;
+    a.mixA = c->mixA;
+    a.mixB = c->mixB;
     int64_t blocks = (n + UNI_WARPS - 1) / UNI_WARPS;
     int64_t maxb = (int64_t)c->sm_count * 2;
     if (blocks > maxb) blocks = maxb;
-    if (c->cfg.collect_stats) k_pair_unidyn<true><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, s>>>(a);
-    else k_pair_unidyn<false><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, s>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+    if (c->mixed) {
+        // mixed-phase / granular scene: pass A, then pass B over the completed drift sums (fsg_unidyn_mixed.cu); the pair counters
+        // of collect_stats come from the pure-fluid kernel's bookkeeping and are not kept here
+        e = fsg_launch_unidyn_mixed(a, 0, c->sm_count, s);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(work, 0, sizeof(int), s);
+        if (e != cudaSuccess) return e;
+        e = fsg_launch_unidyn_mixed(a, 1, c->sm_count, s);
+        if (e != cudaSuccess) return e;
+        *launches += 1;
+    } else {
+        if (c->cfg.collect_stats) k_pair_unidyn<true><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, s>>>(a);
+        else k_pair_unidyn<false><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, s>>>(a);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     k_update_unidyn<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->dev, (int)n, c->keysA, c->A, c->B, c->keysB, c->sums, c->sums2, carry,
-                                                              c->vizb, c->cfg.world > 1 ? c->counters + 6 : nullptr);
+                                                              c->vizb, c->cfg.world > 1 ? c->counters + 6 : nullptr,
+                                                              c->mixed ? c->mixA : nullptr, c->mixed ? c->mixB : nullptr);
     *launches += 2;
     return cudaGetLastError();
 }
@@ -374,7 +406,7 @@ cudaError_t fsg_launch_split_table(const fsg_ctx *c, int *split, cudaStream_t s)
 namespace aos_uni {
 enum { POS = 0, VEL = 12, ACC = 36, INDEX = 60, CELL = 64, SUBINDEX = 68, MASS = 72, DENS = 76, PRESS = 80, DELP_Z = 84, DELP_Y = 88,
        DELP_X = 92, DIFFUSION = 96, NEWDENS = 108, NDELP_Z = 112, NDELP_Y = 116, NDELP_X = 120, BOUNDARY = 316, SOLID = 320, FLUID = 324,
-       DELSOLID = 328, DELFLUID = 332, FLAG = 336, SPLIT = 337 };
+       DELSOLID = 328, DELFLUID = 332, FLAG = 336, SPLIT = 337, STRESS_RATE = 220, STRESS_TENSOR = 256 };
 }
 __device__ __forceinline__ float uldf(const unsigned char *r, int off) { return *reinterpret_cast<const float *>(r + off); }
 __device__ __forceinline__ void ustf(unsigned char *r, int off, float v) { *reinterpret_cast<float *>(r + off) = v; }
@@ -393,7 +425,14 @@ __global__ void k_unpack_aos_unidyn(const unsigned char *__restrict__ aos, int64
     st.dpi[i] = make_float4(uldf(r, DELP_X), uldf(r, DELP_Y), uldf(r, DELP_Z), __int_as_float(*reinterpret_cast<const int *>(r + INDEX)));
     st.mix[i] = make_float4(solid, uldf(r, FLUID), 0.f, 0.f);
     carry[i] = make_float4(uldf(r, NEWDENS), uldf(r, NDELP_X), uldf(r, NDELP_Y), uldf(r, NDELP_Z));
-    if ((!bnd && solid != 0.f) || uldf(r, MASS) != 1.f) atomicOr(bad, 1);
+    if (st.stress) {
+        for (int k = 0; k < 9; k++) {
+            st.stress[(size_t)i * UNI_STRESS + k] = uldf(r, STRESS_TENSOR + 4 * k);
+            st.stress[(size_t)i * UNI_STRESS + 9 + k] = uldf(r, STRESS_RATE + 4 * k);
+        }
+    }
+    if (uldf(r, MASS) != 1.f) atomicOr(bad, 1);           // outside the scope (merged / split particles)
+    if (!bnd && solid != 0.f) atomicOr(bad, 2);           // a mixed-phase / granular scene
 }
 
 __global__ void k_pack_aos_unidyn(unsigned char *__restrict__ aos, int64_t n, FsgState st, const float4 *carry, const int *keys, FsgDev d)
@@ -420,6 +459,12 @@ __global__ void k_pack_aos_unidyn(unsigned char *__restrict__ aos, int64_t n, Fs
     r[BOUNDARY] = pd.w < 0.f ? 1 : 0;
     ustf(r, SOLID, mx.x);
     ustf(r, FLUID, mx.y);
+    if (st.stress) {
+        for (int k = 0; k < 9; k++) {
+            ustf(r, STRESS_TENSOR + 4 * k, st.stress[(size_t)i * UNI_STRESS + k]);
+            ustf(r, STRESS_RATE + 4 * k, st.stress[(size_t)i * UNI_STRESS + 9 + k]);
+        }
+    }
     r[FLAG] = 1;                                     // update() leaves flag = true, cuh:422
 }
 
@@ -655,7 +700,8 @@ k_stage_uni_mykernel2(FsgDev d, unsigned char *__restrict__ aos, int *__restrict
         float4 dpi = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 mx = make_float4(uldf(r, SOLID), uldf(r, FLUID), 0.f, 0.f);
         int key;
-        unidyn_particle_update(d, pd, vp, af, dpi, mx, s, s2, key);                      // cu:469
+        const UniMixedTerms none = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0.f};              // (the stage API keeps the pure-fluid scope)
+        unidyn_particle_update(d, pd, vp, af, dpi, mx, s, s2, key, none);                // cu:469
         ustf(r, POS, pd.x); ustf(r, POS + 4, pd.y); ustf(r, POS + 8, pd.z);
         ustf(r, VEL, vp.x); ustf(r, VEL + 4, vp.y); ustf(r, VEL + 8, vp.z);
         ustf(r, ACC, af.x); ustf(r, ACC + 4, af.y); ustf(r, ACC + 8, af.z);

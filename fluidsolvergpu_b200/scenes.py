@@ -125,3 +125,26 @@ def random_unidyn_scene(n: int, seed: int, boundary_frac: float = 0.1, vel_scale
     st["fluid"] = (1 - st["boundary"]).astype(np.float32)
     st["vel"][st["boundary"] != 0] = 0
     return st
+
+
+def mixed_unidyn_scene(n: int = 4000, seed: int = 7, stress_scale: float = 1e3) -> dict:
+    """Sand on water for the unidyn model: a seeded jittered lattice in the unidyn domain whose upper part is
+    granular material (solid = 1), whose lower part is water (solid = 0) and whose middle band is a mixture (0 < solid < 1,
+    fluid = 1 - solid) — the particles that activate the mixed-phase block (FluidGPU-unidyn.cu:317-357), vel_grad / stress_accel /
+    mixture_accel / delsolid (:368-401) and the granular stress update (:410-446).  Boundary particles as in the default scene
+    (solid = 1, fluid = 0).  stress_tensor / stress_rate start from seeded values on the granular particles so that the stress terms
+    are exercised from the first step."""
+    st = random_unidyn_scene(n, seed, boundary_frac=0.1, vel_scale=0.3)
+    rng = np.random.default_rng(seed + 1)
+    z = st["pos"][:, 2]
+    solid = np.where(z > 0.1, 1.0, np.where(z > -0.1, rng.uniform(0.05, 0.95, z.shape), 0.0)).astype(np.float32)
+    fluid = (1 - solid).astype(np.float32)
+    bnd = st["boundary"] != 0
+    solid[bnd], fluid[bnd] = 1.0, 0.0
+    st["solid"], st["fluid"] = solid, fluid
+    m = z.shape[0]
+    sym = rng.standard_normal((m, 3, 3))
+    sym = (sym + sym.transpose(0, 2, 1)) * 0.5 * stress_scale
+    st["stress_tensor"] = (sym.reshape(m, 9) * (solid[:, None] > 0)).astype(np.float32)
+    st["stress_rate"] = (rng.standard_normal((m, 9)) * stress_scale * 100 * (solid[:, None] > 0)).astype(np.float32)
+    return st

@@ -19,6 +19,7 @@ from ._lib import FsgConfig, FsgError, FsgSoa, FsgStats
 _F3 = ("pos", "vel", "acc", "delpress", "newdelpress")
 _F1 = ("dens", "press", "newdens")
 _FU = ("solid", "fluid")      # unidyn model only
+_F9 = ("stress_tensor", "stress_rate")      # unidyn, granular state [n, 9]
 
 
 class FluidSolver:
@@ -90,7 +91,7 @@ class FluidSolver:
         soa = FsgSoa()
         soa.n = n
         keep = []
-        for k in _F3 + _F1 + (_FU if self.is_unidyn else ()):
+        for k in _F3 + _F1 + (_FU + _F9 if self.is_unidyn else ()):
             if state.get(k) is not None:
                 a = np.ascontiguousarray(state[k], np.float32)
                 keep.append(a)
@@ -115,10 +116,12 @@ class FluidSolver:
         n = st["n"]
         out = {}
         soa = FsgSoa()
-        fields = fields or (_F3 + _F1 + ("index", "cell", "boundary") + (_FU if self.is_unidyn else ()))
+        fields = fields or (_F3 + _F1 + ("index", "cell", "boundary") + (_FU + _F9 if self.is_unidyn else ()))
         for k in fields:
             if k in _F3:
                 out[k] = np.empty((n, 3), np.float32)
+            elif k in _F9:
+                out[k] = np.empty((n, 9), np.float32)
             elif k in _F1 or k in _FU:
                 out[k] = np.empty(n, np.float32)
             elif k in ("index", "cell"):

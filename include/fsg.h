@@ -106,6 +106,9 @@ typedef struct fsg_soa {
     /* unidyn model only (FluidGPU-unidyn.cuh:180-181); NULL on upload: 0/1 for fluid, 1/0 for boundary particles */
     float  *solid;       /* [n] */
     float  *fluid;       /* [n] */
+    /* unidyn, granular state of mixed-phase scenes (FluidGPU-unidyn.cuh stress_tensor[3][3], stress_rate[3][3]); NULL on upload: zeros */
+    float  *stress_tensor; /* [n][9] row major */
+    float  *stress_rate;   /* [n][9] */
 } fsg_soa;
 
 typedef struct fsg_ctx fsg_ctx;

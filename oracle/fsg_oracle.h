@@ -96,12 +96,17 @@ typedef struct fsgo_ustate {
     float *solid;      /* [n] FluidGPU-unidyn.cuh:180 */
     float *fluid;      /* [n] :181 */
     int   *subindex;   /* [n] octant of the particle inside a split bin (:119, FluidGPU-unidyn.cu:182-184) */
+    /* mixed-phase / granular scenes (may be NULL for pure-fluid scenes): FluidGPU-unidyn.cuh stress_tensor[3][3], stress_rate[3][3] */
+    float *stress_tensor; /* [n][9] row major */
+    float *stress_rate;   /* [n][9] */
 } fsgo_ustate;
 
 /* One pass of the solver-unidyn.cu:313-573 loop body on one device: sort (:331) -> count_after_merge (:341)
  * -> findneighbours (:354) -> mykernel (:363) -> mykernel3 (:379) -> mykernel2 (:389) -> cell_calc (:548).
  * split_out[numcells]: split[] as mykernel leaves it (bin id for bins with more than 6 particles, else -1).
  * viz: spts = pre-update positions, a3 = mass, b3 = |diffusion|^2 (FluidGPU-unidyn.cu:462-466).
+ * Scenes with a non-boundary particle of solid != 0 take the race-free two-pass reading of the mixed-phase / granular terms
+ * (see fsg_oracle_unidyn.c) and need stress_tensor / stress_rate.
  * Returns 0; -1 allocation failure; -2 scene outside the restated scope (see fsg_oracle_unidyn.c). */
 int fsgo_unidyn_step(const fsgo_params *p, fsgo_ustate *s, int t, int *cells_sorted, int *start, int *end, int *split,
                      float *spts, float *a3, float *b3, long long *stats);

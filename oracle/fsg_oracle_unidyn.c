@@ -4,13 +4,21 @@
  *
  * TEST INFRASTRUCTURE ONLY (see fsg_oracle.h).  Every function cites the reference file:line it follows.
  *
- * Scope of the restatement: scenes in which every non-boundary particle is pure fluid (solid == 0)
- * and mass == 1 — the default scene of solver-unidyn.cu:127-184 and anything built like it.  For such
- * scenes the mixed-phase block (FluidGPU-unidyn.cu:317-357), mixfactor (:368), vel_grad (:369-377),
- * stress_accel (:379-381), mixture_accel (:391-398), delsolid (:400) and the granular stress update
- * (:410-446) contribute exactly zero, merging is unreachable (`ds <= -10 && ds > 0`, :261) and
- * splitting needs mass > 3 (:278); the live sums are newdens, newdelpress, diffusion and delfluid.
- * fsgo_unidyn_step returns -2 for a scene outside that scope.
+ * Scope of the restatement: mass == 1 (merging is unreachable, `ds <= -10 && ds > 0`, :261, and splitting needs mass > 3, :278).
+ * For scenes in which every non-boundary particle is pure fluid (solid == 0) — the default scene of solver-unidyn.cu:127-184 —
+ * the mixed-phase block (FluidGPU-unidyn.cu:317-357), mixfactor (:368), vel_grad (:369-377), stress_accel (:379-381),
+ * mixture_accel (:391-398), delsolid (:400) and the granular stress update (:410-446) contribute exactly zero; that part is
+ * PINNED by dumps of the reference's own kernels (tests/golden/ref_config2_*, ref_unidyn_random_*).
+ *
+ * MIXED-PHASE / GRANULAR scenes (some non-boundary particle with solid != 0; the caller passes stress_tensor / stress_rate): the
+ * reference's result is NOT a function of its input there — mixture_accel / delsolid / delfluid read the drift velocities of both
+ * particles (:385-401) while other blocks of the same launch are still accumulating them (:351-357), and the stress update (:410-446,
+ * repeated at the end of mykernel3, :832-868) reads vel_grad sums that other blocks are still adding to.  This restatement fixes the
+ * RACE-FREE reading the author evidently meant:  pass A accumulates newdens / newdelpress / diffusion / drift velocities / vel_grad
+ * / stress_accel over all pairs;  pass B evaluates mixture_accel / delsolid / delfluid with the COMPLETED drift velocities of both
+ * particles;  then ONE stress update per particle with the completed vel_grad;  then mykernel2 + update.  Every expression follows
+ * the reference text (types included).  PARITY UNPINNED against the reference for these terms (it cannot be pinned: two runs of
+ * the reference differ at O(1) in them); the CUDA path is pinned against THIS restatement.
  */
 #include "fsg_oracle.h"
 
@@ -49,24 +57,151 @@ static float u_pressure(float dens, float solid, double sound)
            (solid) * 1000 * pow(sound, 0) * 9550 / 7.0 * (pow(dens / 9550, 7) - 1);
 }
 
-typedef struct { float dens, px, py, pz, dx, dy, dz, delfluid; } upair_acc;
+typedef struct {
+    float dens, px, py, pz, dx, dy, dz, delfluid;
+    /* mixed-phase / granular accumulators */
+    float sdrift[3], fdrift[3], vel_grad[9], stress_accel[3], mix[3], delsolid;
+} upair_acc;
 
-/* pair body, FluidGPU-unidyn.cu:258-401 (== :679-821 of mykernel3), live terms only */
-static inline void upair_body(const fsgo_params *P, const fsgo_ustate *s, int i, int j, upair_acc *a, long long *st)
+/* reference constants, FluidGPU-unidyn.cuh:24-33 */
+#define U_C1 1.5e1
+#define U_C2 0e6
+#define U_C3 5e1
+#define U_PHI 1.23
+#define U_KC 1e9
+#define U_MIXPRESSURE 1e-12
+#define U_MIXBROWNIAN 5e-9
+#define U_RHO_0 9550
+#define U_RHO_0_SAND 9550
+
+/* Pass A, mixed-phase / granular terms of one in-range pair (FluidGPU-unidyn.cu:314-357, 368-381), added to the live terms of
+ * upair_body.  i = home particle (ii in the reference), j = neighbour. */
+static inline void upair_mixed_a(const fsgo_params *P, const fsgo_ustate *s, int i, int j, float dkx, float dky, float dkz,
+                                 float vabx, float vaby, float vabz, upair_acc *a)
+{
+    const int bi = s->boundary[i] != 0, bj = s->boundary[j] != 0;
+    const float solid_i = s->solid[i], fluid_i = s->fluid[i], solid_j = s->solid[j], fluid_j = s->fluid[j];
+    const float dens_i = s->dens[i], press_i = s->press[i], press_j = s->press[j];
+    const float *vi = s->vel + 3 * (size_t)i, *dpi = s->delpress + 3 * (size_t)i;
+    float mass_solid_frac = solid_i * U_RHO_0_SAND / (U_RHO_0_SAND * solid_i + U_RHO_0 * (fluid_i));      /* :314 */
+    float mass_fluid_frac = fluid_i * U_RHO_0 / (U_RHO_0_SAND * solid_i + U_RHO_0 * (fluid_i));           /* :315 */
+    if (mass_solid_frac > 0.001 && mass_solid_frac < 0.999 && mass_fluid_frac > 0.001 && mass_fluid_frac < 0.999 && !bi && !bj) {   /* :317 */
+        const float dk[3] = {dkx, dky, dkz}, vab[3] = {vabx, vaby, vabz};
+        for (int c = 0; c < 3; c++) {
+            float solidgrad = (solid_j - solid_i) * dk[c];                                                 /* :318-320 */
+            float fluidgrad = (fluid_j - fluid_i) * dk[c];                                                 /* :322-324 */
+            float solidbrownian = (solidgrad / (solid_i) - (mass_solid_frac * solidgrad / (solid_i) + mass_fluid_frac * fluidgrad / (fluid_i)));   /* :326-328 */
+            float fluidbrownian = (fluidgrad / (fluid_i) - (mass_fluid_frac * fluidgrad / (fluid_i) + mass_solid_frac * solidgrad / (solid_i)));   /* :330-332 */
+            float solidpressureslip = (solid_i * press_i - solid_j * press_j) * dk[c] - mass_solid_frac * (solid_i * press_i - solid_j * press_j) * dk[c] -
+                                      mass_fluid_frac * ((fluid_i) * press_i - (fluid_j) * press_j) * dk[c];                                         /* :334-336 */
+            float fluidpressureslip = (fluid_i * press_i - fluid_j * press_j) * dk[c] - mass_solid_frac * (solid_i * press_i - solid_j * press_j) * dk[c] -
+                                      mass_fluid_frac * ((fluid_i) * press_i - (fluid_j) * press_j) * dk[c];                                         /* :338-340 */
+            /* :342-348 — the second factor is (150.0 / dens) * delpress_c - xvel*dkx*vab_c - yvel*dky*vab_c - zvel*dkz*vab_c, + GRAVITY for z */
+            double second = (c == 2 ? P->gravity : 0.0) + (150.0 / dens_i) * dpi[c] - vi[0] * dkx * vab[c] - vi[1] * dky * vab[c] - vi[2] * dkz * vab[c];
+            if (c != 2) second = (150.0 / dens_i) * dpi[c] - vi[0] * dkx * vab[c] - vi[1] * dky * vab[c] - vi[2] * dkz * vab[c];
+            float solidbody = (solid_i * dens_i - (mass_solid_frac * solid_i * dens_i + mass_fluid_frac * fluid_i * dens_i)) * second;
+            float fluidbody = (fluid_i * dens_i - (mass_solid_frac * solid_i * dens_i + mass_fluid_frac * fluid_i * dens_i)) * second;
+            a->sdrift[c] += (float)(U_MIXPRESSURE * (solidbody + solidpressureslip) - U_MIXBROWNIAN * solidbrownian);                                  /* :350-352 */
+            a->fdrift[c] += (float)(U_MIXPRESSURE * (fluidbody + fluidpressureslip) - U_MIXBROWNIAN * fluidbrownian);                                  /* :354-356 */
+        }
+    }
+    /* :368 */
+    float mixfactor = (!bj) * (!bi) * (solid_i > 0.0) * (solid_j > 0.0) * 2 * (solid_i - 0.0) * (solid_j - 0.0) / (solid_i - 0.0 + solid_j - 0.0 + 0.01);
+    {
+        const float dk[3] = {dkx, dky, dkz}, vab[3] = {vabx, vaby, vabz};
+        for (int p = 0; p < 3; p++)
+            for (int q = 0; q < 3; q++) a->vel_grad[3 * p + q] += (float)(-mixfactor * vab[q] * dk[p] * 1. / dens_i);                               /* :369-377 */
+        const float *st = s->stress_tensor + 9 * (size_t)i;
+        for (int p = 0; p < 3; p++) {                                                                                                              /* :379-381 */
+            a->stress_accel[p] += (float)(mixfactor * (st[3 * p + 0] * dkx + st[3 * p + 1] * dky + st[3 * p + 2] * dkz) / pow(dens_i, 2) +
+                                          (st[3 * p + 0] * dkx + st[3 * p + 1] * dky + st[3 * p + 2] * dkz) / pow(dens_i, 2));
+        }
+    }
+}
+
+/* Pass B of one in-range pair (FluidGPU-unidyn.cu:383-401) with the completed drift velocities (race-free reading, see the header). */
+static inline void upair_mixed_b(const fsgo_ustate *s, const upair_acc *acc, int i, int j, float dkx, float dky, float dkz,
+                                 float vabx, float vaby, float vabz, upair_acc *a)
+{
+    const int bi = s->boundary[i] != 0, bj = s->boundary[j] != 0;
+    const float solid_i = s->solid[i], fluid_i = s->fluid[i], solid_j = s->solid[j], fluid_j = s->fluid[j];
+    const float dens_i = s->dens[i], dens_j = s->dens[j];
+    const float *sdi = acc[i].sdrift, *sdj = acc[j].sdrift, *fdi = acc[i].fdrift, *fdj = acc[j].fdrift;
+    float ds2 = sdj[0] * dkx + sdj[1] * dky + sdj[2] * dkz;          /* :383-387 (dot_prod, FluidGPU-unidyn.cu:46) */
+    float ds = sdi[0] * dkx + sdi[1] * dky + sdi[2] * dkz;
+    float df2 = fdj[0] * dkx + fdj[1] * dky + fdj[2] * dkz;
+    float df = fdi[0] * dkx + fdi[1] * dky + fdi[2] * dkz;
+    for (int c = 0; c < 3; c++)                                       /* :391-398 */
+        a->mix[c] += -1 / dens_i / dens_j * (solid_j * dens_j * (solid_j * sdj[c] * ds2 + solid_i * sdi[c] * ds) +
+                                              fluid_j * dens_j * (fluid_j * fdj[c] * df2 + fluid_i * fdi[c] * df));
+    /* :400-401 */
+    a->delsolid += (float)((!bj) * (!bi) * -0.5 / dens_j * (solid_i + solid_j) * (dkx * vabx + dky * vaby + dkz * vabz) +
+                           (-(solid_i * sdi[0] + solid_j * sdj[0]) * dkx - (solid_i * sdi[1] + solid_j * sdj[1]) * dky -
+                            (solid_i * sdi[2] + solid_j * sdj[2]) * dkz) / dens_j);
+    a->delfluid += (float)((!bj) * (!bi) * -0.5 / dens_j * (fluid_i + fluid_j) * (dkx * vabx + dky * vaby + dkz * vabz) +
+                           (-(fluid_i * fdi[0] + fluid_j * fdj[0]) * dkx - (fluid_i * fdi[1] + fluid_j * fdj[1]) * dky -
+                            (fluid_i * fdi[2] + fluid_j * fdj[2]) * dkz) / dens_j);
+}
+
+/* The granular stress update of one particle (FluidGPU-unidyn.cu:410-446), once per step with the completed vel_grad. */
+static void ustress_update(const fsgo_ustate *s, const upair_acc *a, int i)
+{
+    if (!(s->solid[i])) return;                                       /* :411 */
+    float *st = s->stress_tensor + 9 * (size_t)i, *sr = s->stress_rate + 9 * (size_t)i;
+    const float press = s->press[i];
+    float strain[9];
+    float tr = 0, tr2 = 0, tr3 = 0, tr4 = 0, tr5 = 0;
+    /* strain_rate is complete before the traces that read its transpose are formed (the reference forms tr4 from strain_rate[q][p]
+       inside the same loop, i.e. partly from the previous step's values — an artefact the race-free reading drops) */
+    for (int p = 0; p < 3; p++)
+        for (int q = 0; q < 3; q++) strain[3 * p + q] = 0.5 * (a[i].vel_grad[3 * p + q] + a[i].vel_grad[3 * q + p]);        /* :419 */
+    for (int p = 0; p < 3; p++) {
+        for (int q = 0; q < 3; q++) {
+            tr3 += 0.5 * st[3 * p + q] * st[3 * p + q];                                                                  /* :421 */
+            tr5 += strain[3 * p + q] * strain[3 * p + q];                                                               /* :423 */
+            tr4 += st[3 * p + q] * strain[3 * q + p];                                                                   /* :424 */
+        }
+        tr += strain[3 * p + p];                                                                                        /* :426 */
+        tr2 += st[3 * p + p];
+    }
+    (void)tr2;
+    for (int p = 0; p < 3; p++) {
+        for (int q = 0; q < 3; q++) {
+            /* :435-437 */
+            if (3 * tan(U_PHI) / (sqrt(9 + 12 * pow(tan(U_PHI), 2))) * press * (press > 0) + U_KC / (sqrt(9 + 12 * pow(tan(U_PHI), 2))) < tr3 && tr3 != 0) {
+                st[3 * p + q] *= (3 * tan(U_PHI) / (sqrt(9 + 12 * pow(tan(U_PHI), 2))) * press * (press > 0) + U_KC / (sqrt(9 + 12 * pow(tan(U_PHI), 2)))) / tr3;
+            }
+            /* :438 */
+            sr[3 * p + q] = 3 * U_C1 * (press) * (strain[3 * p + q] - 1. / 3. * tr * (p == q)) +
+                            U_C1 * U_C2 * (tr4 + tr * press * (press > 0)) / (pow(press, 2) + 1e8) * st[3 * p + q] - U_C1 * U_C3 * sqrt(tr5) * st[3 * p + q];
+        }
+    }
+}
+
+static inline void upair_mixed_a(const fsgo_params *P, const fsgo_ustate *s, int i, int j, float dkx, float dky, float dkz,
+                                 float vabx, float vaby, float vabz, upair_acc *a);
+static inline void upair_mixed_b(const fsgo_ustate *s, const upair_acc *acc, int i, int j, float dkx, float dky, float dkz,
+                                 float vabx, float vaby, float vabz, upair_acc *a);
+
+/* pair body, FluidGPU-unidyn.cu:258-401 (== :679-821 of mykernel3).  pass 0: the live terms (+ the mixed-phase / granular pass-A
+ * terms when the scene is mixed); pass 1 (mixed scenes only): mixture_accel / delsolid / delfluid from the completed drift sums `acc`. */
+static inline void upair_body(const fsgo_params *P, const fsgo_ustate *s, int i, int j, upair_acc *a, long long *st, int mixed, int pass,
+                              const upair_acc *acc)
 {
     const double cutoff = P->h;
     const float *pi = s->pos + 3 * (size_t)i, *pj = s->pos + 3 * (size_t)j;
     float rabx = pi[0] - pj[0], raby = pi[1] - pj[1], rabz = pi[2] - pj[2];
     float ds = sqrt(powf(rabx, 2) + powf(raby, 2) + powf(rabz, 2));   /* cuh:211-213: double sqrt of a float sum, narrowed */
-    st[0]++;
+    if (pass == 0) st[0]++;
     if (ds <= (2 * cutoff) && ds > 0) {                                /* cu:287 */
-        st[1]++;
+        if (pass == 0) st[1]++;
         float k = fsgo_kernel_h(ds, cutoff);
         const float *vi = s->vel + 3 * (size_t)i, *vj = s->vel + 3 * (size_t)j;
         float vabx = vi[0] - vj[0], vaby = vi[1] - vj[1], vabz = vi[2] - vj[2];
         float dkx = fsgo_kernel_derivative_h(ds, cutoff) * rabx / ds;  /* cu:296-298 */
         float dky = fsgo_kernel_derivative_h(ds, cutoff) * raby / ds;
         float dkz = fsgo_kernel_derivative_h(ds, cutoff) * rabz / ds;
+        if (pass == 1) { upair_mixed_b(s, acc, i, j, dkx, dky, dkz, vabx, vaby, vabz, a); return; }
         float d = vabx * rabx + vaby * raby + vabz * rabz;             /* cu:304 */
         float d2 = powf(ds, 2);                                        /* cu:305 */
         int bi = s->boundary[i] != 0, bj = s->boundary[j] != 0;
@@ -88,6 +223,7 @@ static inline void upair_body(const fsgo_params *P, const fsgo_ustate *s, int i,
         a->dx += mass / dj * dkx * !bj * !bi;                          /* cu:364-366 */
         a->dy += mass / dj * dky * !bj * !bi;
         a->dz += mass / dj * dkz * !bj * !bi;
+        if (mixed) { upair_mixed_a(P, s, i, j, dkx, dky, dkz, vabx, vaby, vabz, a); return; }     /* delfluid comes from pass B there */
         /* cu:401 with zero drift velocities: (!bj)(!bi) * -0.5/dens_j * (fluid_i+fluid_j) * (dk . vab) + (-0...)/dens_j */
         a->delfluid += (float)((!bj) * (!bi) * -0.5 / dj * (fluid_i + s->fluid[j]) * (dkx * vabx + dky * vaby + dkz * vabz) +
                                (-(fluid_i * 0.0f + s->fluid[j] * 0.0f) * dkx - (fluid_i * 0.0f + s->fluid[j] * 0.0f) * dky -
@@ -157,9 +293,11 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
     (void)t;
     const int n = s->n, G = P->grid, numcells = G * G * G;
     int rc = -1;
-    /* scope check */
+    /* scope: a mixed-phase / granular scene needs the stress arrays */
+    int mixed = 0;
     for (int i = 0; i < n; i++)
-        if (!s->boundary[i] && s->solid[i] != 0.0f) return -2;
+        if (!s->boundary[i] && s->solid[i] != 0.0f) mixed = 1;
+    if (mixed && (!s->stress_tensor || !s->stress_rate)) return -2;
 
     int *perm = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
     float *tmp = (float *)malloc(sizeof(float) * 3 * (size_t)(n > 0 ? n : 1));
@@ -168,9 +306,10 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
     int *split = (int *)malloc(sizeof(int) * (size_t)numcells);
     int *cnt = (int *)calloc((size_t)numcells + 2, sizeof(int));
     upair_acc *acc = (upair_acc *)calloc((size_t)(n > 0 ? n : 1), sizeof(upair_acc));
+    upair_acc *accb = (upair_acc *)calloc((size_t)(n > 0 ? n : 1), sizeof(upair_acc));
     int *occ = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
     long long st[4] = {0, 0, 0, 0};
-    if (!perm || !tmp || !start || !end || !split || !cnt || !acc || !occ) goto done;
+    if (!perm || !tmp || !start || !end || !split || !cnt || !acc || !accb || !occ) goto done;
 
     /* ---- solver-unidyn.cu:331 stable sort by cell id (out-of-grid ids last) ---- */
     for (int i = 0; i < n; i++) {
@@ -194,6 +333,13 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
     permute_f(s->newdelpress, perm, n, 3, tmp);
     permute_f(s->solid, perm, n, 1, tmp);
     permute_f(s->fluid, perm, n, 1, tmp);
+    if (s->stress_tensor && s->stress_rate) {
+        float *t9 = (float *)malloc(sizeof(float) * 9 * (size_t)(n > 0 ? n : 1));
+        if (!t9) goto done;
+        permute_f(s->stress_tensor, perm, n, 9, t9);
+        permute_f(s->stress_rate, perm, n, 9, t9);
+        free(t9);
+    }
     {
         int *ti = (int *)tmp;
         for (int i = 0; i < n; i++) ti[i] = s->index[perm[i]];
@@ -243,8 +389,8 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
     if (end_out) memcpy(end_out, end, sizeof(int) * (size_t)numcells);
     if (split_out) memcpy(split_out, split, sizeof(int) * (size_t)numcells);
 
-    /* ---- mykernel (coarse bins) + mykernel3 (split bins, per octant) ---- */
-    {
+    /* ---- mykernel (coarse bins) + mykernel3 (split bins, per octant); mixed scenes: pass A, then pass B with the completed drift sums ---- */
+    for (int pass = 0; pass < (mixed ? 2 : 1); pass++) {
         int nthreads = P->threads;
         (void)nthreads;
         long long t0 = 0, t1 = 0, t2 = 0;
@@ -268,10 +414,12 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
                 if (split[bidx] == -1) {
                     int nc = ucandidates(P, bidx, nb27, 27, start, end, nlive, cand, cand_max, &drop);
                     for (int i = start[bidx]; i <= end[bidx]; i++) {
-                        upair_acc a = {0, 0, 0, 0, 0, 0, 0, 0};
+                        upair_acc a;
+                        memset(&a, 0, sizeof a);
                         for (int q = 0; q < nc; q++)
-                            if (cand[q] >= 0) upair_body(P, s, i, cand[q], &a, lst);
-                        acc[i] = a;
+                            if (cand[q] >= 0) upair_body(P, s, i, cand[q], &a, lst, mixed, pass, acc);
+                        if (pass == 0) acc[i] = a;
+                        else { memcpy(accb[i].mix, a.mix, sizeof a.mix); accb[i].delsolid = a.delsolid; accb[i].delfluid = a.delfluid; }
                     }
                 } else {
                     for (int oct = 0; oct < 8; oct++) {
@@ -285,10 +433,12 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
                         int nc = ucandidates(P, bidx, nb8, 8, start, end, nlive, cand, cand_max, &drop);
                         for (int i = start[bidx]; i <= end[bidx]; i++) {
                             if (s->subindex[i] != oct) continue;
-                            upair_acc a = {0, 0, 0, 0, 0, 0, 0, 0};
+                            upair_acc a;
+                            memset(&a, 0, sizeof a);
                             for (int q = 0; q < nc; q++)
-                                if (cand[q] >= 0) upair_body(P, s, i, cand[q], &a, lst);
-                            acc[i] = a;
+                                if (cand[q] >= 0) upair_body(P, s, i, cand[q], &a, lst, mixed, pass, acc);
+                            if (pass == 0) acc[i] = a;
+                            else { memcpy(accb[i].mix, a.mix, sizeof a.mix); accb[i].delsolid = a.delsolid; accb[i].delfluid = a.delfluid; }
                         }
                     }
                 }
@@ -298,9 +448,19 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
             }
             free(cand);
         }
-        st[0] = t0;
-        st[1] = t1;
-        st[2] = t2;
+        if (pass == 0) {
+            st[0] = t0;
+            st[1] = t1;
+            st[2] = t2;
+        }
+    }
+    if (mixed) {
+        for (int i = 0; i < nlive; i++) {           /* pass B results join the sums; then the stress update (cu:410-446), once per particle */
+            memcpy(acc[i].mix, accb[i].mix, sizeof accb[i].mix);
+            acc[i].delsolid = accb[i].delsolid;
+            acc[i].delfluid = accb[i].delfluid;
+        }
+        for (int i = 0; i < nlive; i++) ustress_update(s, acc, i);
     }
 
     /* ---- mykernel2 (cu:451-497) + Particle::update(t) (cuh:296-423) + cell_calc (cu:544-551) ---- */
@@ -312,7 +472,9 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
             float ndx = s->newdelpress[3 * (size_t)i + 0] + acc[i].px, ndy = s->newdelpress[3 * (size_t)i + 1] + acc[i].py,
                   ndz = s->newdelpress[3 * (size_t)i + 2] + acc[i].pz;
             float diffx = acc[i].dx, diffy = acc[i].dy, diffz = acc[i].dz;
-            float delfluid = acc[i].delfluid, delsolid = 0.0f;
+            float delfluid = acc[i].delfluid, delsolid = mixed ? acc[i].delsolid : 0.0f;
+            const float sa0 = mixed ? acc[i].stress_accel[0] : 0.0f, sa1 = mixed ? acc[i].stress_accel[1] : 0.0f, sa2 = mixed ? acc[i].stress_accel[2] : 0.0f;
+            const float ma0 = mixed ? acc[i].mix[0] : 0.0f, ma1 = mixed ? acc[i].mix[1] : 0.0f, ma2 = mixed ? acc[i].mix[2] : 0.0f;
             if (spts) { spts[3 * (size_t)i] = x[0]; spts[3 * (size_t)i + 1] = x[1]; spts[3 * (size_t)i + 2] = x[2]; }   /* cu:462-464 */
             if (a3) a3[i] = 1.0f;                                                                                       /* mass, :465 */
             if (b3) b3[i] = powf(diffx, 2) + powf(diffy, 2) + powf(diffz, 2);                                          /* :466 */
@@ -322,6 +484,8 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
             s->press[i] = u_pressure(s->dens[i], solid, P->sound);       /* cuh:301 */
             float *dp = s->delpress + 3 * (size_t)i;
             dp[0] = ndx; dp[1] = ndy; dp[2] = ndz;                      /* cuh:302 */
+            if (s->stress_tensor && s->stress_rate)                      /* cuh:304-308 */
+                for (int pq = 0; pq < 9; pq++) s->stress_tensor[9 * (size_t)i + pq] = DT * s->stress_rate[9 * (size_t)i + pq];
             if (!bnd) {
                 volatile float friction = fabsf(diffx) + fabsf(diffy) + fabsf(diffz);   /* cuh:311 */
                 solid += DT * delsolid;                                   /* :312-313 */
@@ -336,16 +500,16 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
                 x[1] = x[1] + DT * v[1] + 0.5 * DT * DT * a[1] + 0 * diffy;
                 x[2] = x[2] + DT * v[2] + 0.5 * DT * DT * a[2] + 0 * diffz;
                 if (x[2] < -0.89) { v[0] = 0; v[1] = 0; }                 /* :332-341 */
-                /* :351-353 — stress_accel = mixture_accel = 0 here; the y and z lines test the NEW xvel (sic) */
-                v[0] = (v[0] + 0.5 * DT * a[0] + DT * (0.0f) + 5 * DT * DT * (0.0f)) -
-                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) > 0) * friction * 0.0000002 * solid +
-                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) < 0) * friction * 0.0000002 * solid;
-                v[1] = (v[1] + 0.5 * DT * a[1] + DT * (0.0f) + 5 * DT * DT * (0.0f)) -
-                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) > 0) * friction * 0.0000002 * solid +
-                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) < 0) * friction * 0.0000002 * solid;
-                v[2] = (v[2] + 0.5 * DT * a[2] + DT * (0.0f) + 5 * DT * DT * (0.0f)) -
-                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) > 0) * friction * 0.0000002 * solid +
-                       ((v[0] + DT * a[0] + DT * (0.0f) + DT * DT * (0.0f)) < 0) * friction * 0.0000002 * solid;
+                /* :351-353 — the y and z lines test the NEW xvel and xacc (sic), with their own stress_accel / mixture_accel component */
+                v[0] = (v[0] + 0.5 * DT * a[0] + DT * (sa0) + 5 * DT * DT * (ma0)) -
+                       ((v[0] + DT * a[0] + DT * (sa0) + DT * DT * (ma0)) > 0) * friction * 0.0000002 * solid +
+                       ((v[0] + DT * a[0] + DT * (sa0) + DT * DT * (ma0)) < 0) * friction * 0.0000002 * solid;
+                v[1] = (v[1] + 0.5 * DT * a[1] + DT * (sa1) + 5 * DT * DT * (ma1)) -
+                       ((v[0] + DT * a[0] + DT * (sa1) + DT * DT * (ma1)) > 0) * friction * 0.0000002 * solid +
+                       ((v[0] + DT * a[0] + DT * (sa1) + DT * DT * (ma1)) < 0) * friction * 0.0000002 * solid;
+                v[2] = (v[2] + 0.5 * DT * a[2] + DT * (sa2) + 5 * DT * DT * (ma2)) -
+                       ((v[0] + DT * a[0] + DT * (sa2) + DT * DT * (ma2)) > 0) * friction * 0.0000002 * solid +
+                       ((v[0] + DT * a[0] + DT * (sa2) + DT * DT * (ma2)) < 0) * friction * 0.0000002 * solid;
                 /* :357-359 */
                 a[0] = -((220.0 - 70.0 * solid) / s->dens[i]) * dp[0];
                 a[1] = -((220.0 - 70.0 * solid) / s->dens[i]) * dp[1];
@@ -386,6 +550,6 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
     if (stats) memcpy(stats, st, sizeof(st));
     rc = 0;
 done:
-    free(perm); free(tmp); free(start); free(end); free(split); free(cnt); free(acc); free(occ);
+    free(perm); free(tmp); free(start); free(end); free(split); free(cnt); free(acc); free(accb); free(occ);
     return rc;
 }

@@ -25,7 +25,8 @@ class State(C.Structure):
 
 class UState(C.Structure):
     _fields_ = [("n", C.c_int)] + [(k, C.c_void_p) for k in ("pos", "vel", "acc", "dens", "press", "delpress", "newdens",
-                                                              "newdelpress", "index", "cell", "boundary", "solid", "fluid", "subindex")]
+                                                              "newdelpress", "index", "cell", "boundary", "solid", "fluid", "subindex",
+                                                              "stress_tensor", "stress_rate")]
 
 
 _lib = None
@@ -93,6 +94,8 @@ class OracleSimUnidyn:
         self.n = n
         self.s["cell"] = np.clip(cell_ids(self.p, self.s["pos"]), -1, params.grid ** 3).astype(np.int32)
         self.s.setdefault("subindex", np.zeros(n, np.int32))
+        self.s.setdefault("stress_tensor", np.zeros((n, 9), np.float32))
+        self.s.setdefault("stress_rate", np.zeros((n, 9), np.float32))
         nc = params.grid ** 3
         self.cells_sorted = np.zeros(n, np.int32)
         self.start, self.end, self.split = np.zeros(nc, np.int32), np.zeros(nc, np.int32), np.zeros(nc, np.int32)
@@ -104,7 +107,7 @@ class OracleSimUnidyn:
         st = UState()
         st.n = self.n
         for k in ("pos", "vel", "acc", "dens", "press", "delpress", "newdens", "newdelpress", "index", "cell", "boundary", "solid",
-                  "fluid", "subindex"):
+                  "fluid", "subindex", "stress_tensor", "stress_rate"):
             setattr(st, k, self.s[k].ctypes.data)
         for _ in range(nsteps):
             rc = self.lib.fsgo_unidyn_step(C.byref(self.p), C.byref(st), self.t, self.cells_sorted.ctypes.data, self.start.ctypes.data,

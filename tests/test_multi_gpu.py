@@ -65,7 +65,11 @@ def test_the_real_unidyn_driver_links_and_runs_against_libfsg(tmp_path):
         assert a.exists() and b.exists(), t
         (pa, ma, sa), (pb, mb, sb) = _read_vtk_ascii(a), _read_vtk_ascii(b)
         assert pa.shape == pb.shape
-        oa, ob = np.lexsort(pa.T[::-1]), np.lexsort(pb.T[::-1])
-        err = float(np.sqrt(((pa[oa] - pb[ob]) ** 2).sum() / (pb ** 2).sum()))
+        # frames carry no particle index and each run writes its own sorted order: match every particle of one frame with its
+        # nearest neighbour in the other (particle spacing 0.04 .. 0.05 >> the differences looked for); the match must be one to one
+        from scipy.spatial import cKDTree
+        dist, nn = cKDTree(pb).query(pa)
+        assert len(np.unique(nn)) == len(nn), t
+        err = float(np.sqrt((dist ** 2).sum() / (pb ** 2).sum()))
         assert err <= 1e-4, (t, err)
-        assert np.array_equal(ma, mb)
+        assert np.array_equal(ma, mb[nn])
