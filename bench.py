@@ -271,8 +271,12 @@ def reference_gpu_leg(fsg, torch, steps=100):
     s3["solid"], s3["fluid"] = np.zeros(n3, np.float32), np.ones(n3, np.float32)
     r = ref("ref_harness_unidyn_g128", s3, ukeys, 10, 600)
     o = ours(cfg, s3, 20)
+    # the SAME model on both sides: libfsg's unidyn path on that scene (unit-box floor / walls off, as in the rebuilt reference)
+    ucfg = fsg.FluidSolver.unidyn_config(capacity=n3, grid=128, origin=cfg.origin, unidyn_open_box=1)
+    ou = ours(ucfg, s3, 10)
     res["plume128"] = {"scene": f"synthetic plume 128^3 bins, {n3} particles (the largest grid the reference's launch shapes address)", "steps": 10,
-                       "ref_ms": r.get("ms_per_step"), "fsg_ms": o, "ref_detail": r,
+                       "ref_ms": r.get("ms_per_step"), "fsg_ms": o, "fsg_unidyn_ms": ou, "ref_detail": r,
+                       "speedup_same_model": (r["ms_per_step"] / ou) if r.get("ms_per_step") else None,
                        "note": "reference = its unidyn kernels rebuilt with build-time constants for a 128^3 grid (oracle/Makefile); throughput comparison, "
                                "different update physics (leapfrog vs Euler), same pair sums"}
     for v in res.values():

@@ -22,7 +22,7 @@ class FsgConfig(C.Structure):
         ("alpha_boundary", C.c_double), ("neighbour_cap", C.c_int32), ("bin_cap", C.c_int32), ("capacity", C.c_int64),
         ("device", C.c_int32), ("pair_fp64", C.c_int32), ("collect_stats", C.c_int32), ("rank", C.c_int32),
         ("world", C.c_int32), ("slab_x0", C.c_int32), ("slab_x1", C.c_int32),
-        ("pair_mode", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("pair_mode", C.c_int32), ("unidyn_open_box", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 

@@ -48,6 +48,7 @@ void fsg_update_pair_mode(fsg_ctx *c)
 void fsg_derive_constants(const fsg_config &cfg, FsgDev &d)
 {
     d.sym = 0;
+    d.uni_open = cfg.unidyn_open_box != 0;
     d.G = cfg.grid;
     d.G2 = cfg.grid * cfg.grid;
     d.numcells = cfg.grid * cfg.grid * cfg.grid;

@@ -19,6 +19,7 @@ struct FsgDev {
     int rl, rr;      // slab contexts: layers [x0, rl) and [rr, x1) are within two layers of a face that has a neighbour
     int bx0, bx1;    // interior layers [bx0, bx1): home bins outside are the slab's boundary bins (done first when the
                      // exchange overlaps the interior; == x0, x1 otherwise)
+    int uni_open;    // unidyn: 1 = no unit-box floor / walls in Particle::update (fsg_config.unidyn_open_box)
     int sym;         // 1: the symmetric pair kernel runs (fsg_pair_v3.cu): the ghost layer x0 - 1 is listed as home bins too
     int dead;        // key of a slot that no longer holds a particle of this slab (sorts last, is trimmed)
     int cap, bin_cap;

@@ -251,7 +251,7 @@ __device__ __forceinline__ void unidyn_particle_update(const FsgDev &d, float4 &
         float y = (float)((double)pd.y + DT * (double)vp.y + 0.5 * DT * DT * (double)af.y + (double)(0 * diffy));
         float z = (float)((double)pd.z + DT * (double)vp.z + 0.5 * DT * DT * (double)af.z + (double)(0 * diffz));
         float vx = vp.x, vy = vp.y, vz = vp.z;
-        if ((double)z < -0.89) { vx = 0; vy = 0; }                        // :332-341
+        if (!d.uni_open && (double)z < -0.89) { vx = 0; vy = 0; }         // :332-341
         // :351-353 — the y and z lines test the NEW xvel with xacc (sic), each with its own stress_accel / mixture_accel component
         const double fr = (double)friction * 0.0000002 * (double)solid;
         double tx = (double)vx + DT * (double)af.x + DT * (double)mt.sa[0] + DT * DT * (double)mt.ma[0];
@@ -266,9 +266,11 @@ __device__ __forceinline__ void unidyn_particle_update(const FsgDev &d, float4 &
         vx = (float)((double)vx + 0.5 * (double)af.x * DT);                // :390-392
         vy = (float)((double)vy + 0.5 * (double)af.y * DT);
         vz = (float)((double)vz + 0.5 * (double)af.z * DT);
-        if ((double)fabsf(z) > 0.98) { z = (float)(0.97 / (double)z); vz = 0; }               // :404-413
-        if ((double)fabsf(y) > 0.98) vy = -vy;
-        if ((double)fabsf(x) > 0.98) vx = -vx;
+        if (!d.uni_open) {          // the reference's unit-box floor and walls are literals of Particle::update (fsg_config.unidyn_open_box)
+            if ((double)fabsf(z) > 0.98) { z = (float)(0.97 / (double)z); vz = 0; }           // :404-413
+            if ((double)fabsf(y) > 0.98) vy = -vy;
+            if ((double)fabsf(x) > 0.98) vx = -vx;
+        }
         pd.x = x; pd.y = y; pd.z = z;
         vp.x = vx; vp.y = vy; vp.z = vz;
         mx.x = solid; mx.y = fluid;

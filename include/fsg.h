@@ -84,7 +84,10 @@ typedef struct fsg_config {
                                two bins is evaluated once and added to both through float reductions, so sums are
                                reproducible to rounding (~1e-7), not bit for bit; 1: deterministic gather kernel
                                (every particle sums its own 27 bins in a fixed order)                         */
-    int32_t reserved[2];
+    int32_t unidyn_open_box; /* unidyn model.  0 (default): Particle::update keeps the reference's literal unit-box floor and walls
+                               (z < -0.89, |x|,|y|,|z| > 0.98, FluidGPU-unidyn.cuh:332,404-411); 1: they are switched off, for domains
+                               other than [-1,1]^3 (the reference has to be rebuilt for that: oracle/Makefile, ref_harness_unidyn_g128) */
+    int32_t reserved[1];
 } fsg_config;
 
 /* Host-side structure-of-arrays view used by fsg_upload_soa / fsg_download_soa: the live fields
