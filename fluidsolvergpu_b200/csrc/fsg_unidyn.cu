@@ -17,13 +17,28 @@
 
 #include "fsg_unidyn.cuh"
 
+// Pure-fluid pair sums, one warp per home bin.  The neighbourhood (27 bins by linear offset, the first UNI_TILE = 1024 neighbour
+// particles like the reference's 1024 threads) is staged in tiles of UP_TILE candidates — position + density and the sorted slot,
+// 22 bytes each, so that 16 warps are resident per SM (the first version staged 39 bytes x 1024 per warp and ran 4 warps per
+// SM) — and every home particle sweeps only the candidate ranges it may see: everything for an unsplit bin, the four (dx, dy)
+// columns x two z-adjacent bins of its octant for a split one (contiguous in the staged order).  In-range candidates are
+// compacted into a queue; their velocity / pressure / volume fraction come from global memory (L2) when the pair is evaluated.
+#define UP_WARPS 4
+#define UP_TILE 512
+struct UpWarpSmem {
+    float4 sp[UP_TILE];                 // x, y, z, +-dens (sign = boundary)
+    int sj[UP_TILE];                    // sorted slot of the candidate
+    unsigned short q[UP_TILE];
+};
+#define UP_SMEM (sizeof(UpWarpSmem) * UP_WARPS)
+
 template <bool STATS>
-__global__ void __launch_bounds__(UNI_WARPS * 32)
+__global__ void __launch_bounds__(UP_WARPS * 32)
 k_pair_unidyn(UniArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    UniWarpSmem &S = reinterpret_cast<UniWarpSmem *>(s_raw)[warp];
+    UpWarpSmem &S = reinterpret_cast<UpWarpSmem *>(s_raw)[warp];
     const FsgDev &d = a.d;
     const int nocc = *a.nocc;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -60,113 +75,134 @@ k_pair_unidyn(UniArgs a)
         const int hs = __shfl_sync(FULL, st, 13), hn = __shfl_sync(FULL, p, 13);
         const bool split = hn > 6;                  // cu:181
 
-        // ---- stage the neighbourhood ----
-        __syncwarp();
-#pragma unroll 1
-        for (int t = 0; t < 27; t++) {
-            int pt = __shfl_sync(FULL, p, t);
-            if (pt == 0) continue;
-            int ex = __shfl_sync(FULL, excl, t), stt = __shfl_sync(FULL, st, t);
-            int hi = min(ex + pt, C);
-            for (int k = ex + lane; k < hi; k += 32) {
-                int j = stt + (k - ex);
-                float4 pj = a.A.posd[j], vj = a.A.velp[j];
-                float dj = fabsf(pj.w);
-                vj.w = vj.w / (dj * dj);              // press / powf(dens, 2), cu:310
-                S.sp[k] = pj;
-                S.sv[k] = vj;
-                S.sf[k] = a.A.mix[j].y;
-                S.tag[k] = (unsigned char)t;
-            }
-        }
-        __syncwarp();
-
         for (int ig = 0; ig < hn; ig += 32) {
             const int gcount = min(32, hn - ig);
             float s_nd = 0.f, s_x = 0.f, s_y = 0.f, s_z = 0.f, s_dx = 0.f, s_dy = 0.f, s_dz = 0.f, s_df = 0.f;
 #pragma unroll 1
-            for (int il = 0; il < gcount; il++) {
-                const int i = hs + ig + il;
-                const float4 pi = a.A.posd[i], vi = a.A.velp[i];
-                const float4 mi = a.A.mix[i];
-                const float densi = fabsf(pi.w);
-                const bool bi = pi.w < 0.f;
-                const float pod2i = vi.w / (densi * densi);
-                const float solid_i = mi.x, fluid_i = mi.y;
-                const unsigned allow = split ? uni_octant_mask(uni_subindex(d, pi.x, pi.y, pi.z)) : 0x7ffffffu;
-                int qn = 0, ntest = 0;
-                for (int c0 = 0; c0 < C; c0 += 32) {
-                    int c = c0 + lane;
-                    bool ok = false, in = false;
-                    if (c < C) {
-                        ok = (allow >> S.tag[c]) & 1u;
-                        float4 pj = S.sp[c];
-                        float d2 = dist2(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-                        in = ok && (d2 <= d.d2_max) && (d2 > 0.f);       // cu:287
-                    }
-                    unsigned mk = __ballot_sync(FULL, in);
-                    if (in) S.q[qn + __popc(mk & lt_mask)] = (unsigned short)c;
-                    qn += __popc(mk);
-                    if (STATS) ntest += __popc(__ballot_sync(FULL, ok));
-                }
-                if (STATS && lane == 0) { st_tested += ntest; st_in += qn; }
+            for (int t0 = 0; t0 < C; t0 += UP_TILE) {
+                const int t1 = min(t0 + UP_TILE, C);
+                // ---- stage candidates [t0, t1) of the concatenated neighbourhood ----
                 __syncwarp();
-                float t_nd = 0.f, t_x = 0.f, t_y = 0.f, t_z = 0.f, t_dx = 0.f, t_dy = 0.f, t_dz = 0.f, t_df = 0.f;
-                for (int q = lane; q < qn; q += 32) {
-                    const int c = S.q[q];
-                    const float4 pj = S.sp[c], vj = S.sv[c];
-                    const float fluid_j = S.sf[c];
-                    const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-                    const float ds = sqrtf(dist2(rx, ry, rz));
-                    const float densj = fabsf(pj.w);
-                    const bool bj = pj.w < 0.f;
-                    // W(ds), FluidGPU-unidyn.cu:11-21
-                    float w;
-                    const float qq = ds * d.inv_h;
-                    if (ds <= d.h_le) w = d.w_c * (1.f - 1.5f * qq * qq + 0.75f * qq * qq * qq);
-                    else if (ds <= d.twoh_lt) { float tt = 2.f - qq; w = d.w_c * 0.25f * tt * tt * tt; }
-                    else w = 0.f;
-                    t_nd += w * ((!bi && bj) ? 2.5f : 1.f);                         // cu:362 (mass == 1)
-                    if (ds <= d.h_lt) {                                             // support of dW, cu:35-43
-                        const float tt = d.hf - ds;
-                        const float g = d.dw_c * tt * tt / ds;
-                        const float dkx = g * rx, dky = g * ry, dkz = g * rz;       // cu:296-298
-                        const float vabx = vi.x - vj.x, vaby = vi.y - vj.y, vabz = vi.z - vj.z;
-                        const float dd = vabx * rx + vaby * ry + vabz * rz;         // cu:304
-                        float s = 0.f;
-                        if (dd < 0.f) {                                             // cu:307
-                            const float mu = dd / (ds * ds + d.eps);
-                            const float hm = d.hf * mu;
-                            const float bf = (!bi && bj) ? 1.f + (1.f + 3.f * fluid_i * fluid_i) * alpha_sb : 1.f;
-                            s = ((solid_i * 9.f + 1.f) * (float)d.alpha_fluid) * (float)d.sound * (hm + d.visc_q * hm * hm) /
-                                ((densi + densj) * 0.5f) * bf;
-                        }
-                        const float pp = vj.w + pod2i + s;                          // cu:310-312
-                        t_x += pp * dkx;
-                        t_y += pp * dky;
-                        t_z += pp * dkz;
-                        if (!bi && !bj) {
-                            const float inv = 1.f / densj;
-                            t_dx += inv * dkx;                                      // cu:364-366
-                            t_dy += inv * dky;
-                            t_dz += inv * dkz;
-                            t_df += -0.5f * inv * (fluid_i + fluid_j) * (dkx * vabx + dky * vaby + dkz * vabz);   // cu:401
-                        }
+#pragma unroll 1
+                for (int t = 0; t < 27; t++) {
+                    const int pt = __shfl_sync(FULL, p, t);
+                    if (pt == 0) continue;
+                    const int ex = __shfl_sync(FULL, excl, t), stt = __shfl_sync(FULL, st, t);
+                    const int lo = max(ex, t0), hi = min(ex + pt, t1);
+                    for (int k = lo + lane; k < hi; k += 32) {
+                        const int j = stt + (k - ex);
+                        S.sp[k - t0] = a.A.posd[j];
+                        S.sj[k - t0] = j;
                     }
                 }
+                __syncwarp();
+#pragma unroll 1
+                for (int il = 0; il < gcount; il++) {
+                    const int i = hs + ig + il;
+                    const float4 pi = a.A.posd[i], vi = a.A.velp[i];
+                    const float4 mi = a.A.mix[i];
+                    const float densi = fabsf(pi.w);
+                    const bool bi = pi.w < 0.f;
+                    const float pod2i = vi.w / (densi * densi);
+                    const float solid_i = mi.x, fluid_i = mi.y;
+                    // candidate ranges this particle sees: [0, C) or, in a split bin, 4 columns x 2 z-adjacent bins of its octant
+                    int nr = 1, zlo = 0;
+                    int ax = 0, ay = 0;
+                    if (split) {
+                        const int oct = uni_subindex(d, pi.x, pi.y, pi.z);            // cu:182-184, neighbourhood cu:579-583
+                        ax = (oct & 1) ? 1 : -1; ay = (oct & 2) ? 1 : -1;
+                        zlo = (oct & 4) ? 0 : 1;                                       // z offsets {-1, 0} (tags +0, +1) or {0, +1} (tags +1, +2)
+                        nr = 4;
+                    }
+                    int qn = 0, ntest = 0;
+#pragma unroll 1
+                    for (int r = 0; r < nr; r++) {
+                        int lo = 0, hi = C;
+                        if (split) {
+                            const int a_ = (r & 1) ? ax : 0, b_ = (r & 2) ? ay : 0;
+                            const int tl = (a_ + 1) * 9 + (b_ + 1) * 3 + zlo;
+                            lo = __shfl_sync(FULL, excl, tl);
+                            hi = __shfl_sync(FULL, excl, tl + 1) + __shfl_sync(FULL, p, tl + 1);
+                            hi = min(hi, C);
+                        }
+                        if (STATS) ntest += max(hi - lo, 0) * (t0 == 0);               // (counted once, not per tile)
+                        lo = max(lo, t0);
+                        hi = min(hi, t1);
+                        for (int c0 = lo; c0 < hi; c0 += 32) {
+                            const int c = c0 + lane;
+                            bool in = false;
+                            if (c < hi) {
+                                const float4 pj = S.sp[c - t0];
+                                const float d2 = dist2(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+                                in = (d2 <= d.d2_max) && (d2 > 0.f);                   // cu:287
+                            }
+                            const unsigned mk = __ballot_sync(FULL, in);
+                            if (in) S.q[qn + __popc(mk & lt_mask)] = (unsigned short)(c - t0);
+                            qn += __popc(mk);
+                        }
+                    }
+                    if (STATS && lane == 0) { st_tested += ntest; st_in += qn; }
+                    __syncwarp();
+                    float t_nd = 0.f, t_x = 0.f, t_y = 0.f, t_z = 0.f, t_dx = 0.f, t_dy = 0.f, t_dz = 0.f, t_df = 0.f;
+                    for (int q = lane; q < qn; q += 32) {
+                        const int c = S.q[q];
+                        const int j = S.sj[c];
+                        const float4 pj = S.sp[c];
+                        float4 vj = a.A.velp[j];
+                        const float fluid_j = a.A.mix[j].y;
+                        const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+                        const float ds = sqrtf(dist2(rx, ry, rz));
+                        const float densj = fabsf(pj.w);
+                        const bool bj = pj.w < 0.f;
+                        vj.w = vj.w / (densj * densj);                                  // press / powf(dens, 2), cu:310
+                        // W(ds), FluidGPU-unidyn.cu:11-21
+                        float w;
+                        const float qq = ds * d.inv_h;
+                        if (ds <= d.h_le) w = d.w_c * (1.f - 1.5f * qq * qq + 0.75f * qq * qq * qq);
+                        else if (ds <= d.twoh_lt) { float tt = 2.f - qq; w = d.w_c * 0.25f * tt * tt * tt; }
+                        else w = 0.f;
+                        t_nd += w * ((!bi && bj) ? 2.5f : 1.f);                         // cu:362 (mass == 1)
+                        if (ds <= d.h_lt) {                                             // support of dW, cu:35-43
+                            const float tt = d.hf - ds;
+                            const float g = d.dw_c * tt * tt / ds;
+                            const float dkx = g * rx, dky = g * ry, dkz = g * rz;       // cu:296-298
+                            const float vabx = vi.x - vj.x, vaby = vi.y - vj.y, vabz = vi.z - vj.z;
+                            const float dd = vabx * rx + vaby * ry + vabz * rz;         // cu:304
+                            float s = 0.f;
+                            if (dd < 0.f) {                                             // cu:307
+                                const float mu = dd / (ds * ds + d.eps);
+                                const float hm = d.hf * mu;
+                                const float bf = (!bi && bj) ? 1.f + (1.f + 3.f * fluid_i * fluid_i) * alpha_sb : 1.f;
+                                s = ((solid_i * 9.f + 1.f) * (float)d.alpha_fluid) * (float)d.sound * (hm + d.visc_q * hm * hm) /
+                                    ((densi + densj) * 0.5f) * bf;
+                            }
+                            const float pp = vj.w + pod2i + s;                          // cu:310-312
+                            t_x += pp * dkx;
+                            t_y += pp * dky;
+                            t_z += pp * dkz;
+                            if (!bi && !bj) {
+                                const float inv = 1.f / densj;
+                                t_dx += inv * dkx;                                      // cu:364-366
+                                t_dy += inv * dky;
+                                t_dz += inv * dkz;
+                                t_df += -0.5f * inv * (fluid_i + fluid_j) * (dkx * vabx + dky * vaby + dkz * vabz);   // cu:401
+                            }
+                        }
+                    }
 #pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    t_nd += __shfl_xor_sync(FULL, t_nd, o);
-                    t_x += __shfl_xor_sync(FULL, t_x, o);
-                    t_y += __shfl_xor_sync(FULL, t_y, o);
-                    t_z += __shfl_xor_sync(FULL, t_z, o);
-                    t_dx += __shfl_xor_sync(FULL, t_dx, o);
-                    t_dy += __shfl_xor_sync(FULL, t_dy, o);
-                    t_dz += __shfl_xor_sync(FULL, t_dz, o);
-                    t_df += __shfl_xor_sync(FULL, t_df, o);
+                    for (int o = 16; o; o >>= 1) {
+                        t_nd += __shfl_xor_sync(FULL, t_nd, o);
+                        t_x += __shfl_xor_sync(FULL, t_x, o);
+                        t_y += __shfl_xor_sync(FULL, t_y, o);
+                        t_z += __shfl_xor_sync(FULL, t_z, o);
+                        t_dx += __shfl_xor_sync(FULL, t_dx, o);
+                        t_dy += __shfl_xor_sync(FULL, t_dy, o);
+                        t_dz += __shfl_xor_sync(FULL, t_dz, o);
+                        t_df += __shfl_xor_sync(FULL, t_df, o);
+                    }
+                    if (lane == il) { s_nd += t_nd; s_x += t_x; s_y += t_y; s_z += t_z; s_dx += t_dx; s_dy += t_dy; s_dz += t_dz; s_df += t_df; }
+                    __syncwarp();
                 }
-                if (lane == il) { s_nd = t_nd; s_x = t_x; s_y = t_y; s_z = t_z; s_dx = t_dx; s_dy = t_dy; s_dz = t_dz; s_df = t_df; }
-                __syncwarp();
             }
             if (lane < gcount) {
                 a.sums[hs + ig + lane] = make_float4(s_nd, s_x, s_y, s_z);
@@ -350,8 +386,8 @@ cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, c
     if (n <= 0) return cudaSuccess;
     static FsgAttrOnce attr_once;
     if (attr_once.need()) {
-        cudaFuncSetAttribute(k_pair_unidyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
-        cudaFuncSetAttribute(k_pair_unidyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
+        cudaFuncSetAttribute(k_pair_unidyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM);
+        cudaFuncSetAttribute(k_pair_unidyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM);
     }
     UniArgs a;
     a.d = c->dev;
@@ -367,8 +403,8 @@ cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, c
     a.stats = c->dstats;
     a.mixA = c->mixA;
     a.mixB = c->mixB;
-    int64_t blocks = (n + UNI_WARPS - 1) / UNI_WARPS;
-    int64_t maxb = (int64_t)c->sm_count * 2;
+    int64_t blocks = (n + UP_WARPS - 1) / UP_WARPS;
+    int64_t maxb = (int64_t)c->sm_count * 4;
     if (blocks > maxb) blocks = maxb;
     cudaError_t e;
     if (c->mixed) {
@@ -382,8 +418,8 @@ cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, c
         if (e != cudaSuccess) return e;
         *launches += 1;
     } else {
-        if (c->cfg.collect_stats) k_pair_unidyn<true><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, s>>>(a);
-        else k_pair_unidyn<false><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, s>>>(a);
+        if (c->cfg.collect_stats) k_pair_unidyn<true><<<(unsigned)blocks, UP_WARPS * 32, UP_SMEM, s>>>(a);
+        else k_pair_unidyn<false><<<(unsigned)blocks, UP_WARPS * 32, UP_SMEM, s>>>(a);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -626,8 +662,8 @@ static int uni_stage_pairs(fsg_ctx *c, void *d_particles, const int32_t *d_cells
     CUU(c, cudaSetDevice(c->device));
     static FsgAttrOnce attr_once;
     if (attr_once.need()) {
-        cudaFuncSetAttribute(k_pair_unidyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
-        cudaFuncSetAttribute(k_pair_unidyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UNI_SMEM);
+        cudaFuncSetAttribute(k_pair_unidyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM);
+        cudaFuncSetAttribute(k_pair_unidyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM);
     }
     int *binlist = c->binlist[0], *nocc = c->counters + 7, *work = c->counters + 2;
     CUU(c, cudaMemsetAsync(nocc, 0, sizeof(int), c->stream));
@@ -647,10 +683,10 @@ static int uni_stage_pairs(fsg_ctx *c, void *d_particles, const int32_t *d_cells
     a.sums = c->sums;
     a.sums2 = c->sums2;
     a.stats = c->dstats;
-    int64_t blocks = (n + UNI_WARPS - 1) / UNI_WARPS;
+    int64_t blocks = (n + UP_WARPS - 1) / UP_WARPS;
     const int64_t maxb = (int64_t)c->sm_count * 2;
     if (blocks > maxb) blocks = maxb;
-    k_pair_unidyn<false><<<(unsigned)blocks, UNI_WARPS * 32, UNI_SMEM, c->stream>>>(a);
+    k_pair_unidyn<false><<<(unsigned)blocks, UP_WARPS * 32, UP_SMEM, c->stream>>>(a);
     CUU(c, cudaGetLastError());
     k_stage_uni_add_sums<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((unsigned char *)d_particles, d_cells, d_start, d_end, c->sums,
                                                                            c->sums2, n, c->dev.numcells, which);
