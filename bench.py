@@ -351,7 +351,7 @@ def make_solver(fsg, G, rank, world, local, args):
     cap_m, cap_g = fsg.slab.message_caps(hist, cuts)
     solver = fsg.SlabSolver(cfg, fsg.DistExchange(), cap_m, cap_g)
     if args.exchange == "peer":
-        solver.setup_peer_exchange(overlap=args.overlap)
+        solver.setup_peer_exchange(overlap=args.overlap, classic=args.classic_slabs)
     return solver, cfg, n_total
 
 
@@ -451,14 +451,15 @@ def fsg_arm(args):
         ph = [phase[k] / max(1, phase["steps"]) for k in ("sort", "reorder", "pair_update", "other")]
         payload = 64.0 * (info["sent"][0] + info["sent"][2]) + 32.0 * (info["sent"][1] + info["sent"][3])
         xm = solver.exchange_ms()
-        mine = torch.tensor(ph + [float(n_local), payload, float(solver.wire_bytes_per_step), xm["pack"], xm["exchange"], xm["unpack"]],
+        gms = solver.ghost_ms() if solver.mode == 2 else 0.0
+        mine = torch.tensor(ph + [float(n_local), payload, float(solver.wire_bytes_per_step), xm["pack"], xm["exchange"], xm["unpack"], gms],
                             device="cuda", dtype=torch.float64)
         allr = torch.empty(world * mine.numel(), device="cuda", dtype=torch.float64)
         dist.all_gather_into_tensor(allr, mine)
         allr = allr.cpu().view(world, -1)
         per_rank = {"ms_sort": allr[:, 0].tolist(), "ms_reorder": allr[:, 1].tolist(), "ms_pair_update": allr[:, 2].tolist(),
                     "ms_pack": allr[:, 7].tolist(), "ms_exchange_incl_wait": allr[:, 8].tolist(), "ms_unpack": allr[:, 9].tolist(),
-                    "particles": [int(v) for v in allr[:, 4].tolist()]}
+                    "ms_ghost_exchange_in_reorder": allr[:, 10].tolist(), "particles": [int(v) for v in allr[:, 4].tolist()]}
         t2 = torch.tensor([float(launches), float(solver.owned_count())], device="cuda", dtype=torch.float64)
         dist.all_reduce(t2, op=dist.ReduceOp.SUM)
         launches = int(t2[0])
@@ -468,10 +469,14 @@ def fsg_arm(args):
         halo = {"wire_bytes_per_step_all_ranks": wire, "payload_bytes_last_step_all_ranks": payload_all,
                 "wire_GBps_all_ranks": wire / (ms_total / args.steps * 1e-3) / 1e9, "nvlink_peak_GBps_per_direction": 770.0,
                 "exchange": args.exchange, "overlap": args.exchange == "peer" and args.overlap,
-                "note": "one fixed-size message per neighbour and direction (counts in the header, read on the device): no host "
-                        "synchronisation inside a step; peer = copied into the neighbour's inbox over NVLink by the copy engines "
-                        "(CUDA IPC mapping), sequence stamp copied last and awaited on the device; overlap = boundary bins first, next step's "
-                        "pack + copies on a second stream beside the interior bins; nccl = NCCL send/recv"}
+                "pipeline": "sorted ghosts (fsg_slab2.cu)" if solver.mode == 2 else "classic (ghosts appended and sorted)",
+                "note": "no host synchronisation inside a step, every count is read on the device.  sorted ghosts: migrants (pre-update "
+                        "state + pending pair sums) are copied into the neighbour's inbox before the key sort (CUDA IPC mapping, copy engines, "
+                        "sequence stamp last, awaited on the device); after the reorder the face layers of the SORTED state are written "
+                        "straight into the neighbours' ghost zones by a kernel (remote stores over NVLink) — ghosts never pass through the "
+                        "sort; per_rank.ms_ghost_exchange_in_reorder (send + wait + install) is part of ms_reorder.  classic: one fixed-size "
+                        "message per neighbour and direction with migrants and ghosts, appended and sorted; overlap = boundary bins first, "
+                        "next step's pack + copies on a second stream beside the interior bins; nccl = NCCL send/recv"}
     ms_step = ms_total / args.steps
     value = G ** 3 / (ms_step * 1e-3)
 
@@ -758,6 +763,7 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="N>1, peer exchange: boundary bins first, next step's pack + copies on a second stream beside the interior bins "
                          "(measured slower than the plain order at 512^3: splitting the pair kernel costs more than the exchange it hides)")
+    ap.add_argument("--classic-slabs", action="store_true", help="N > 1: the classic slab pipeline (ghosts appended and sorted) instead of sorted ghosts")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: peer = messages copied into the neighbours' memory over NVLink (CUDA IPC) + 4-byte NCCL signal; "
                          "nccl = whole messages through NCCL send/recv")

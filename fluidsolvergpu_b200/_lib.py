@@ -80,6 +80,11 @@ SIGNATURES = {
     "fsg_slab_message_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
     "fsg_slab_message_bytes_model": (C.c_int64, [C.c_int, C.c_int64, C.c_int64]),
     "fsg_slab_alloc_messages": (C.c_int, [P, C.c_int64, C.c_int64]),
+    "fsg_slab_alloc_messages2": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int]),
+    "fsg_slab_mode": (C.c_int, [P]),
+    "fsg_slab_set_split_step": (C.c_int, [P, C.c_int]),
+    "fsg_slab_step_finish": (C.c_int, [P]),
+    "fsg_slab_get_ghost_ms": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fsg_slab_inbox_handle": (C.c_int, [P, C.c_int, C.c_int, P]),
     "fsg_slab_open_peer": (C.c_int, [P, C.c_int, C.c_int, P]),
     "fsg_slab_pack_send": (C.c_int, [P]),

@@ -1,5 +1,6 @@
 // fsg_api.cu — the extern "C" boundary of libfsg (include/fsg.h): context lifetime, host<->device
 // movement and the step schedule.  No torch types, no exceptions across the boundary, no CPU path.
+#include <limits.h>
 #include "fsg_device.cuh"
 #ifndef FSG_SORT_MERGE_MIN_CAP
 #define FSG_SORT_MERGE_MIN_CAP (1 << 20)
@@ -60,6 +61,7 @@ void fsg_derive_constants(const fsg_config &cfg, FsgDev &d)
     d.rr = d.x1 - ((cfg.world > 1 && cfg.rank < cfg.world - 1) ? 2 : 0);
     if (d.rr < d.rl) d.rr = d.rl;
     d.dead = d.numcells + 1;
+    d.kx0 = d.kx1 = INT_MIN;
     d.cap = cfg.neighbour_cap;
     d.bin_cap = cfg.bin_cap;
     d.origin = cfg.origin;
@@ -170,6 +172,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     if (c->host_flag) cudaFreeHost((void *)c->host_flag);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_used) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_ghost) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return FSG_OK;
@@ -227,9 +230,9 @@ static int create_impl(fsg_ctx *c)
     const int64_t nb = cap < nc ? cap : nc;
     CU(c, cudaMalloc(&c->binlist[0], sizeof(int) * (nb > 0 ? nb : 1)));
     CU(c, cudaMalloc(&c->binlist[1], sizeof(int) * (nb > 0 ? nb : 1)));
-    CU(c, cudaMalloc(&c->counters, sizeof(int) * 16));
+    CU(c, cudaMalloc(&c->counters, sizeof(int) * 32));
     CU(c, cudaMalloc(&c->dstats, sizeof(unsigned long long) * 4));
-    CU(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * 16, c->stream));
+    CU(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * 32, c->stream));
     CU(c, cudaMemsetAsync(c->dstats, 0, sizeof(unsigned long long) * 4, c->stream));
     CU(c, fsg_launch_iota(c->iota, cap, c->stream));
     CU(c, fsg_launch_fill(c->start, -1, nc, c->stream));    // solver.cu:163-169
@@ -273,6 +276,7 @@ extern "C" int fsg_create(const fsg_config *cfg, fsg_ctx **out)
     c->device = cfg->device;
     c->ns_mode = -1;
     c->defer_mode = -1;
+    c->gh_par_last = -1;
     fsg_derive_constants(*cfg, c->dev);
     fsg_update_pair_mode(c);
     int rc = create_impl(c);
@@ -318,7 +322,13 @@ static int after_upload(fsg_ctx *c, int64_t n, const int *slot_state = nullptr)
         else CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, c->n, c->stream));
         c->launches++;
         c->tables_dirty = false;
+        if (c->slab2) { int rc = fsg_slab2_reset_ghost_tables(c); if (rc != FSG_OK) return rc; }
     }
+    if (c->slab2 && n > c->n_own) {
+        c->err = "upload: n exceeds the context capacity minus the two ghost zones (capacity - 2 * cap_g)";
+        return FSG_E_INVALID;
+    }
+    c->slab2_mid = false;
     c->n = n;
     c->keys_prev_valid = false;
     c->deferred = false;
@@ -345,7 +355,7 @@ static int after_upload(fsg_ctx *c, int64_t n, const int *slot_state = nullptr)
     CU(c, cudaMemcpyAsync(flag, c->counters + 4, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->has_boundary = flag[0] != 0;
-    if (c->cfg.world > 1) c->n = c->cap;
+    if (c->cfg.world > 1) c->n = c->slab2 ? c->n_own : c->cap;
     CU(c, cudaMemsetAsync(c->counters + 8, 0, sizeof(int), c->stream));
     c->mixed = false;
     if (c->cfg.model == FSG_MODEL_UNIDYN && flag[4]) {
@@ -663,7 +673,7 @@ static bool nearly_sorted_enabled(fsg_ctx *c)
     return c->ns_mode == 1;
 }
 
-// Deferred update: single-device base contexts running the pipelined fp32 pair kernels (they write `sums`); FSG_DEFER_UPDATE=0
+// Deferred update: single-device base contexts (and slab contexts on the sorted-ghost pipeline, fsg_slab2.cu) running the pipelined fp32 pair kernels (they write `sums`); FSG_DEFER_UPDATE=0
 // keeps the separate k_update pass after every step.
 static bool defer_enabled(fsg_ctx *c)
 {
@@ -672,7 +682,7 @@ static bool defer_enabled(fsg_ctx *c)
         c->defer_mode = e ? atoi(e) != 0 : 1;
     }
     const fsg_config &f = c->cfg;
-    return c->defer_mode == 1 && f.world == 1 && f.model == FSG_MODEL_BASE && f.pair_fp64 == 0 && f.neighbour_cap == 0 && f.bin_cap == 0 &&
+    return c->defer_mode == 1 && (f.world == 1 || c->slab2) && f.model == FSG_MODEL_BASE && f.pair_fp64 == 0 && f.neighbour_cap == 0 && f.bin_cap == 0 &&
            !c->overlap;
 }
 
@@ -680,11 +690,45 @@ static bool defer_enabled(fsg_ctx *c)
 int fsg_materialize(fsg_ctx *c)
 {
     if (!c->deferred) return FSG_OK;
+    if (c->slab2_mid) {
+        c->err = "the state cannot be read between fsg_slab_pack_send and fsg_step (migrants have left, their update is pending at the neighbours)";
+        return FSG_E_STATE;
+    }
     CU(c, cudaSetDevice(c->device));
     CU(c, fsg_launch_update(c->dev, c->n, c->keysA, c->A, c->B, c->keysB, c->sums, c->carry_pending ? c->carryA : nullptr, 0, nullptr, c->stream));
     c->launches++;
     c->deferred = false;
     c->carry_pending = false;
+    return FSG_OK;
+}
+
+// second half of a step: (sorted-ghost slabs: the neighbours' ghosts) + mykernel + mykernel2 (solver.cu:187,198)
+static int step_second_half(fsg_ctx *c, int64_t n, int nxt, bool prof)
+{
+    if (c->slab2) { int rc = fsg_slab2_ghost_recv(c, nxt); if (rc != FSG_OK) return rc; }
+    if (prof) prof_mark(c);
+    const bool defer = defer_enabled(c);
+    int l = 0;
+    if (c->cfg.model == FSG_MODEL_UNIDYN)      // mykernel + mykernel3 + mykernel2 + cell_calc (solver-unidyn.cu:363-548)
+        CU(c, fsg_launch_unidyn(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2, c->carry_live ? c->carryA : nullptr, &l,
+                                c->stream));
+    else if (defer) {
+        // pair sums only: the update they feed runs inside the next step's reorder (or in fsg_materialize)
+        // (slab2: the candidates include the ghost zones at the top of the arrays, the sums of every slot are cleared)
+        CU(c, fsg_launch_pair_sums(c, c->slab2 ? c->cap : n, c->binlist[nxt], c->counters + nxt, c->counters + 2, &l, c->stream));
+        c->deferred = true;
+        c->carry_pending = c->carry_live;
+    } else
+        CU(c, fsg_launch_pair_update(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2,
+                                     c->carry_live ? c->carryA : nullptr, &l, c->stream));
+    c->launches += l;
+    if (prof) prof_mark(c);
+    c->carry_live = false;
+    c->slab2_mid = false;
+    c->cur = nxt;
+    c->tables_dirty = true;
+    c->keys_prev_valid = true;      // keysA = this step's sorted keys, keysB = the new keys of the same slots
+    c->steps++;
     return FSG_OK;
 }
 
@@ -698,6 +742,7 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         return FSG_E_STATE;
     }
     if (c->cfg.world > 1) { int rc = fsg_slab_sticky_error(c); if (rc != FSG_OK) return rc; }
+    if (c->step_pending) { c->err = "fsg_step: the previous step is half done (fsg_slab_step_finish)"; return FSG_E_STATE; }
     const int64_t n = c->n;
     if (n <= 0) { c->steps += nsteps; return FSG_OK; }
     for (int t = 0; t < nsteps; t++) {
@@ -707,13 +752,14 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
             if (c->cfg.world > 1) CU(c, fsg_launch_reset_tables_keys(c->dev, c->keysA, c->start, c->end, c->n_sorted, c->stream));
             else CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, n, c->stream));
             c->launches++;
+            if (c->slab2) { int rc = fsg_slab2_reset_ghost_tables(c); if (rc != FSG_OK) return rc; }
         }
         const int nxt = c->cur ^ 1;
         CU(c, cudaMemsetAsync(c->counters + nxt, 0, sizeof(int), c->stream));
         CU(c, cudaMemsetAsync(c->counters + 2, 0, 2 * sizeof(int), c->stream));
         CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(int), c->stream));
         CU(c, cudaMemsetAsync(c->counters + 10, 0, 2 * sizeof(int), c->stream));
-        if (c->cfg.world > 1) CU(c, fsg_launch_fill(c->counters + 12, (int)n, 2, c->stream));
+        if (c->cfg.world > 1) CU(c, fsg_launch_fill(c->counters + 16, (int)n, 4, c->stream));
         if (c->cfg.collect_stats) CU(c, cudaMemsetAsync(c->dstats, 0, 4 * sizeof(unsigned long long), c->stream));
         if (prof) prof_mark(c);
         // thrust::sort_by_key, key half (solver.cu:181)
@@ -735,7 +781,8 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         if (c->deferred) {
             CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->A, c->B, c->carry_pending ? c->carryA : nullptr, nullptr, c->sums,
                                      defer ? c->keysB : nullptr, c->start, c->end, c->binlist[nxt], c->counters + nxt, c->binlist[nxt],
-                                     c->counters + 10, c->counters + 3, c->counters + 5, nullptr, c->counters + 14, c->stream));
+                                     c->counters + 10, c->counters + 3, c->counters + 5, c->cfg.world > 1 ? c->counters + 16 : nullptr,
+                                     c->counters + 14, c->stream));
             FsgState t = c->A; c->A = c->B; c->B = t;      // A: the sorted pre-update state of THIS step; B: scratch until materialised
             c->carry_pending = false;
             c->deferred = false;
@@ -743,32 +790,44 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
             CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA, nullptr,
                                      defer ? c->keysB : nullptr, c->start, c->end, c->binlist[nxt], c->counters + nxt,
                                      c->binlistB ? c->binlistB : c->binlist[nxt], c->counters + 10, c->counters + 3, c->counters + 5,
-                                     c->cfg.world > 1 ? c->counters + 12 : nullptr, c->counters + 14, c->stream));
+                                     c->cfg.world > 1 ? c->counters + 16 : nullptr, c->counters + 14, c->stream));
         c->n_sorted = n;
         c->launches++;
-        if (prof) prof_mark(c);
-        // mykernel + mykernel2 (solver.cu:187,198)
-        int l = 0;
-        if (c->cfg.model == FSG_MODEL_UNIDYN)      // mykernel + mykernel3 + mykernel2 + cell_calc (solver-unidyn.cu:363-548)
-            CU(c, fsg_launch_unidyn(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2, c->carry_live ? c->carryA : nullptr, &l,
-                                    c->stream));
-        else if (defer) {
-            // pair sums only: the update they feed runs inside the next step's reorder (or in fsg_materialize)
-            CU(c, fsg_launch_pair_sums(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2, &l, c->stream));
-            c->deferred = true;
-            c->carry_pending = c->carry_live;
-        } else
-            CU(c, fsg_launch_pair_update(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2,
-                                         c->carry_live ? c->carryA : nullptr, &l, c->stream));
-        c->launches += l;
-        if (prof) prof_mark(c);
-        c->carry_live = false;
-        c->cur = nxt;
-        c->tables_dirty = true;
-        c->keys_prev_valid = true;      // keysA = this step's sorted keys, keysB = the new keys of the same slots
-        c->steps++;
+        // sorted-ghost slab pipeline: the face layers of the sorted state go to the neighbours' ghost zones, theirs come in
+        if (c->slab2) {
+            int rc = fsg_slab2_ghost_send(c);
+            if (rc != FSG_OK) return rc;
+            if (c->slab2_split) {           // in-process slab groups: the second half runs once every slab has sent (fsg_slab_step_finish)
+                c->step_pending = true;
+                c->pending_nxt = nxt;
+                c->pending_prof = prof;
+                return FSG_OK;
+            }
+        }
+        int rc = step_second_half(c, n, nxt, prof);
+        if (rc != FSG_OK) return rc;
     }
     return FSG_OK;
+}
+
+// In-process slab groups on the sorted-ghost pipeline (several slab contexts of ONE process sharing a device, fluidsolvergpu_b200.slab.
+// SlabGroup): with split steps on, fsg_step returns after the ghost send and fsg_slab_step_finish does the rest — the caller
+// finishes the first half of every slab before any second half, so no kernel ever spins on a device that has yet to run (or
+// lazily load) the kernels it is waiting for.  One process per device (the production layout) needs neither call.
+extern "C" int fsg_slab_set_split_step(fsg_ctx *c, int on)
+{
+    if (!c) return FSG_E_INVALID;
+    if (c->step_pending) { c->err = "fsg_slab_set_split_step: a step is half done"; return FSG_E_STATE; }
+    c->slab2_split = on != 0;
+    return FSG_OK;
+}
+extern "C" int fsg_slab_step_finish(fsg_ctx *c)
+{
+    if (!c) return FSG_E_INVALID;
+    if (!c->step_pending) return FSG_OK;
+    CU(c, cudaSetDevice(c->device));
+    c->step_pending = false;
+    return step_second_half(c, c->n, c->pending_nxt, c->pending_prof);
 }
 
 extern "C" int fsg_export_viz(fsg_ctx *c, float *spts, float *a3, float *b3)

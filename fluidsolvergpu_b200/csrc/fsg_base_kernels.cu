@@ -173,6 +173,10 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
             const int KL = d.rl * d.G2, KR = d.rr * d.G2;
             if (key >= KL && prevk < KL) ranges[0] = (int)k;
             if (key >= KR && prevk < KR) ranges[1] = (int)k;
+            // the face layers themselves (sorted-ghost pipeline): first slot beyond layer x0, first slot of layer x1 - 1
+            const int KL1 = (d.x0 + 1) * d.G2, KR1 = (d.x1 - 1) * d.G2;
+            if (key >= KL1 && prevk < KL1) ranges[2] = (int)k;
+            if (key >= KR1 && prevk < KR1) ranges[3] = (int)k;
         }
     }
     // block-aggregated append of the home-bin heads: ONE atomic per block and list (a per-warp atomic on the

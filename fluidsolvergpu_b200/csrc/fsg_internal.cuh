@@ -22,6 +22,8 @@ struct FsgDev {
     int uni_open;    // unidyn: 1 = no unit-box floor / walls in Particle::update (fsg_config.unidyn_open_box)
     int sym;         // 1: the symmetric pair kernel runs (fsg_pair_v3.cu): the ghost layer x0 - 1 is listed as home bins too
     int dead;        // key of a slot that no longer holds a particle of this slab (sorts last, is trimmed)
+    int kx0, kx1;    // sorted-ghost slab pipeline (fsg_slab2.cu): bin ids x0*G^2 and x1*G^2, where the particle array is NOT contiguous
+                     // (ghost layers live in their own zones); INT_MIN otherwise
     int cap, bin_cap;
     float origin;
     double cellsize, h, dt, gravity, sound, alpha_fluid, alpha_boundary;
@@ -86,8 +88,11 @@ struct fsg_ctx {
     int *perm, *iota;
     int *start, *end;   // dense bin tables, -1 = empty  (FluidGPU.cu:106-117)
     int *binlist[2];    // ids of the occupied home bins (unordered), ping-pong
-    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live, [4] any-boundary flag, [5] n_keep, [12..13] pack ranges,
-                        // [14] the sorted key array was found out of order by k_reorder (never expected; reported by fsg_get_stats / downloads)
+    int *counters;      // [0..1] nocc ping-pong, [2] work counter, [3] n_live, [4] any-boundary flag, [5] n_keep,
+                        // [14] the sorted key array was found out of order by k_reorder (never expected; reported by fsg_get_stats / downloads),
+                        // [16..19] slab contexts: sorted-slot bounds found by k_reorder — first slot of layer rl, of layer rr (the pack's
+                        // two-layer regions), of layer x0 + 1, of layer x1 - 1 (the face layers the sorted-ghost pipeline sends),
+                        // [20..21] blocks of k_slab2_ghost_send that have finished (left, right)
     unsigned long long *dstats;   // [0] tested, [1] in range, [2] dropped
     int *slab_cnt;      // slab pack: per-warp counts of the 4 message categories, then their exclusive scan
     void *scan_tmp;
@@ -101,6 +106,22 @@ struct fsg_ctx {
     volatile int *host_flag;        // pinned, device-mapped: raised by k_slab_wait when a neighbour's message never arrived (sticky)
     int *host_flag_dev;
     unsigned long long slab_timeout_ns;
+    // Sorted-ghost pipeline (fsg_slab2.cu; base model, library-owned peer messages): ghosts never pass through the sort.  The top
+    // 2 * msg_cap_g slots of every particle array are the two ghost zones, the context works on n_own = cap - 2 * msg_cap_g slots,
+    // the update is deferred like on a single device, migrants travel with their pending pair sums before the sort and the face
+    // layers of the SORTED state are copied into the neighbours' ghost zones after the reorder.
+    bool slab2;
+    bool slab2_split;   // in-process slab groups: fsg_step stops after the ghost send, fsg_slab_step_finish does the rest
+    bool step_pending, pending_prof, ghost_prof;
+    int pending_nxt;
+    bool slab2_mid;     // between fsg_slab_pack_send and fsg_step: migrants have left, B cannot be materialised
+    int64_t n_own;
+    int gh_par_last;    // parity of the ghost messages whose bins are in the tables (-1: none)
+    long long seq_ghost;
+    size_t mig_bytes, gh_bytes;      // the two parts of a library-owned message buffer in this mode
+    std::vector<cudaEvent_t> ev_ghost;   // profiling: pairs of events around the ghost exchange of every step
+    double ghost_ms;
+    int64_t ghost_steps;
     bool keep_foreign;  // slab contexts: uploads are not filtered by position (fsg_slab_keep_foreign)
     bool peer_local;    // peer_inbox holds plain pointers of this process (fsg_slab_set_peer), not IPC mappings
     bool overlap;       // pack + copies of the NEXT step's messages run on `comm` behind the boundary bins, beside the interior bins
@@ -162,6 +183,13 @@ cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, cons
                                cudaStream_t s);
 int fsg_slab_sticky_error(fsg_ctx *c); // fsg_slab.cu: FSG_E_STATE once a device-side wait for a neighbour has timed out
 int fsg_slab_send_next(fsg_ctx *c);   // fsg_slab.cu: pack + copies of the next step's messages on c->comm (overlap mode)
+// fsg_slab2.cu — the sorted-ghost slab pipeline
+int fsg_slab2_engage(fsg_ctx *c, int64_t cap_m, int64_t cap_g, size_t *bytes);   // decides the mode at fsg_slab_alloc_messages; message buffer size
+int fsg_slab2_pack_send(fsg_ctx *c);         // migrants (pre-update state + pending sums) -> the neighbours' inboxes
+int fsg_slab2_unpack_recv(fsg_ctx *c);       // waits for the neighbours' migrants, appends them behind the slots in use
+int fsg_slab2_ghost_send(fsg_ctx *c);            // after the reorder: the sorted face layers -> the neighbours' ghost messages
+int fsg_slab2_ghost_recv(fsg_ctx *c, int nxt);   // wait for the neighbours' ghosts, install them + their bins
+int fsg_slab2_reset_ghost_tables(fsg_ctx *c);        // start / end = -1 for the ghost bins of the last step
 cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work,
                                    const float4 *carry, int *launches, cudaStream_t s);
 cudaError_t fsg_launch_unpack_aos(int model, const unsigned char *aos, int64_t n, FsgState st, float4 *carry,

@@ -181,9 +181,9 @@ k_pair_v2(V2Args va)
             pf_s0 = pf_s1 = pf_s2 = pf_e0 = pf_e1 = pf_e2 = -1;
             if (lane < 9) {
                 const int c0 = b + (lane / 3 - 1) * d.G2 + (lane % 3 - 1) * d.G;
-                if (c0 - 1 >= 0 && c0 - 1 < d.numcells) { pf_s0 = a.start[c0 - 1]; pf_e0 = a.end[c0 - 1]; }
+                if (c0 - 1 >= 0 && c0 - 1 < d.numcells && c0 != d.kx0 && c0 != d.kx1) { pf_s0 = a.start[c0 - 1]; pf_e0 = a.end[c0 - 1]; }
                 if (c0 >= 0 && c0 < d.numcells) { pf_s1 = a.start[c0]; pf_e1 = a.end[c0]; }
-                if (c0 + 1 >= 0 && c0 + 1 < d.numcells) { pf_s2 = a.start[c0 + 1]; pf_e2 = a.end[c0 + 1]; }
+                if (c0 + 1 >= 0 && c0 + 1 < d.numcells && c0 + 1 != d.kx0 && c0 + 1 != d.kx1) { pf_s2 = a.start[c0 + 1]; pf_e2 = a.end[c0 + 1]; }
             }
         };
         for (;;) {

@@ -112,14 +112,19 @@ __device__ __forceinline__ int v3_global_slot(const V3Warp &W, int stage, int c)
 }
 
 // one batch of <= 32 queued near pairs: lanes = pairs, both sides reduced straight into sums[]
-__device__ __forceinline__ void v3_drain_batch(const V3Near &d, const V3Warp &W, int stage, int hs, int t0, int hnlim,
+// (queue entries are RAW marks — bits 0-4: 8 * pass + position in the mark word, bit 5: which home particle of the pass, bits 8-12:
+// the lane that held the mark, bits 16+: first home particle of the batch — decoded here, 32 at a time, instead of once per mark in
+// the append loop, where only the lanes that hold a mark are active)
+__device__ __forceinline__ void v3_drain_batch(const V3Near &d, const V3Warp &W, int stage, int hs, int t0, int hnlim, int nch,
                                                const float4 *__restrict__ velp, float4 *__restrict__ sums, int qh, int qn, int lane)
 {
     const int e = qh + lane;
     if (e < qn) {
         const V3Stage &S = W.st[stage];
-        unsigned ent = W.q[e];
-        const int k = (int)(ent >> 16), c = (int)(ent & 0xffffu);
+        const unsigned ent = W.q[e];
+        const int p5 = (int)(ent & 31u);
+        const int k = (int)(ent >> 16) + 2 * (p5 >> 3) + (int)((ent >> 5) & 1u);
+        const int c = (nch - 1 - (p5 & 7)) * 32 + (int)((ent >> 8) & 31u);
         const int i = hs + k, j = v3_global_slot(W, stage, c);
         const float *P = reinterpret_cast<const float *>(&S.hp[0]) + (k >> 1) * 8 + (k & 1);     // packed homes, see the main loop
         const float4 pi = make_float4(-P[0], -P[2], -P[4], P[6]);
@@ -235,9 +240,9 @@ k_pair_v3(V3Args va)
         pf_s0 = pf_s1 = pf_s2 = pf_e0 = pf_e1 = pf_e2 = -1;
         if (lane < 5) {
             const int c0 = b + (lane == 0 ? 0 : lane == 1 ? d.G : d.G2 + (lane - 3) * d.G);
-            if (lane != 0 && c0 - 1 >= 0 && c0 - 1 < d.numcells) { pf_s0 = a.start[c0 - 1]; pf_e0 = a.end[c0 - 1]; }
+            if (lane != 0 && c0 - 1 >= 0 && c0 - 1 < d.numcells && c0 != d.kx0 && c0 != d.kx1) { pf_s0 = a.start[c0 - 1]; pf_e0 = a.end[c0 - 1]; }
             if (c0 >= 0 && c0 < d.numcells) { pf_s1 = a.start[c0]; pf_e1 = a.end[c0]; }
-            if (c0 + 1 >= 0 && c0 + 1 < d.numcells) { pf_s2 = a.start[c0 + 1]; pf_e2 = a.end[c0 + 1]; }
+            if (c0 + 1 >= 0 && c0 + 1 < d.numcells && c0 + 1 != d.kx0 && c0 + 1 != d.kx1) { pf_s2 = a.start[c0 + 1]; pf_e2 = a.end[c0 + 1]; }
         }
     };
     auto next_sub = [&](V3Sub &sub) -> bool {
@@ -391,7 +396,7 @@ k_pair_v3(V3Args va)
                 __syncwarp();
                 int qh = 0;
                 while (qn - qh >= 32 || (all && qh < qn)) {
-                    v3_drain_batch(nc, W, stage, cur.hs, cur.t0, cur.hnlim, a.A.velp, sums, qh, qn, lane);
+                    v3_drain_batch(nc, W, stage, cur.hs, cur.t0, cur.hnlim, nch, a.A.velp, sums, qh, qn, lane);
                     qh += 32;
                 }
                 const int left = max(qn - qh, 0);
@@ -407,21 +412,30 @@ k_pair_v3(V3Args va)
                 const unsigned smask = nsl == 1 ? 0xffffffffu : 1u << sl;
                 const unsigned a0 = M0 & smask, a1 = M1 & smask;
                 const int mine = __popc(a0) + __popc(a1);
-                int incl = mine;
+                // exclusive prefix of the lanes' mark counts: three ballots while every lane holds fewer than 8 marks (nearly always),
+                // the shuffle scan otherwise
+                int excl_m, total;
+                if (__ballot_sync(FULL, mine >= 8) == 0u) {
+                    const unsigned ltm = (1u << lane) - 1u;
+                    const unsigned b0 = __ballot_sync(FULL, mine & 1), b1 = __ballot_sync(FULL, mine & 2), b2 = __ballot_sync(FULL, mine & 4);
+                    excl_m = __popc(b0 & ltm) + 2 * __popc(b1 & ltm) + 4 * __popc(b2 & ltm);
+                    total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                } else {
+                    int incl = mine;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += t;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    total = __shfl_sync(FULL, incl, 31);
+                    excl_m = incl - mine;
                 }
-                const int total = __shfl_sync(FULL, incl, 31);
                 if (qn + total > V3_QCAP) drain(false);
-                int at = qn + incl - mine;
-                // one loop over both halves' marks (bit 32 * half + 8 * pass + pos): its trip count is the largest number of marks
-                // any lane holds, not the sum of the two halves' maxima
-                for (unsigned long long m = (unsigned long long)a0 | ((unsigned long long)a1 << 32); m; m &= m - 1) {
-                    const int p = __ffsll((long long)m) - 1;
-                    W.q[at++] = ((unsigned)(kb + ((p >> 2) & 6) + (p >> 5)) << 16) | (unsigned)((nch - 1 - (p & 7)) * 32 + lane);
-                }
+                int at = qn + excl_m;
+                // raw marks, one 32-bit loop per home particle of the passes (decoded by v3_drain_batch)
+                const unsigned ebase = ((unsigned)kb << 16) | ((unsigned)lane << 8);
+                for (unsigned m = a0; m; m &= m - 1) W.q[at++] = ebase | (unsigned)(__ffs((int)m) - 1);
+                for (unsigned m = a1; m; m &= m - 1) W.q[at++] = ebase | 32u | (unsigned)(__ffs((int)m) - 1);
                 qn += total;
             }
             if (last_batch && qn > 0) drain(true);

@@ -10,12 +10,13 @@
 //   ghosts   : particles in layer x0 (for the left neighbour) or x1-1 (for the right one): read state
 // Message order = current particle order (two-phase count / scan / scatter, no atomics), so runs are
 // reproducible.
-#include "fsg_device.cuh"
+#include "fsg_slab_common.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <limits.h>
 
 size_t fsg_scan_temp_bytes(int64_t n)
 {
@@ -42,27 +43,6 @@ __device__ __forceinline__ int slab_category(const FsgDev &d, int key, int rank,
     }
     return c;
 }
-
-// After the first step the particles are in bin-sorted order, and only slots within two layers of a face that has
-// a neighbour can have become migrants or ghosts (a particle moves less than one bin per step): the sorted slots
-// [0, region[0]) and [region[1], n_keep), found by k_reorder (n_keep: the slots in use; dead slots sort last).  The pack
-// kernels are launched over THAT index space only — compact index t -> slot t (head) or region[1] + t - region[0] (tail) —
-// with a fixed-size grid that strides over it: nothing is launched, read or written for the slots in between, which is
-// also what lets overlap mode pack while the interior particles are still being updated.
-struct SlabRegion {
-    int64_t r0, r1, total;            // head = [0, r0), tail = [r1, r1 + total - r0)
-};
-__device__ __forceinline__ SlabRegion slab_region(const int *__restrict__ region, const int *__restrict__ n_keep, int64_t n)
-{
-    SlabRegion R;
-    if (!region) { R.r0 = n; R.r1 = n; R.total = n; return R; }      // before the first step: every slot
-    const int64_t keep = min((int64_t)*n_keep, n);
-    R.r0 = min((int64_t)region[0], keep);
-    R.r1 = max(min((int64_t)region[1], keep), R.r0);
-    R.total = R.r0 + (keep - R.r1);
-    return R;
-}
-__device__ __forceinline__ int64_t slab_slot(const SlabRegion &R, int64_t t) { return t < R.r0 ? t : R.r1 + (t - R.r0); }
 
 // counts per warp of the compact index space: cnt[cat * nw + warp] (cnt is cleared by the caller; only non-zero counts are written)
 __global__ void __launch_bounds__(256)
@@ -219,17 +199,6 @@ k_slab_unpack(FsgDev d, const void *from_left, const void *from_right, int64_t c
     keys[i] = bin_id(d, pd.x, pd.y, pd.z);
 }
 
-#define CUS(ctx, call)                                                                                  \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess) {                                                                        \
-            char b_[512];                                                                               \
-            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-            (ctx)->err = b_;                                                                            \
-            return e_ == cudaErrorMemoryAllocation ? FSG_E_NOMEM : FSG_E_CUDA;                          \
-        }                                                                                               \
-    } while (0)
-
 extern "C" int64_t fsg_slab_message_bytes(int64_t cap_m, int64_t cap_g) { return 64 + slab_body_float4(false, cap_m, cap_g) * (int64_t)sizeof(float4) + 64; }
 extern "C" int64_t fsg_slab_message_bytes_model(int model, int64_t cap_m, int64_t cap_g)
 {
@@ -267,6 +236,32 @@ __global__ void k_slab_wait(const volatile long long *tail_left, const volatile 
     __threadfence_system();
 }
 
+int fsg_slab_ensure_counts(fsg_ctx *c, int64_t nw)
+{
+    if (nw <= c->slab_warps) return FSG_OK;
+    CUS(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->slab_cnt); cudaFree(c->scan_tmp);
+    c->slab_cnt = nullptr; c->scan_tmp = nullptr;
+    const int64_t capw = (c->cap + 31) / 32 + 1;
+    CUS(c, cudaMalloc(&c->slab_cnt, sizeof(int) * 2 * (4 * capw + 8) + 128));
+    CUS(c, cudaMemsetAsync(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * capw + 8), 0, 128, c->stream));
+    c->scan_tmp_bytes = fsg_scan_temp_bytes(4 * capw + 1);
+    CUS(c, cudaMalloc(&c->scan_tmp, c->scan_tmp_bytes ? c->scan_tmp_bytes : 16));
+    c->slab_warps = capw;
+    return FSG_OK;
+}
+long long *fsg_slab_diag(fsg_ctx *c)
+{
+    return reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
+}
+cudaError_t fsg_launch_slab_wait(fsg_ctx *c, const long long *tail_left, const long long *tail_right, long long expected, cudaStream_t s);
+
+cudaError_t fsg_launch_slab_wait(fsg_ctx *c, const long long *tail_left, const long long *tail_right, long long expected, cudaStream_t s)
+{
+    k_slab_wait<<<1, 32, 0, s>>>(tail_left, tail_right, expected, c->counters + 9, c->host_flag_dev, c->slab_timeout_ns);
+    return cudaGetLastError();
+}
+
 // counters: [5] slots in use (device-side), [6] ghost-band violation, [9] message / capacity overflow
 static int slab_pack_on(fsg_ctx *c, void *d_to_left, void *d_to_right, int64_t cap_m, int64_t cap_g, const int *region, long long stamp,
                         cudaStream_t st)
@@ -277,18 +272,9 @@ static int slab_pack_on(fsg_ctx *c, void *d_to_left, void *d_to_right, int64_t c
     CUS(c, cudaSetDevice(c->device));
     const int64_t n = c->n;                           // == capacity for a slab context: unused slots hold the dead key
     const int64_t nw = (n + 31) / 32 > 0 ? (n + 31) / 32 : 1;
-    if (nw > c->slab_warps) {
-        CUS(c, cudaStreamSynchronize(c->stream));
-        cudaFree(c->slab_cnt); cudaFree(c->scan_tmp);
-        c->slab_cnt = nullptr; c->scan_tmp = nullptr;
-        const int64_t capw = (c->cap + 31) / 32 + 1;
-        CUS(c, cudaMalloc(&c->slab_cnt, sizeof(int) * 2 * (4 * capw + 8) + 128));
-        c->scan_tmp_bytes = fsg_scan_temp_bytes(4 * capw + 1);
-        CUS(c, cudaMalloc(&c->scan_tmp, c->scan_tmp_bytes ? c->scan_tmp_bytes : 16));
-        c->slab_warps = capw;
-    }
+    if (int rc = fsg_slab_ensure_counts(c, nw)) return rc;
     int *cnt = c->slab_cnt, *off = c->slab_cnt + (4 * c->slab_warps + 8);
-    long long *diag = reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
+    long long *diag = fsg_slab_diag(c);
     // a fixed-size grid strides over the compact index space (its length is only known on the device)
     int64_t want = (nw * 32 + 255) / 256;
     const int64_t cap_blocks = (int64_t)c->sm_count * 16;
@@ -322,7 +308,7 @@ extern "C" int fsg_slab_unpack(fsg_ctx *c, const void *d_from_left, const void *
     if (c->cfg.rank == 0) d_from_left = nullptr;
     if (c->cfg.rank == c->cfg.world - 1) d_from_right = nullptr;
     if (!c->slab_cnt) { c->err = "fsg_slab_unpack: call fsg_slab_pack first"; return FSG_E_STATE; }
-    long long *diag = reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
+    long long *diag = fsg_slab_diag(c);
     const int64_t threads = 2 * (cap_m + cap_g);
     if (threads > 0) {
         k_slab_unpack<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->dev, d_from_left, d_from_right, cap_m, cap_g,
@@ -347,8 +333,7 @@ extern "C" int fsg_slab_check(fsg_ctx *c, int64_t info[9])
     if (c->comm) CUS(c, cudaStreamSynchronize(c->comm));
     CUS(c, cudaMemcpyAsync(cnt, c->counters, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
     if (c->slab_cnt) {
-        long long *d = reinterpret_cast<long long *>(reinterpret_cast<char *>(c->slab_cnt) + sizeof(int) * 2 * (4 * c->slab_warps + 8));
-        CUS(c, cudaMemcpyAsync(diag, d, sizeof diag, cudaMemcpyDeviceToHost, c->stream));
+        CUS(c, cudaMemcpyAsync(diag, fsg_slab_diag(c), sizeof diag, cudaMemcpyDeviceToHost, c->stream));
     }
     CUS(c, cudaStreamSynchronize(c->stream));
     if (info) {
@@ -361,7 +346,8 @@ extern "C" int fsg_slab_check(fsg_ctx *c, int64_t info[9])
         return FSG_E_STATE;
     }
     if (cnt[9]) {
-        c->err = (cnt[9] & 4) ? "slab exchange: timed out waiting for a neighbour's message"
+        c->err = (cnt[9] & 8) ? "slab exchange: a neighbour sent migrants in a different update state (every rank has to make the same calls)"
+                 : (cnt[9] & 4) ? "slab exchange: timed out waiting for a neighbour's message"
                  : (cnt[9] & 2) ? "slab exchange: received particles exceed the context capacity"
                               : "slab exchange: a message exceeded its capacity (cap_m / cap_g)";
         return FSG_E_NOMEM;
@@ -378,7 +364,7 @@ extern "C" int fsg_slab_check(fsg_ctx *c, int64_t info[9])
 // Inboxes are double-buffered by step parity: a message for step s+1 never lands in memory the
 // neighbour may still be unpacking for step s.
 // ------------------------------------------------------------------------------------------------
-extern "C" int fsg_slab_alloc_messages(fsg_ctx *c, int64_t cap_m, int64_t cap_g)
+static int slab_alloc_messages(fsg_ctx *c, int64_t cap_m, int64_t cap_g, int flags)
 {
     if (!c || cap_m < 0 || cap_g < 0) return FSG_E_INVALID;
     if (c->cfg.world <= 1) { c->err = "fsg_slab_alloc_messages: not a slab context (world == 1)"; return FSG_E_STATE; }
@@ -386,7 +372,11 @@ extern "C" int fsg_slab_alloc_messages(fsg_ctx *c, int64_t cap_m, int64_t cap_g)
     CUS(c, cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 2; k++) { cudaFree(c->outbox[k]); c->outbox[k] = nullptr; }
     for (int k = 0; k < 4; k++) { cudaFree(c->inbox[k]); c->inbox[k] = nullptr; }
-    const size_t bytes = slab_bytes(c, cap_m, cap_g);
+    size_t bytes = slab_bytes(c, cap_m, cap_g);
+    // the sorted-ghost pipeline (fsg_slab2.cu) where it applies, unless the caller asked for the classic one (flags bit 0)
+    c->slab2 = false;
+    c->dev.kx0 = c->dev.kx1 = INT_MIN;
+    if (!(flags & 1)) { int rc = fsg_slab2_engage(c, cap_m, cap_g, &bytes); if (rc != FSG_OK) return rc; }
     for (int k = 0; k < 2; k++) { CUS(c, cudaMalloc(&c->outbox[k], bytes)); CUS(c, cudaMemsetAsync(c->outbox[k], 0, bytes, c->stream)); }
     for (int k = 0; k < 4; k++) { CUS(c, cudaMalloc(&c->inbox[k], bytes)); CUS(c, cudaMemsetAsync(c->inbox[k], 0, bytes, c->stream)); }
     CUS(c, cudaStreamSynchronize(c->stream));
@@ -402,6 +392,10 @@ extern "C" int fsg_slab_alloc_messages(fsg_ctx *c, int64_t cap_m, int64_t cap_g)
     c->slab_timeout_ns = (unsigned long long)((tms > 1.0 ? tms : 1.0) * 1e6);
     return FSG_OK;
 }
+
+extern "C" int fsg_slab_alloc_messages(fsg_ctx *c, int64_t cap_m, int64_t cap_g) { return slab_alloc_messages(c, cap_m, cap_g, 0); }
+extern "C" int fsg_slab_alloc_messages2(fsg_ctx *c, int64_t cap_m, int64_t cap_g, int flags) { return slab_alloc_messages(c, cap_m, cap_g, flags); }
+extern "C" int fsg_slab_mode(fsg_ctx *c) { return !c || c->cfg.world <= 1 ? 0 : c->slab2 ? 2 : 1; }
 
 // side 0: the inbox that receives from the LEFT neighbour, side 1: from the RIGHT one; parity 0/1
 extern "C" int fsg_slab_inbox_handle(fsg_ctx *c, int side, int parity, void *handle64)
@@ -469,7 +463,8 @@ extern "C" int fsg_slab_pack_send(fsg_ctx *c)
     if (int rc = fsg_slab_sticky_error(c)) return rc;
     if (c->sent_ahead) { c->sent_ahead = false; return FSG_OK; }      // fsg_step already issued this exchange (overlap mode)
     // (before the first step the particles are in upload order: every slot is looked at)
-    return slab_send_on(c, c->steps > 0 ? c->counters + 12 : nullptr, c->stream);
+    if (c->slab2) return fsg_slab2_pack_send(c);
+    return slab_send_on(c, c->steps > 0 ? c->counters + 16 : nullptr, c->stream);
 }
 
 // overlap mode, called by fsg_step between the boundary and the interior bins: the next step's messages are
@@ -478,7 +473,7 @@ int fsg_slab_send_next(fsg_ctx *c)
 {
     CUS(c, cudaEventRecord(c->ev_boundary, c->stream));
     CUS(c, cudaStreamWaitEvent(c->comm, c->ev_boundary, 0));
-    int rc = slab_send_on(c, c->counters + 12, c->comm);
+    int rc = slab_send_on(c, c->counters + 16, c->comm);
     if (rc != FSG_OK) return rc;
     CUS(c, cudaEventRecord(c->ev_sent, c->comm));
     c->sent_ahead = true;
@@ -491,15 +486,14 @@ extern "C" int fsg_slab_unpack_recv(fsg_ctx *c)
     if (!c->inbox[0]) { c->err = "fsg_slab_unpack_recv: call fsg_slab_alloc_messages first"; return FSG_E_STATE; }
     if (int rc = fsg_slab_sticky_error(c)) return rc;
     CUS(c, cudaSetDevice(c->device));
+    if (c->slab2) return fsg_slab2_unpack_recv(c);
     const long long seq = ++c->seq_recv;
     const int par = (int)(seq & 1);
     const bool left = c->cfg.rank > 0, right = c->cfg.rank < c->cfg.world - 1;
     if (c->overlap) CUS(c, cudaStreamWaitEvent(c->stream, c->ev_sent, 0));   // my own pack (other stream) reads the slots unpack writes
     const size_t tail = (slab_bytes(c, c->msg_cap_m, c->msg_cap_g) - 64);
-    k_slab_wait<<<1, 32, 0, c->stream>>>(left ? (const long long *)((char *)c->inbox[par] + tail) : nullptr,
-                                         right ? (const long long *)((char *)c->inbox[2 + par] + tail) : nullptr, seq, c->counters + 9,
-                                         c->host_flag_dev, c->slab_timeout_ns);
-    CUS(c, cudaGetLastError());
+    CUS(c, fsg_launch_slab_wait(c, left ? (const long long *)((char *)c->inbox[par] + tail) : nullptr,
+                                right ? (const long long *)((char *)c->inbox[2 + par] + tail) : nullptr, seq, c->stream));
     c->launches++;
     return fsg_slab_unpack(c, c->inbox[par], c->inbox[2 + par], c->msg_cap_m, c->msg_cap_g);
 }
@@ -527,6 +521,10 @@ extern "C" int fsg_slab_set_overlap(fsg_ctx *c, int on)
     if (c->cfg.world <= 1) { c->err = "fsg_slab_set_overlap: not a slab context (world == 1)"; return FSG_E_STATE; }
     if (on && !c->outbox[0]) { c->err = "fsg_slab_set_overlap: needs the peer-memory exchange (fsg_slab_alloc_messages)"; return FSG_E_STATE; }
     if (on && c->cfg.model != FSG_MODEL_BASE) { c->err = "fsg_slab_set_overlap: base model only"; return FSG_E_UNSUPPORTED; }
+    if (on && c->slab2) {
+        c->err = "fsg_slab_set_overlap: the messages were allocated for the sorted-ghost pipeline; use fsg_slab_alloc_messages2(.., 1)";
+        return FSG_E_STATE;
+    }
     CUS(c, cudaSetDevice(c->device));
     CUS(c, cudaStreamSynchronize(c->stream));
     if (on && !c->comm) {

@@ -31,8 +31,10 @@ from .solver import FluidSolver
 # ---------------------------------------------------------------------------------------------
 # partition
 # ---------------------------------------------------------------------------------------------
-def slab_cuts(hist, world: int, min_layers: int = 2) -> list[tuple[int, int]]:
-    """Cuts bin layers 0..G-1 into `world` contiguous slabs minimising the largest particle count.
+def slab_cuts(hist, world: int, min_layers: int = 2, ghost_weight: float = 0.0) -> list[tuple[int, int]]:
+    """Cuts bin layers 0..G-1 into `world` contiguous slabs minimising the largest load, load = particles owned +
+    ghost_weight x particles of the layer below the slab (the symmetric pair kernel walks that ghost layer as home bins
+    restricted to 3 of its 5 runs: ghost_weight = 0.6; 0 = plain particle count).
     hist[ix] = particles in bin layer ix.  Empty outer layers go to the end ranks.
     Every slab is at least `min_layers` thick: a particle that migrates into a slab must not at the
     same time be needed as a ghost by the slab beyond it (the one-layer ghost band of the reference,
@@ -46,6 +48,10 @@ def slab_cuts(hist, world: int, min_layers: int = 2) -> list[tuple[int, int]]:
     if G < min_layers * world:
         raise ValueError(f"{G} bin layers cannot hold {world} slabs of at least {min_layers} layers")
     cum = np.concatenate([[0], np.cumsum(hist)])
+    gw = float(ghost_weight)
+
+    def ghost(x):
+        return int(gw * hist[x - 1]) if (gw > 0.0 and x > 0) else 0
 
     def feasible(limit):
         """Greedy: can the layers be covered by `world` slabs of >= min_layers layers and <= limit particles?"""
@@ -57,12 +63,12 @@ def slab_cuts(hist, world: int, min_layers: int = 2) -> list[tuple[int, int]]:
             if lo > hi:
                 return None
             # furthest end with load <= limit
-            e = int(np.searchsorted(cum, cum[x] + limit, side="right")) - 1
+            e = int(np.searchsorted(cum, cum[x] + limit - ghost(x), side="right")) - 1
             e = min(e, hi)
             if e < lo:
                 return None
             if remaining == 0:
-                if cum[G] - cum[x] > limit:
+                if cum[G] - cum[x] + ghost(x) > limit:
                     return None
                 e = G
             cuts.append(e)
@@ -70,7 +76,7 @@ def slab_cuts(hist, world: int, min_layers: int = 2) -> list[tuple[int, int]]:
         return cuts
 
     # smallest achievable maximum load (binary search over the load limit)
-    lo_l, hi_l = int(hist.max()) * min_layers // 2, int(hist.sum()) + 1
+    lo_l, hi_l = int(hist.max()) * min_layers // 2, int(hist.sum() * (1.0 + gw)) + 1
     best = feasible(hi_l)
     while lo_l < hi_l:
         mid = (lo_l + hi_l) // 2
@@ -199,13 +205,16 @@ class SlabSolver(FluidSolver):
     def unpack(self, from_left_ptr, from_right_ptr):
         self._check(self._lib.fsg_slab_unpack(self._ctx, from_left_ptr, from_right_ptr, self.cap_m, self.cap_g), "fsg_slab_unpack")
 
-    def setup_peer_exchange(self, overlap: bool = False):
+    def setup_peer_exchange(self, overlap: bool = False, classic: bool = False):
         """Maps the neighbours' inboxes into this process (CUDA IPC; one process per GPU on one node).  From
-        then on a step copies its messages straight into the neighbours' memory over NVLink (copy engines); the
-        sequence number copied last tells the receiver, on the device, that the message is complete — no
-        communication library and no host inside a step."""
+        then on a step copies its messages straight into the neighbours' memory over NVLink; the
+        sequence number written last tells the receiver, on the device, that the message is complete — no
+        communication library and no host inside a step.  Base-model contexts run the sorted-ghost pipeline
+        (fsg_slab2.cu: migrants before the sort, the sorted face layers after the reorder) unless `classic` or
+        `overlap` asks for the one whose ghosts travel through the sort."""
         ex = self.exchange
-        self._check(self._lib.fsg_slab_alloc_messages(self._ctx, self.cap_m, self.cap_g), "fsg_slab_alloc_messages")
+        self._check(self._lib.fsg_slab_alloc_messages2(self._ctx, self.cap_m, self.cap_g, 1 if (classic or overlap) else 0),
+                    "fsg_slab_alloc_messages2")
         mine = {}
         for side in (0, 1):
             for par in (0, 1):
@@ -222,6 +231,17 @@ class SlabSolver(FluidSolver):
         self.peer = True
         if overlap:
             self.set_overlap(True)
+
+    @property
+    def mode(self) -> int:
+        """1: classic pipeline (ghosts appended and sorted), 2: sorted ghosts."""
+        return int(self._lib.fsg_slab_mode(self._ctx))
+
+    def ghost_ms(self) -> float:
+        """Mean device milliseconds per step of the ghost exchange inside fsg_step (sorted-ghost pipeline, profiling on)."""
+        ms, k = C.c_double(0.0), C.c_int64(0)
+        self._check(self._lib.fsg_slab_get_ghost_ms(self._ctx, C.byref(ms), C.byref(k)), "fsg_slab_get_ghost_ms")
+        return float(ms.value)
 
     def set_overlap(self, on: bool = True):
         """Boundary bins first, then the next step's pack + peer copies on a second stream beside the interior bins."""
@@ -287,8 +307,13 @@ class SlabSolver(FluidSolver):
 
     @property
     def wire_bytes_per_step(self) -> int:
-        """Bytes this rank sends per step (fixed-size messages to its 1 or 2 neighbours)."""
-        return self.msg_bytes * ((self.cfg.rank > 0) + (self.cfg.rank < self.cfg.world - 1))
+        """Bytes this rank sends per step: fixed-size messages to its 1 or 2 neighbours; on the sorted-ghost pipeline the
+        fixed-size migrant part + the ghosts actually sent in the last step (36 B each: posd, velp, key)."""
+        nb = (self.cfg.rank > 0) + (self.cfg.rank < self.cfg.world - 1)
+        if self.mode == 2:
+            sent = self.check()["sent"]
+            return (128 + 80 * self.cap_m) * nb + 36 * (sent[1] + sent[3])
+        return self.msg_bytes * nb
 
     def download(self, fields=None) -> dict:
         """Only the particles this slab owns (ghost / migrated / unused slots are dropped)."""
@@ -305,14 +330,14 @@ class SlabSolver(FluidSolver):
 # ---------------------------------------------------------------------------------------------
 class SlabGroup:
     def __init__(self, base_cfg: FsgConfig, world: int, cuts, capacity: int, device: int = 0, cap_m: int = 4096, cap_g: int = 65536,
-                 peer: bool = False, overlap: bool = False):
+                 peer: bool = False, overlap: bool = False, classic: bool = False):
         self.world = world
         self.cuts = cuts
         self.peer = peer
         self.slabs = [SlabSolver(slab_config(base_cfg, r, world, cuts, capacity, device), None, cap_m, cap_g) for r in range(world)]
         if peer:         # the peer-memory protocol with plain pointers instead of IPC mappings (same process)
             for s in self.slabs:
-                s._check(s._lib.fsg_slab_alloc_messages(s._ctx, cap_m, cap_g), "fsg_slab_alloc_messages")
+                s._check(s._lib.fsg_slab_alloc_messages2(s._ctx, cap_m, cap_g, 1 if (classic or overlap) else 0), "fsg_slab_alloc_messages2")
             for r, s in enumerate(self.slabs):
                 for par in (0, 1):
                     if r > 0:
@@ -322,6 +347,8 @@ class SlabGroup:
                 s.peer = True
                 if overlap:
                     s.set_overlap(True)
+                if s.mode == 2:     # one device runs every slab: first halves of all steps, then the second halves
+                    s._check(s._lib.fsg_slab_set_split_step(s._ctx, 1), "fsg_slab_set_split_step")
 
     def close(self):
         for s in self.slabs:
@@ -354,6 +381,10 @@ class SlabGroup:
                     s.sync()
                 for s in self.slabs:
                     s._check(s._lib.fsg_step(s._ctx, 1), "fsg_step")
+                for s in self.slabs:
+                    s.sync()
+                for s in self.slabs:      # (a no-op unless the step was split: sorted-ghost pipeline)
+                    s._check(s._lib.fsg_slab_step_finish(s._ctx), "fsg_slab_step_finish")
                 for s in self.slabs:
                     s.sync()
                 continue

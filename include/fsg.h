@@ -236,6 +236,23 @@ FSG_API int64_t fsg_slab_message_bytes_model(int model, int64_t cap_m, int64_t c
  * behind the copy with any stream-ordered signal (a few-byte NCCL send/recv).  side 0 = left, 1 = right;
  * inboxes are double-buffered by step parity. */
 FSG_API int  fsg_slab_alloc_messages(fsg_ctx *ctx, int64_t cap_m, int64_t cap_g);
+/* For the base model the library-owned messages run the SORTED-GHOST pipeline (fsg_slab2.cu) when they are allocated before the
+ * first upload: ghosts never pass through the sort.  fsg_slab_pack_send moves only the migrants (pre-update state + pending pair
+ * sums; the update is deferred like on one device), fsg_slab_unpack_recv appends them, and fsg_step — after its reorder — copies
+ * the face layers of the SORTED state straight into the neighbours' ghost zones (the top 2 * cap_g slots of the particle arrays:
+ * the context works on capacity - 2 * cap_g slots), waits for theirs on the device and adds their bins to the tables.  Every rank
+ * has to make the same calls; the state cannot be read between fsg_slab_pack_send and fsg_step.
+ * fsg_slab_alloc_messages2: flags bit 0 = keep the classic pipeline (ghosts appended and sorted; needed by fsg_slab_set_overlap).
+ * fsg_slab_mode: 0 not a slab context, 1 classic, 2 sorted ghosts.  fsg_slab_get_ghost_ms: mean device time per step of the
+ * ghost exchange inside fsg_step (send + wait for the neighbours + install) while profiling is on. */
+FSG_API int  fsg_slab_alloc_messages2(fsg_ctx *ctx, int64_t cap_m, int64_t cap_g, int flags);
+FSG_API int  fsg_slab_mode(fsg_ctx *ctx);
+FSG_API int  fsg_slab_get_ghost_ms(fsg_ctx *ctx, double *ms, int64_t *steps);
+/* Several slab contexts of ONE process on one device (tests): with split steps on, fsg_step returns after its ghost send and
+ * fsg_slab_step_finish does the rest (wait, install, pair sums) — finish the first half of every slab before any second half, so
+ * that no kernel spins on a device that still has to run (or lazily load) what it waits for.  One process per device needs neither. */
+FSG_API int  fsg_slab_set_split_step(fsg_ctx *ctx, int on);
+FSG_API int  fsg_slab_step_finish(fsg_ctx *ctx);
 FSG_API int  fsg_slab_inbox_handle(fsg_ctx *ctx, int side, int parity, void *handle64);
 FSG_API int  fsg_slab_open_peer(fsg_ctx *ctx, int side, int parity, const void *handle64);
 FSG_API int  fsg_slab_pack_send(fsg_ctx *ctx);

@@ -339,20 +339,26 @@ def _slab_scene(fsg, fast: bool):
     return cfg, state
 
 
-@pytest.mark.parametrize("mode", ["messages", "peer", "peer+overlap"])
+@pytest.mark.parametrize("mode", ["messages", "peer", "peer-classic", "peer+overlap"])
 @pytest.mark.parametrize("world", [2, 3, 5])
 @pytest.mark.parametrize("fast", [False, True])
 def test_slabs_match_single_device(fsg, world, fast, mode):
     """W x-slabs with migration + one-layer ghost exchange against ONE context on the same scene,
     resynchronised every step: positions, velocities and every integer result bit-exact (they do
-    not depend on the summation order), sums within 1e-5."""
+    not depend on the summation order), sums within 1e-5.  "peer" runs the sorted-ghost pipeline (fsg_slab2.cu),
+    the other modes the classic one (ghosts appended and sorted)."""
     cfg, state = _slab_scene(fsg, fast)
     n = state["pos"].shape[0]
     cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), world)
     cfg.capacity = n
     moved = 0
-    kw = dict(peer=mode != "messages", overlap=mode == "peer+overlap")
-    with fsg.SlabGroup(cfg, world, cuts, capacity=2 * n + 64, **kw) as g, fsg.FluidSolver(cfg) as s:
+    kw = dict(peer=mode != "messages", overlap=mode == "peer+overlap", classic=mode == "peer-classic")
+    cap = 2 * n + 64
+    if mode == "peer":
+        kw.update(cap_m=n, cap_g=n)
+        cap += 2 * n                   # the two ghost zones are carved out of the capacity
+    with fsg.SlabGroup(cfg, world, cuts, capacity=cap, **kw) as g, fsg.FluidSolver(cfg) as s:
+        assert all(sl.mode == (2 if mode == "peer" else 1) for sl in g.slabs)
         g.upload(state)
         # (the boundary scene is stiff — ALPHA_BOUNDARY = 200 — and is only followed for a few steps)
         for k in range(6 if fast else 3):
@@ -377,6 +383,56 @@ def test_slabs_match_single_device(fsg, world, fast, mode):
             assert ix.size == 0 or (ix.min() >= cuts[r][0] - 1 and ix.max() <= cuts[r][1])
     if fast:
         assert moved > 0, "the scene was meant to exercise migration"
+
+
+@pytest.mark.parametrize("pair_mode", [0, 1])
+@pytest.mark.parametrize("world", [2, 4])
+def test_sorted_ghost_pipeline_free_running(fsg, world, pair_mode):
+    """The sorted-ghost pipeline WITHOUT resynchronisation: eight steps in which nothing is downloaded, so that the update stays
+    deferred on every slab and migrants travel with their pre-update state and pending pair sums (fsg_slab2.cu).  Against one
+    context running the same eight steps, and against the classic slab pipeline: the particle set is conserved, particles migrate,
+    and the trajectories agree to rounding (they differ only by the order of the pair sums)."""
+    cfg, state = _slab_scene(fsg, True)
+    cfg.pair_mode = pair_mode
+    n = state["pos"].shape[0]
+    cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), world)
+    cfg.capacity = n
+    steps = 8
+    with fsg.FluidSolver(cfg) as s:
+        s.upload(state)
+        s.step(steps)
+        ref = fsg.by_index(s.download())
+    out = {}
+    for name, kw, cap in (("sorted", dict(cap_m=n, cap_g=n), 4 * n + 64), ("classic", dict(classic=True), 2 * n + 64)):
+        with fsg.SlabGroup(cfg, world, cuts, capacity=cap, peer=True, **kw) as g:
+            assert all(sl.mode == (2 if name == "sorted" else 1) for sl in g.slabs)
+            g.upload(state)
+            moved = 0
+            for _ in range(steps):
+                g.step(1)
+                moved += sum(c["sent"][0] + c["sent"][2] for c in g.check())     # (reads counters only: the update stays deferred)
+            out[name] = fsg.by_index(g.download())
+            assert moved > 0, "the scene was meant to exercise migration"
+    for name, got in out.items():
+        assert got["index"].shape[0] == n and np.array_equal(got["index"], np.arange(n)), (name, "particles lost or duplicated")
+        assert np.array_equal(got["boundary"], ref["boundary"])
+        for f in ("pos", "vel", "acc", "dens", "press", "delpress"):
+            err = rel_l2(got[f], ref[f])
+            assert err <= 20 * TOL, (name, f, err)
+        assert (got["cell"] == ref["cell"]).mean() > 0.999, name
+
+
+def test_sorted_ghost_pipeline_reports_overflow(fsg):
+    """Ghost zones / migrant messages that are too small are reported, not silently truncated."""
+    cfg, state = _slab_scene(fsg, True)
+    n = state["pos"].shape[0]
+    cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), 2)
+    with fsg.SlabGroup(cfg, 2, cuts, capacity=2 * n + 64, peer=True, cap_m=n, cap_g=16) as g:
+        assert g.slabs[0].mode == 2
+        g.upload(state)
+        g.step(1)
+        with pytest.raises(fsg.FsgError, match="capacity"):
+            g.check()
 
 
 def test_slab_plume_device_scene(fsg):
