@@ -66,10 +66,12 @@ def test_the_real_unidyn_driver_links_and_runs_against_libfsg(tmp_path):
         (pa, ma, sa), (pb, mb, sb) = _read_vtk_ascii(a), _read_vtk_ascii(b)
         assert pa.shape == pb.shape
         # frames carry no particle index and each run writes its own sorted order: match every particle of one frame with its
-        # nearest neighbour in the other (particle spacing 0.04 .. 0.05 >> the differences looked for); the match must be one to one
+        # nearest neighbour in the other (particle spacing 0.04 .. 0.05 >> the differences looked for), in both directions.  (The
+        # match is not one to one: the driver's GPU0 frame holds 155 records twice — its buffer copies — with either set of kernels.)
         from scipy.spatial import cKDTree
         dist, nn = cKDTree(pb).query(pa)
-        assert len(np.unique(nn)) == len(nn), t
+        back, _ = cKDTree(pa).query(pb)
+        assert len(np.unique(nn)) == len(np.unique(pb, axis=0)), t
         err = float(np.sqrt((dist ** 2).sum() / (pb ** 2).sum()))
-        assert err <= 1e-4, (t, err)
+        assert err <= 1e-4 and float(back.max()) <= 1e-4, (t, err, float(back.max()))
         assert np.array_equal(ma, mb[nn])
