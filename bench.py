@@ -346,9 +346,12 @@ def make_solver(fsg, G, rank, world, local, args):
     hist = fsg.slab.plume_layer_hist(cfg, SPACING)
     cuts = fsg.slab_cuts(hist, world)
     owned = [int(hist[a:b].sum()) for a, b in cuts]
-    cap = int(max(owned) * 1.05) + 3 * int(hist.max()) + 65536
-    cfg = fsg.slab_config(cfg, rank, world, cuts, cap, local)
     cap_m, cap_g = fsg.slab.message_caps(hist, cuts)
+    if args.exchange == "peer" and not (args.overlap or args.classic_slabs):
+        cap = int(max(owned) * 1.03) + 2 * cap_g + 65536          # sorted ghosts: own particles + slack | the two ghost zones
+    else:
+        cap = int(max(owned) * 1.05) + 3 * int(hist.max()) + 65536  # classic: ghosts are appended behind the own particles
+    cfg = fsg.slab_config(cfg, rank, world, cuts, cap, local)
     solver = fsg.SlabSolver(cfg, fsg.DistExchange(), cap_m, cap_g)
     if args.exchange == "peer":
         solver.setup_peer_exchange(overlap=args.overlap, classic=args.classic_slabs)
