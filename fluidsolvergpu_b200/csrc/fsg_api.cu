@@ -318,7 +318,7 @@ static int after_upload(fsg_ctx *c, int64_t n, const int *slot_state = nullptr)
 {
     // the bin tables may hold the entries of a previous run
     if (c->tables_dirty) {
-        if (c->cfg.world > 1) CU(c, fsg_launch_reset_tables_keys(c->dev, c->keysA, c->start, c->end, c->n_sorted, c->stream));
+        if (c->cfg.world > 1 && !c->slab2) CU(c, fsg_launch_reset_tables_keys(c->dev, c->keysA, c->start, c->end, c->n_sorted, c->stream));
         else CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, c->n, c->stream));
         c->launches++;
         c->tables_dirty = false;
@@ -749,7 +749,9 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         const bool prof = c->profiling && c->ev_used.size() < 5 * 4096;
         if (prof) prof_mark(c);
         if (c->tables_dirty) {
-            if (c->cfg.world > 1) CU(c, fsg_launch_reset_tables_keys(c->dev, c->keysA, c->start, c->end, c->n_sorted, c->stream));
+            // (classic slab contexts: ghost bins have table entries but are not in the home-bin list, so the reset walks the sorted
+            // keys; on the sorted-ghost pipeline every own bin is a home bin and the ghost bins are reset from their messages)
+            if (c->cfg.world > 1 && !c->slab2) CU(c, fsg_launch_reset_tables_keys(c->dev, c->keysA, c->start, c->end, c->n_sorted, c->stream));
             else CU(c, fsg_launch_reset_tables(c->binlist[c->cur], c->counters + c->cur, c->keysA, c->start, c->end, n, c->stream));
             c->launches++;
             if (c->slab2) { int rc = fsg_slab2_reset_ghost_tables(c); if (rc != FSG_OK) return rc; }

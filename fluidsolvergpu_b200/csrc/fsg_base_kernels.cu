@@ -127,19 +127,10 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
     const int numcells = d.numcells;
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool head = false, headB = false;
-    int key = -1;
     if (k < n) {
-        key = keysA[k];
-        if (key == d.dead) {
-            // an unused slot of a slab context (a third of the capacity at 8 slabs): nothing to gather, update or list
-            if (keys_next) keys_next[k] = key;
-            if (k + 1 < n && keysA[k + 1] < key) atomicOr(order_flag, 1);
-            key = -1;
-        }
-    }
-    if (k < n && key >= 0) {
         int sidx = perm[k];
         float4 a = src.posd[sidx], b = src.velp[sidx], c = src.accf[sidx], e = src.dpi[sidx];
+        int key = keysA[k];
         if (UPD) {
             // particles that were parked BEFORE the update pass through unchanged, like k_update; one that leaves the grid in this
             // update (key == numcells now, position still inside) gets it, and is parked from then on

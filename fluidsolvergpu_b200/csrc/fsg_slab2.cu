@@ -310,7 +310,9 @@ int fsg_slab2_pack_send(fsg_ctx *c)
     int64_t want = (nw * 32 + 255) / 256;
     const int64_t cap_blocks = (int64_t)c->sm_count * 16;
     const unsigned blocks = (unsigned)(want < cap_blocks ? (want > 0 ? want : 1) : cap_blocks);
-    const int *region = c->steps > 0 ? c->counters + 16 : nullptr;     // (before the first step the particles are in upload order)
+    // (before the first step the particles are in upload order: every slot is looked at; afterwards only the two face layers —
+    // a particle moves less than one bin layer per step, so a migrant was in layer x0 or x1 - 1)
+    const int *region = c->steps > 0 ? c->counters + 18 : nullptr;
     const int *n_keep = c->counters + 5;
     // the state a migrant carries: pre-update + pending sums while the update is deferred, else the materialised state
     const FsgState S = c->deferred ? c->A : c->B;

@@ -78,3 +78,23 @@ def _exchange_worker(rank, world, port, rounds):
 @pytest.mark.parametrize("world", [2, 3])
 def test_dist_exchange_gloo(world):
     mp.spawn(_exchange_worker, args=(world, _free_port(), 3), nprocs=world, join=True)
+
+
+def test_slab_cuts_with_a_ghost_layer_weight():
+    """ghost_weight adds a share of the layer below each slab to its load (the symmetric pair kernel walks that ghost layer as home
+    bins): the cuts stay a partition into slabs of at least two layers, and the weighted maximum is never worse than what the
+    unweighted cuts give under the same measure."""
+    import numpy as np
+    import fluidsolvergpu_b200 as fsg
+    rng = np.random.default_rng(5)
+    for G, world in ((40, 3), (64, 8), (17, 2)):
+        hist = (rng.integers(0, 1000, size=G) * (rng.random(G) < 0.7)).astype(np.int64)
+        hist[G // 3:2 * G // 3] += 500
+
+        def load(cuts, w):
+            return max(int(hist[a:b].sum()) + (int(w * hist[a - 1]) if a > 0 else 0) for a, b in cuts)
+        plain, weighted = fsg.slab_cuts(hist, world), fsg.slab_cuts(hist, world, ghost_weight=0.6)
+        for cuts in (plain, weighted):
+            assert cuts[0][0] == 0 and cuts[-1][1] == G and all(b - a >= 2 for a, b in cuts)
+            assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+        assert load(weighted, 0.6) <= load(plain, 0.6)
