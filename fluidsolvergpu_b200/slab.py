@@ -414,14 +414,17 @@ class SlabGroup:
 # N slab processes against one context, through the real transport (bench.py `slab_parity`, tests/test_multi_gpu.py)
 # ---------------------------------------------------------------------------------------------
 def parity_against_single(grid: int, rank: int, world: int, device: int, exchange: str = "peer", steps: int = 4, pair_mode: int = 0,
-                          spacing: float = 0.05, jitter: float = 0.005, seed: int = 20261018, drift: float = 25.0) -> dict | None:
+                          spacing: float = 0.05, jitter: float = 0.005, seed: int = 20261018, drift: float = 25.0,
+                          free_steps: int = 6) -> dict | None:
     """Runs the plume scene at grid^3 bins on `world` slab PROCESSES (this is one of them; torch.distributed is initialised,
     one GPU per rank) over the `exchange` transport ('peer': CUDA-IPC inboxes + device-side stamps, 'nccl': send/recv) and,
     on rank 0, on a single context.  Every step starts from identical bits (the single context is re-uploaded from the slabs'
     gathered state, like tests/test_parity_gpu.py::test_slabs_match_single_device does in one process), so that positions,
     velocities, bin ids and boundary flags must agree bit for bit and the pair sums to rounding.  A common drift along x
     (drift * DT * steps >= one lattice spacing, so some lattice plane crosses every slab face; still far below one bin layer per
-    step) makes particles migrate.  Returns the comparison record on rank 0, None elsewhere."""
+    step) makes particles migrate.  Then `free_steps` steps WITHOUT any download in between — on the sorted-ghost pipeline the update
+    stays deferred and migrants travel with their pre-update state and pending pair sums — against the same steps on the single
+    context: same particle set, trajectories equal to rounding (`free_running`).  Returns the record on rank 0, None elsewhere."""
     import torch.distributed as dist
     from . import scenes
     from .solver import by_index
@@ -490,6 +493,30 @@ def parity_against_single(grid: int, rank: int, world: int, device: int, exchang
                     den = float(np.sqrt((b[f].astype(np.float64) ** 2).sum()))
                     err = float(np.sqrt(((a[f].astype(np.float64) - b[f].astype(np.float64)) ** 2).sum()))
                     rec["max_rel_l2"] = max(rec["max_rel_l2"], err / den if den > 0 else err)
+        if free_steps > 0 and rec["bit_exact"]:
+            cur = gather()
+            if rank == 0:
+                single.upload({f: v for f, v in cur.items() if f != "cell"})
+            sent = 0
+            for _ in range(free_steps):
+                s.step(1)
+                info = s.check()                      # (reads counters only: nothing is materialised)
+                sent += info["sent"][0] + info["sent"][2]
+            migrated = ex.global_sum([sent], s.tdev)[0]
+            if rank == 0:
+                single.step(free_steps)
+            a = gather()
+            if rank == 0:
+                b = by_index(single.download())
+                fr = {"steps": free_steps, "migrated": migrated, "pipeline": "sorted ghosts" if s.mode == 2 else "classic",
+                      "conserved": bool(a["index"].shape[0] == n and np.array_equal(a["index"], b["index"])), "max_rel_l2": 0.0}
+                if fr["conserved"]:
+                    fr["cells_equal_frac"] = float((a["cell"] == b["cell"]).mean())
+                    for f in ("pos", "vel") + flds:
+                        den = float(np.sqrt((b[f].astype(np.float64) ** 2).sum()))
+                        err = float(np.sqrt(((a[f].astype(np.float64) - b[f].astype(np.float64)) ** 2).sum()))
+                        fr["max_rel_l2"] = max(fr["max_rel_l2"], err / den if den > 0 else err)
+                rec["free_running"] = fr
         return rec if rank == 0 else None
     finally:
         s.close()

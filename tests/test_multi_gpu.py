@@ -40,6 +40,11 @@ def test_slab_processes_match_single_context(exchange):
         assert r["bit_exact"] and r["cells_equal_frac"] == 1.0, r
         assert r["max_rel_l2"] <= 1e-5, r
         assert r["migrated"] > 0, "the drift was meant to carry particles across the slab faces"
+        # six more steps without a download in between (on the sorted-ghost pipeline: deferred update, migrants with pending sums)
+        fr = r["free_running"]
+        assert fr["conserved"] and fr["migrated"] > 0, fr
+        assert fr["max_rel_l2"] <= 2e-4 and fr["cells_equal_frac"] > 0.999, fr
+        assert fr["pipeline"] == ("sorted ghosts" if exchange == "peer" else "classic"), fr
 
 
 def test_the_real_unidyn_driver_links_and_runs_against_libfsg(tmp_path):
