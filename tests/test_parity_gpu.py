@@ -791,15 +791,19 @@ def test_reference_style_unidyn_driver_links_and_runs_against_libfsg(fsg, tmp_pa
             assert err <= 1e-5, (k, f, err)
 
 
-def test_slab_raw_round_trip_through_host_memory(fsg):
+@pytest.mark.parametrize("pipeline", ["classic", "sorted"])
+def test_slab_raw_round_trip_through_host_memory(fsg, pipeline):
     """The end-to-end path of a slab context: download every slot, upload it again (fsg_slab_keep_foreign), go on.
     Must be bit-identical to a run that never left the device — including particles that had crossed a face and were
-    waiting to migrate when they were downloaded."""
+    waiting to migrate when they were downloaded.  On the sorted-ghost pipeline the run that stays on the device keeps its update
+    deferred all the way while the other one is materialised and re-uploaded every step: same bits."""
     cfg, state = _slab_scene(fsg, True)
     cfg.pair_mode = 1      # bit-identity needs the deterministic gather kernel; the symmetric one sums through float reductions
     n = state["pos"].shape[0]
     cuts = fsg.slab_cuts(fsg.slab.layer_hist_from_positions(cfg, state["pos"]), 3)
-    with fsg.SlabGroup(cfg, 3, cuts, capacity=2 * n + 64) as a, fsg.SlabGroup(cfg, 3, cuts, capacity=2 * n + 64) as b:
+    kw = dict(capacity=2 * n + 64) if pipeline == "classic" else dict(capacity=4 * n + 64, peer=True, cap_m=n, cap_g=n)
+    with fsg.SlabGroup(cfg, 3, cuts, **kw) as a, fsg.SlabGroup(cfg, 3, cuts, **kw) as b:
+        assert all(sl.mode == (2 if pipeline == "sorted" else 1) for sl in a.slabs + b.slabs)
         a.upload(state)
         b.upload(state)
         for sl in b.slabs:
