@@ -77,7 +77,6 @@ k_pair_unidyn(UniArgs a)
 
         for (int ig = 0; ig < hn; ig += 32) {
             const int gcount = min(32, hn - ig);
-            float s_nd = 0.f, s_x = 0.f, s_y = 0.f, s_z = 0.f, s_dx = 0.f, s_dy = 0.f, s_dz = 0.f, s_df = 0.f;
 #pragma unroll 1
             for (int t0 = 0; t0 < C; t0 += UP_TILE) {
                 const int t1 = min(t0 + UP_TILE, C);
@@ -96,11 +95,13 @@ k_pair_unidyn(UniArgs a)
                     }
                 }
                 __syncwarp();
+                // the home particle of the NEXT iteration is requested while this one is being processed
+                float4 n_pi = a.A.posd[hs + ig], n_vi = a.A.velp[hs + ig], n_mi = a.A.mix[hs + ig];
 #pragma unroll 1
                 for (int il = 0; il < gcount; il++) {
                     const int i = hs + ig + il;
-                    const float4 pi = a.A.posd[i], vi = a.A.velp[i];
-                    const float4 mi = a.A.mix[i];
+                    const float4 pi = n_pi, vi = n_vi, mi = n_mi;
+                    if (il + 1 < gcount) { n_pi = a.A.posd[i + 1]; n_vi = a.A.velp[i + 1]; n_mi = a.A.mix[i + 1]; }
                     const float densi = fabsf(pi.w);
                     const bool bi = pi.w < 0.f;
                     const float pod2i = vi.w / (densi * densi);
@@ -189,24 +190,32 @@ k_pair_unidyn(UniArgs a)
                             }
                         }
                     }
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        t_nd += __shfl_xor_sync(FULL, t_nd, o);
-                        t_x += __shfl_xor_sync(FULL, t_x, o);
-                        t_y += __shfl_xor_sync(FULL, t_y, o);
-                        t_z += __shfl_xor_sync(FULL, t_z, o);
-                        t_dx += __shfl_xor_sync(FULL, t_dx, o);
-                        t_dy += __shfl_xor_sync(FULL, t_dy, o);
-                        t_dz += __shfl_xor_sync(FULL, t_dz, o);
-                        t_df += __shfl_xor_sync(FULL, t_df, o);
+                    // The eight sums of this home particle over the 32 lanes by recursive halving (9 shuffles instead of 40): after the
+                    // rounds with 16, 8 and 4 every lane holds ONE of the eight values summed over the 8 lanes that differ from it in
+                    // those bits; two more rounds complete it.  Lane 4 k (k = 0..7) then holds sum number (k&4 ? 4 : 0) + (k&2) + (k&1)
+                    // read off its own bits 4, 3, 2 — and stores it (first tile) or adds it to what the earlier tiles stored.
+                    float r4[4], r2[2], r1;
+                    {
+                        const bool h = lane & 16;
+                        r4[0] = (h ? t_dx : t_nd) + __shfl_xor_sync(FULL, h ? t_nd : t_dx, 16);
+                        r4[1] = (h ? t_dy : t_x) + __shfl_xor_sync(FULL, h ? t_x : t_dy, 16);
+                        r4[2] = (h ? t_dz : t_y) + __shfl_xor_sync(FULL, h ? t_y : t_dz, 16);
+                        r4[3] = (h ? t_df : t_z) + __shfl_xor_sync(FULL, h ? t_z : t_df, 16);
+                        const bool g = lane & 8;
+                        r2[0] = (g ? r4[2] : r4[0]) + __shfl_xor_sync(FULL, g ? r4[0] : r4[2], 8);
+                        r2[1] = (g ? r4[3] : r4[1]) + __shfl_xor_sync(FULL, g ? r4[1] : r4[3], 8);
+                        const bool f = lane & 4;
+                        r1 = (f ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, f ? r2[0] : r2[1], 4);
+                        r1 += __shfl_xor_sync(FULL, r1, 2);
+                        r1 += __shfl_xor_sync(FULL, r1, 1);
                     }
-                    if (lane == il) { s_nd += t_nd; s_x += t_x; s_y += t_y; s_z += t_z; s_dx += t_dx; s_dy += t_dy; s_dz += t_dz; s_df += t_df; }
+                    if ((lane & 3) == 0) {
+                        // component held by this lane: bit 4 -> sums2 (else sums), bit 3 -> +2, bit 2 -> +1   (nd, x, y, z | dx, dy, dz, df)
+                        float *dst = reinterpret_cast<float *>((lane & 16) ? a.sums2 + i : a.sums + i) + ((lane >> 2) & 3);
+                        *dst = t0 == 0 ? r1 : *dst + r1;
+                    }
                     __syncwarp();
                 }
-            }
-            if (lane < gcount) {
-                a.sums[hs + ig + lane] = make_float4(s_nd, s_x, s_y, s_z);
-                a.sums2[hs + ig + lane] = make_float4(s_dx, s_dy, s_dz, s_df);
             }
         }
         __syncwarp();
@@ -404,7 +413,7 @@ cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, c
     a.mixA = c->mixA;
     a.mixB = c->mixB;
     int64_t blocks = (n + UP_WARPS - 1) / UP_WARPS;
-    int64_t maxb = (int64_t)c->sm_count * 4;
+    int64_t maxb = (int64_t)c->sm_count * 5;           // 5 x 45 KB of shared memory per SM
     if (blocks > maxb) blocks = maxb;
     cudaError_t e;
     if (c->mixed) {
