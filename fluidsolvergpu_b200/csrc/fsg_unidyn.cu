@@ -90,10 +90,16 @@ k_pair_unidyn(UniArgs a)
                     const int lo = max(ex, t0), hi = min(ex + pt, t1);
                     for (int k = lo + lane; k < hi; k += 32) {
                         const int j = stt + (k - ex);
-                        S.sp[k - t0] = a.A.posd[j];
+                        // (asynchronous 16-byte copies: the loop does not wait for one bin's particles before it asks for the next bin's)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&S.sp[k - t0])),
+                                     "l"(a.A.posd + j) : "memory");
                         S.sj[k - t0] = j;
                     }
                 }
+                // octants of this group's home particles (cu:182-184), one per lane instead of one warp-wide evaluation per particle
+                int my_oct = 0;
+                if (split && lane < gcount) { const float4 ph = a.A.posd[hs + ig + lane]; my_oct = uni_subindex(d, ph.x, ph.y, ph.z); }
+                asm volatile("cp.async.wait_all;" ::: "memory");
                 __syncwarp();
                 // the home particle of the NEXT iteration is requested while this one is being processed
                 float4 n_pi = a.A.posd[hs + ig], n_vi = a.A.velp[hs + ig], n_mi = a.A.mix[hs + ig];
@@ -110,7 +116,7 @@ k_pair_unidyn(UniArgs a)
                     int nr = 1, zlo = 0;
                     int ax = 0, ay = 0;
                     if (split) {
-                        const int oct = uni_subindex(d, pi.x, pi.y, pi.z);            // cu:182-184, neighbourhood cu:579-583
+                        const int oct = __shfl_sync(FULL, my_oct, il);                // cu:182-184, neighbourhood cu:579-583
                         ax = (oct & 1) ? 1 : -1; ay = (oct & 2) ? 1 : -1;
                         zlo = (oct & 4) ? 0 : 1;                                       // z offsets {-1, 0} (tags +0, +1) or {0, +1} (tags +1, +2)
                         nr = 4;
