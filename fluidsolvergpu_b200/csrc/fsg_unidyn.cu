@@ -110,7 +110,7 @@ k_pair_unidyn(UniArgs a)
                     if (il + 1 < gcount) { n_pi = a.A.posd[i + 1]; n_vi = a.A.velp[i + 1]; n_mi = a.A.mix[i + 1]; }
                     const float densi = fabsf(pi.w);
                     const bool bi = pi.w < 0.f;
-                    const float pod2i = vi.w / (densi * densi);
+                    const float pod2i = __fdividef(vi.w, densi * densi);
                     const float solid_i = mi.x, fluid_i = mi.y;
                     // candidate ranges this particle sees: [0, C) or, in a split bin, 4 columns x 2 z-adjacent bins of its octant
                     int nr = 1, zlo = 0;
@@ -161,7 +161,7 @@ k_pair_unidyn(UniArgs a)
                         const float ds = sqrtf(dist2(rx, ry, rz));
                         const float densj = fabsf(pj.w);
                         const bool bj = pj.w < 0.f;
-                        vj.w = vj.w / (densj * densj);                                  // press / powf(dens, 2), cu:310
+                        vj.w = __fdividef(vj.w, densj * densj);                         // press / powf(dens, 2), cu:310 (approximate reciprocals: <= 2 ulp, the parity bar is 1e-5)
                         // W(ds), FluidGPU-unidyn.cu:11-21
                         float w;
                         const float qq = ds * d.inv_h;
@@ -171,24 +171,24 @@ k_pair_unidyn(UniArgs a)
                         t_nd += w * ((!bi && bj) ? 2.5f : 1.f);                         // cu:362 (mass == 1)
                         if (ds <= d.h_lt) {                                             // support of dW, cu:35-43
                             const float tt = d.hf - ds;
-                            const float g = d.dw_c * tt * tt / ds;
+                            const float g = __fdividef(d.dw_c * tt * tt, ds);
                             const float dkx = g * rx, dky = g * ry, dkz = g * rz;       // cu:296-298
                             const float vabx = vi.x - vj.x, vaby = vi.y - vj.y, vabz = vi.z - vj.z;
                             const float dd = vabx * rx + vaby * ry + vabz * rz;         // cu:304
                             float s = 0.f;
                             if (dd < 0.f) {                                             // cu:307
-                                const float mu = dd / (ds * ds + d.eps);
+                                const float mu = __fdividef(dd, ds * ds + d.eps);
                                 const float hm = d.hf * mu;
                                 const float bf = (!bi && bj) ? 1.f + (1.f + 3.f * fluid_i * fluid_i) * alpha_sb : 1.f;
-                                s = ((solid_i * 9.f + 1.f) * (float)d.alpha_fluid) * (float)d.sound * (hm + d.visc_q * hm * hm) /
-                                    ((densi + densj) * 0.5f) * bf;
+                                s = __fdividef(((solid_i * 9.f + 1.f) * (float)d.alpha_fluid) * (float)d.sound * (hm + d.visc_q * hm * hm),
+                                               (densi + densj) * 0.5f) * bf;
                             }
                             const float pp = vj.w + pod2i + s;                          // cu:310-312
                             t_x += pp * dkx;
                             t_y += pp * dky;
                             t_z += pp * dkz;
                             if (!bi && !bj) {
-                                const float inv = 1.f / densj;
+                                const float inv = __fdividef(1.f, densj);
                                 t_dx += inv * dkx;                                      // cu:364-366
                                 t_dy += inv * dky;
                                 t_dz += inv * dkz;
