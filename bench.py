@@ -37,9 +37,13 @@ sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 
 ALG_BYTES_STEP = 272      # algorithmic HBM bytes per particle-step (reorder 136 + tables 4 + pair/update 132)
-ALG_BYTES_PAIR = 132      # the fused pair-sum/EOS/integrate/re-bin kernel: read 64 + write 64 + new key 4
+ALG_BYTES_PAIR = 132      # pair sums + EOS/integrate/re-bin as ONE phase (survey's figure): read 64 + write 64 + new key 4
+# With the deferred update (single device and the sorted-ghost slab pipeline) the pair phase is the pair sums alone — it reads the
+# read state (posd, velp: 32 B) and writes the four sums (16 B) — and Particle::update runs inside the next step's reorder:
+ALG_BYTES_PAIR_DEFERRED = 48
+ALG_BYTES_STREAM_DEFERRED = 188   # key sort (8 + 8 + 16) + reorder with update (8 keys/perm, 64 + 16 in, 64 + 4 out)
 # measured DRAM bytes per particle of the pair kernel (ncu --set full at 256^3): [symmetric k_pair_v3, gather k_pair_v2]
-NCU_PAIR_DRAM_BYTES_PER_PARTICLE = [(62.6, "profiles/r1_ncu_pair_v3.txt"), (47.2, "profiles/r1_ncu_pair_v2_final.txt")]
+NCU_PAIR_DRAM_BYTES_PER_PARTICLE = [(62.5, "profiles/r2_ncu_pair_v3.txt"), (47.2, "profiles/r1_ncu_pair_v2_final.txt")]
 FLOP_IN_RANGE, FLOP_REJECTED = 50, 12   # SURVEY.md §8d algorithmic flop per in-range / rejected candidate
 SPACING, JITTER, SEED = 0.05, 0.005, 20261018
 CPU_SAMPLE_GRID = 128     # bounded sample for the CPU legs: the same plume at 128^3 bins (1.07 M particles)
@@ -498,17 +502,22 @@ def fsg_arm(args):
 
     # ---- roofline of the dominant kernel ----
     pair_ms = phase["pair_update"] / max(1, phase["steps"])
-    achieved = ALG_BYTES_PAIR * n_local / (pair_ms * 1e-3) / 1e9
+    # the update is deferred into the next reorder on a single device and on the sorted-ghost slab pipeline: the pair phase is the pair sums alone
+    deferred = os.environ.get("FSG_DEFER_UPDATE", "1") != "0" and (world == 1 or solver.mode == 2)
+    alg_pair = ALG_BYTES_PAIR_DEFERRED if deferred else ALG_BYTES_PAIR
+    achieved = alg_pair * n_local / (pair_ms * 1e-3) / 1e9
     symmetric = args.pair_mode == 0 and not (world > 1 and args.exchange == "peer" and args.overlap)
     kname = "k_pair_v3 (symmetric pair sums)" if symmetric else "k_pair_v2 (gather pair sums)"
     ncu_b = NCU_PAIR_DRAM_BYTES_PER_PARTICLE[0 if symmetric else 1]
-    roofline = {"bound": "hbm", "kernel": kname + " + k_update (EOS/integrate/re-bin)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": kname + ("; Particle::update is deferred into the next step's k_reorder" if deferred else
+                                                   " + k_update (EOS/integrate/re-bin)"), "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": ncu_b[0] * n_local + 152.0 * n_local, "peak_source": peak_src,
+                "traffic": ncu_b[0] * n_local + (0.0 if deferred else 152.0 * n_local), "peak_source": peak_src,
                 "traffic_note": f"pair kernel: dram__bytes_read+write = {ncu_b[0]} B/particle under ncu --set full at 256^3 ({ncu_b[1]}), "
-                                "scaled by the particle count; k_update: its 152 B/particle of streaming reads + writes",
+                                "scaled by the particle count" + ("" if deferred else "; k_update: its 152 B/particle of streaming reads + writes"),
                 "kernel_ms": pair_ms, "share_of_step": pair_ms / ms_step,
-                "algorithmic_bytes_per_launch": ALG_BYTES_PAIR * n_local,
+                "algorithmic_bytes_per_launch": alg_pair * n_local,
+                "algorithmic_bytes_per_particle": alg_pair,
                 "note": "this kernel is CUDA-core (FP32 issue) bound, not HBM bound: see roofline_fp32; the HBM-bound phases are in `phases`"}
     extra = {}
     if st is not None:
@@ -523,9 +532,12 @@ def fsg_arm(args):
     phases = {k: phase[k] / max(1, phase["steps"]) for k in ("sort", "reorder", "pair_update", "other")}
     stream_ms = phases["sort"] + phases["reorder"]
     extra["phases_ms"] = phases
-    extra["streaming_phases"] = {"what": "key sort + reorder/bin tables (HBM-bound)", "algorithmic_GBps": (ALG_BYTES_STEP - ALG_BYTES_PAIR) * n_local / (stream_ms * 1e-3) / 1e9,
-                                 "frac_of_hbm_peak": (ALG_BYTES_STEP - ALG_BYTES_PAIR) * n_local / (stream_ms * 1e-3) / 1e9 / hbm_peak}
-    extra["step_hbm"] = {"algorithmic_GBps": ALG_BYTES_STEP * n_local / (ms_step * 1e-3) / 1e9,
+    alg_stream = ALG_BYTES_STREAM_DEFERRED if deferred else ALG_BYTES_STEP - ALG_BYTES_PAIR
+    extra["streaming_phases"] = {"what": "key sort + reorder/bin tables" + (" + the previous step's Particle::update" if deferred else "") + " (HBM-bound)",
+                                 "algorithmic_bytes_per_particle": alg_stream,
+                                 "algorithmic_GBps": alg_stream * n_local / (stream_ms * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": alg_stream * n_local / (stream_ms * 1e-3) / 1e9 / hbm_peak}
+    extra["step_hbm"] = {"algorithmic_bytes_per_particle": ALG_BYTES_STEP, "algorithmic_GBps": ALG_BYTES_STEP * n_local / (ms_step * 1e-3) / 1e9,
                          "frac_of_hbm_peak": ALG_BYTES_STEP * n_local / (ms_step * 1e-3) / 1e9 / hbm_peak}
 
     # ---- end to end through the C ABI with host buffers ----
