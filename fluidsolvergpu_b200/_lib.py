@@ -22,7 +22,8 @@ class FsgConfig(C.Structure):
         ("alpha_boundary", C.c_double), ("neighbour_cap", C.c_int32), ("bin_cap", C.c_int32), ("capacity", C.c_int64),
         ("device", C.c_int32), ("pair_fp64", C.c_int32), ("collect_stats", C.c_int32), ("rank", C.c_int32),
         ("world", C.c_int32), ("slab_x0", C.c_int32), ("slab_x1", C.c_int32),
-        ("pair_mode", C.c_int32), ("unidyn_open_box", C.c_int32), ("reserved", C.c_int32 * 1),
+        ("pair_mode", C.c_int32), ("unidyn_open_box", C.c_int32), ("unidyn_adapt", C.c_int32),
+        ("unidyn_merge_distance", C.c_double), ("unidyn_split_mass_min", C.c_double),
     ]
 
 
@@ -31,7 +32,7 @@ class FsgSoa(C.Structure):
         ("n", C.c_int64), ("pos", C.c_void_p), ("vel", C.c_void_p), ("acc", C.c_void_p), ("dens", C.c_void_p),
         ("press", C.c_void_p), ("delpress", C.c_void_p), ("newdens", C.c_void_p), ("newdelpress", C.c_void_p),
         ("index", C.c_void_p), ("cell", C.c_void_p), ("boundary", C.c_void_p), ("solid", C.c_void_p), ("fluid", C.c_void_p),
-        ("stress_tensor", C.c_void_p), ("stress_rate", C.c_void_p),
+        ("stress_tensor", C.c_void_p), ("stress_rate", C.c_void_p), ("mass", C.c_void_p),
     ]
 
 
@@ -73,6 +74,7 @@ SIGNATURES = {
     "fsg_write_frame": (C.c_int, [P, C.c_char_p, C.c_int]),
     "fsg_write_frame_async": (C.c_int, [P, C.c_char_p, C.c_int]),
     "fsg_frame_wait": (C.c_int, [P, C.POINTER(C.c_int64)]),
+    "fsg_unidyn_adapt_counts": (C.c_int, [P, C.POINTER(C.c_int64 * 3), C.POINTER(C.c_int64 * 3)]),
     "fsg_slab_pack": (C.c_int, [P, P, P, C.c_int64, C.c_int64]),
     "fsg_slab_unpack": (C.c_int, [P, P, P, C.c_int64, C.c_int64]),
     "fsg_slab_check": (C.c_int, [P, C.POINTER(C.c_int64 * 9)]),

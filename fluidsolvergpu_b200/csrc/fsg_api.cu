@@ -133,6 +133,8 @@ extern "C" int fsg_config_default(fsg_config *cfg, int model)
         cfg->neighbour_cap = 1024;
         cfg->bin_cap = 0;
         cfg->capacity = 14040;
+        cfg->unidyn_merge_distance = -10.0;   // FluidGPU-unidyn.cu:261
+        cfg->unidyn_split_mass_min = 3.0;     // :278
     } else
         return FSG_E_INVALID;
     return FSG_OK;
@@ -159,6 +161,7 @@ extern "C" int fsg_destroy(fsg_ctx *c)
     cudaFree(c->binlist[0]); cudaFree(c->binlist[1]);
     cudaFree(c->counters); cudaFree(c->dstats); cudaFree(c->sort_tmp);
     cudaFree(c->keysC); cudaFree(c->ns_ws);
+    cudaFree(c->adapt_ws); cudaFree(c->adapt_scan);
     cudaFree(c->slab_cnt); cudaFree(c->scan_tmp);
     if (c->comm) cudaStreamSynchronize(c->comm);
     for (int k = 0; k < 4; k++) if (c->peer_inbox[k] && !c->peer_local) cudaIpcCloseMemHandle(c->peer_inbox[k]);
@@ -265,6 +268,10 @@ extern "C" int fsg_create(const fsg_config *cfg, fsg_ctx **out)
                        "and a one-layer ghost band, i.e. cellsize >= 2h";
         return FSG_E_UNSUPPORTED;
     }
+    if (cfg->unidyn_adapt && (cfg->model != FSG_MODEL_UNIDYN || cfg->world > 1)) {
+        g_create_err = "fsg_create: unidyn_adapt (particle merging / splitting) needs the unidyn model on a single-device context";
+        return FSG_E_UNSUPPORTED;
+    }
     int ndev = fsg_device_count();
     if (ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
         g_create_err = "fsg_create: no usable CUDA device (libfsg has no CPU path)";
@@ -361,15 +368,19 @@ static int after_upload(fsg_ctx *c, int64_t n, const int *slot_state = nullptr)
     if (c->cfg.model == FSG_MODEL_UNIDYN && flag[4]) {
         // bit 1: a particle with mass != 1 (merged / split particles are outside the built scope); bit 2: a non-boundary particle
         // with solid != 0 — a mixed-phase / granular scene: the two-pass kernels of fsg_unidyn_mixed.cu, single-device contexts
-        if ((flag[4] & 1) || c->cfg.world > 1) {
+        const bool bad_mass = (flag[4] & 1) && !c->cfg.unidyn_adapt, mixed_scene = (flag[4] & 2) != 0;
+        if (bad_mass || (mixed_scene && (c->cfg.world > 1 || c->cfg.unidyn_adapt))) {
             c->n = 0;
-            c->err = (flag[4] & 1) ? "upload: the unidyn path needs mass == 1 for every particle (solver-unidyn.cu:127-184)"
+            c->err = bad_mass ? "upload: the unidyn path needs mass == 1 for every particle unless fsg_config.unidyn_adapt is set (solver-unidyn.cu:127-184)"
+                     : c->cfg.unidyn_adapt ? "upload: particle merging / splitting (unidyn_adapt) runs on pure-fluid scenes only"
                                    : "upload: mixed-phase / granular unidyn scenes (a non-boundary particle with solid != 0) run on single-device "
                                      "contexts only (the slab messages do not carry the granular stress state)";
             return FSG_E_UNSUPPORTED;
         }
-        c->mixed = true;
+        c->mixed = mixed_scene;
     }
+    c->adapt_next_index = (int)n;             // children continue the numbering 0 .. n-1 of the uploaded particles
+    for (int k = 0; k < 3; k++) c->adapt_counts[k] = c->adapt_totals[k] = 0;
     c->carry_live = true;
     c->steps = 0;
     return FSG_OK;
@@ -440,7 +451,7 @@ extern "C" int fsg_download_aos(fsg_ctx *c, void *particles, int64_t n)
 __global__ void k_pack_soa(int64_t n, const float *pos, const float *vel, const float *acc, const float *dens,
                            const float *press, const float *delp, const float *nd, const float *ndp, const int *index,
                            const unsigned char *bnd, const float *solid, const float *fluid, const float *stress_tensor, const float *stress_rate,
-                           float gravity, FsgState st, float4 *carry, int *bad)
+                           const float *mass, float gravity, FsgState st, float4 *carry, int *bad)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -455,7 +466,9 @@ __global__ void k_pack_soa(int64_t n, const float *pos, const float *vel, const 
     carry[i] = make_float4(nd ? nd[i] : 9550.f, ndp ? ndp[3 * i] : 0.f, ndp ? ndp[3 * i + 1] : 0.f, ndp ? ndp[3 * i + 2] : 0.f);
     if (st.mix) {      // unidyn: solid / fluid default to 0/1 for fluid, 1/0 for boundary particles (solver-unidyn.cu:129-143)
         float so = solid ? solid[i] : (b ? 1.f : 0.f), fl = fluid ? fluid[i] : (b ? 0.f : 1.f);
-        st.mix[i] = make_float4(so, fl, 0.f, 0.f);
+        const float ms = mass ? mass[i] : 1.f;
+        st.mix[i] = make_float4(so, fl, ms - 1.f, 0.f);                                   // z = mass - 1 (fsg_unidyn_adapt.cu)
+        if (ms != 1.f) atomicOr(bad, 1);              // merged / split particles: fsg_config.unidyn_adapt
         if (!b && so != 0.f) atomicOr(bad, 2);        // a mixed-phase / granular scene
     }
     if (st.stress) {
@@ -468,7 +481,7 @@ __global__ void k_pack_soa(int64_t n, const float *pos, const float *vel, const 
 
 __global__ void k_unpack_soa(int64_t n, FsgState st, const float4 *carry, const int *keys, float *pos, float *vel, float *acc,
                              float *dens, float *press, float *delp, float *nd, float *ndp, int *index, int *cell,
-                             unsigned char *bnd, float *solid, float *fluid, float *stress_tensor, float *stress_rate)
+                             unsigned char *bnd, float *solid, float *fluid, float *stress_tensor, float *stress_rate, float *mass)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -485,10 +498,11 @@ __global__ void k_unpack_soa(int64_t n, FsgState st, const float4 *carry, const 
     if (index) index[i] = __float_as_int(dp.w);
     if (cell) cell[i] = keys[i];
     if (bnd) bnd[i] = pd.w < 0.f ? 1 : 0;
-    if (st.mix && (solid || fluid)) {
+    if (st.mix && (solid || fluid || mass)) {
         float4 mx = st.mix[i];
         if (solid) solid[i] = mx.x;
         if (fluid) fluid[i] = mx.y;
+        if (mass) mass[i] = 1.f + mx.z;
     }
     for (int k = 0; k < 9; k++) {
         if (stress_tensor) stress_tensor[9 * i + k] = st.stress ? st.stress[i * 18 + k] : 0.f;
@@ -500,7 +514,7 @@ struct SoaStage {
     float *pos, *vel, *acc, *dens, *press, *delp, *nd, *ndp;
     int *index, *cell;
     unsigned char *bnd;
-    float *solid, *fluid, *stress_tensor, *stress_rate;
+    float *solid, *fluid, *stress_tensor, *stress_rate, *mass;
 };
 static size_t soa_stage_layout(char *base, int64_t n, const fsg_soa *h, SoaStage &s)
 {
@@ -526,6 +540,7 @@ static size_t soa_stage_layout(char *base, int64_t n, const fsg_soa *h, SoaStage
     s.fluid = (float *)take(h->fluid, 4 * n);
     s.stress_tensor = (float *)take(h->stress_tensor, 36 * n);
     s.stress_rate = (float *)take(h->stress_rate, 36 * n);
+    s.mass = (float *)take(h->mass, 4 * n);
     return o + 256;
 }
 
@@ -550,12 +565,13 @@ extern "C" int fsg_upload_soa(fsg_ctx *c, const fsg_soa *h)
     H2D(s.ndp, h->newdelpress, 12 * n); H2D(s.index, h->index, 4 * n); H2D(s.bnd, h->boundary, n);
     H2D(s.solid, h->solid, 4 * n); H2D(s.fluid, h->fluid, 4 * n);
     H2D(s.stress_tensor, h->stress_tensor, 36 * n); H2D(s.stress_rate, h->stress_rate, 36 * n);
+    H2D(s.mass, h->mass, 4 * n);
     if (hh.cell) CU(c, cudaMemcpyAsync(s.cell, h->cell, (size_t)(4 * n), cudaMemcpyHostToDevice, c->stream));
 #undef H2D
     if (n > 0) {
         k_pack_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, s.pos, s.vel, s.acc, s.dens, s.press, s.delp, s.nd,
                                                                        s.ndp, s.index, s.bnd, s.solid, s.fluid, s.stress_tensor, s.stress_rate,
-                                                                       (float)c->cfg.gravity, c->B, c->carryB, c->counters + 8);
+                                                                       c->B.mix ? s.mass : nullptr, (float)c->cfg.gravity, c->B, c->carryB, c->counters + 8);
         CU(c, cudaGetLastError());
         c->launches++;
     }
@@ -577,7 +593,8 @@ extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
     if (n > 0) {
         k_unpack_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->B, c->carry_live ? c->carryB : nullptr, c->keysB,
                                                                          s.pos, s.vel, s.acc, s.dens, s.press, s.delp, s.nd,
-                                                                         s.ndp, s.index, s.cell, s.bnd, s.solid, s.fluid, s.stress_tensor, s.stress_rate);
+                                                                         s.ndp, s.index, s.cell, s.bnd, s.solid, s.fluid, s.stress_tensor, s.stress_rate,
+                                                                         c->B.mix ? s.mass : nullptr);
         CU(c, cudaGetLastError());
         c->launches++;
     }
@@ -585,7 +602,7 @@ extern "C" int fsg_download_soa(fsg_ctx *c, fsg_soa *h)
     D2H(h->pos, s.pos, 12 * n); D2H(h->vel, s.vel, 12 * n); D2H(h->acc, s.acc, 12 * n); D2H(h->dens, s.dens, 4 * n);
     D2H(h->press, s.press, 4 * n); D2H(h->delpress, s.delp, 12 * n); D2H(h->newdens, s.nd, 4 * n);
     D2H(h->newdelpress, s.ndp, 12 * n); D2H(h->index, s.index, 4 * n); D2H(h->cell, s.cell, 4 * n); D2H(h->boundary, s.bnd, n);
-    if (c->B.mix) { D2H(h->solid, s.solid, 4 * n); D2H(h->fluid, s.fluid, 4 * n); }
+    if (c->B.mix) { D2H(h->solid, s.solid, 4 * n); D2H(h->fluid, s.fluid, 4 * n); D2H(h->mass, s.mass, 4 * n); }
     D2H(h->stress_tensor, s.stress_tensor, 36 * n); D2H(h->stress_rate, s.stress_rate, 36 * n);
 #undef D2H
     int order_bad = 0;
@@ -722,6 +739,10 @@ static int step_second_half(fsg_ctx *c, int64_t n, int nxt, bool prof)
         CU(c, fsg_launch_pair_update(c, n, c->binlist[nxt], c->counters + nxt, c->counters + 2,
                                      c->carry_live ? c->carryA : nullptr, &l, c->stream));
     c->launches += l;
+    if (c->cfg.model == FSG_MODEL_UNIDYN && c->cfg.unidyn_adapt && !c->mixed) {      // children of the split particles (fsg_unidyn_adapt.cu)
+        int rc = fsg_unidyn_adapt_post(c, n);
+        if (rc != FSG_OK) return rc;
+    }
     if (prof) prof_mark(c);
     c->carry_live = false;
     c->slab2_mid = false;
@@ -844,7 +865,8 @@ extern "C" int fsg_export_viz(fsg_ctx *c, float *spts, float *a3, float *b3)
     CU(c, fsg_launch_export_viz(n, c->A.posd, c->keysA, ds, da, db, c->stream));
     c->launches++;
     if (c->cfg.model == FSG_MODEL_UNIDYN) {        // a3 = mass, b3 = |diffusion|^2 (FluidGPU-unidyn.cu:465-466)
-        CU(c, fsg_launch_fill((int *)da, 0x3f800000, n, c->stream));
+        if (c->cfg.unidyn_adapt) CU(c, fsg_launch_export_mass(n, c->A.mix, da, c->stream));
+        else CU(c, fsg_launch_fill((int *)da, 0x3f800000, n, c->stream));
         CU(c, cudaMemcpyAsync(db, c->vizb, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
         c->launches++;
     }

@@ -366,7 +366,7 @@ extern "C" int fsg_write_frame_async(fsg_ctx *c, const char *filename, int use_b
     cudaError_t e = fsg_launch_export_viz(n, c->A.posd, c->keysA, ds, da, db, c->stream);       // mykernel2's export, FluidGPU.cu:410-414
     c->launches++;
     if (e == cudaSuccess && c->cfg.model == FSG_MODEL_UNIDYN) {                                   // a3 = mass, b3 = |diffusion|^2 (FluidGPU-unidyn.cu:465-466)
-        e = fsg_launch_fill((int *)da, 0x3f800000, n, c->stream);
+        e = c->cfg.unidyn_adapt ? fsg_launch_export_mass(n, c->A.mix, da, c->stream) : fsg_launch_fill((int *)da, 0x3f800000, n, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(db, c->vizb, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream);
         c->launches++;
     }

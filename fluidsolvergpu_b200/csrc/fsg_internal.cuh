@@ -137,6 +137,12 @@ struct fsg_ctx {
     int ns_mode;        // -1 not decided yet, 0 off, 1 on (FSG_SORT_MERGE)
     bool keys_prev_valid;   // keysA holds the sorted keys of the step that produced B / keysB (same slot order)
     int64_t ns_used;
+    // unidyn particle merging / splitting (fsg_unidyn_adapt.cu)
+    int *adapt_ws;          // nn | split flags | their scan: three int arrays of `cap`, then 4 counters
+    void *adapt_scan;
+    size_t adapt_scan_bytes;
+    int adapt_next_index;   // Particle::index of the next child
+    int64_t adapt_counts[3], adapt_totals[3];
     FsgFrameWriter *frame_writer;   // created by the first fsg_write_frame_async
     void *stage;        // device staging area for host<->device conversion
     size_t stage_bytes;
@@ -202,8 +208,12 @@ cudaError_t fsg_launch_plume(const FsgDev &d, double spacing, double jitter, uin
                              FsgState st, float4 *carry, int64_t capacity, unsigned long long *count, cudaStream_t s);
 
 // fsg_unidyn.cu
-cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work, const float4 *carry,
+cudaError_t fsg_launch_unidyn(fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work, const float4 *carry,
                               int *launches, cudaStream_t s);
+// fsg_unidyn_adapt.cu
+cudaError_t fsg_unidyn_adapt_pre(fsg_ctx *c, int64_t n, cudaStream_t s);     // merge + split marks, between the pair sums and the update
+int fsg_unidyn_adapt_post(fsg_ctx *c, int64_t n);                            // children appended; c->n grows (one read-back)
+cudaError_t fsg_launch_export_mass(int64_t n, const float4 *mix, float *a3, cudaStream_t s);
 cudaError_t fsg_launch_split_table(const fsg_ctx *c, int *split, cudaStream_t s);
 cudaError_t fsg_launch_unpack_aos_unidyn(const unsigned char *aos, int64_t n, FsgState st, float4 *carry, int *bad, cudaStream_t s);
 cudaError_t fsg_launch_pack_aos_unidyn(unsigned char *aos, int64_t n, FsgState st, const float4 *carry, const int *keys, const FsgDev &d,

@@ -111,7 +111,7 @@ k_pair_unidyn(UniArgs a)
                     const float densi = fabsf(pi.w);
                     const bool bi = pi.w < 0.f;
                     const float pod2i = __fdividef(vi.w, densi * densi);
-                    const float solid_i = mi.x, fluid_i = mi.y;
+                    const float solid_i = mi.x, fluid_i = mi.y, mass_i = 1.f + mi.z;
                     // candidate ranges this particle sees: [0, C) or, in a split bin, 4 columns x 2 z-adjacent bins of its octant
                     int nr = 1, zlo = 0;
                     int ax = 0, ay = 0;
@@ -156,7 +156,8 @@ k_pair_unidyn(UniArgs a)
                         const int j = S.sj[c];
                         const float4 pj = S.sp[c];
                         float4 vj = a.A.velp[j];
-                        const float fluid_j = a.A.mix[j].y;
+                        const float4 mjx = a.A.mix[j];
+                        const float fluid_j = mjx.y, mass_j = 1.f + mjx.z;             // Particle::mass of the candidate, cu:358-366
                         const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
                         const float ds = sqrtf(dist2(rx, ry, rz));
                         const float densj = fabsf(pj.w);
@@ -168,7 +169,7 @@ k_pair_unidyn(UniArgs a)
                         if (ds <= d.h_le) w = d.w_c * (1.f - 1.5f * qq * qq + 0.75f * qq * qq * qq);
                         else if (ds <= d.twoh_lt) { float tt = 2.f - qq; w = d.w_c * 0.25f * tt * tt * tt; }
                         else w = 0.f;
-                        t_nd += w * ((!bi && bj) ? 2.5f : 1.f);                         // cu:362 (mass == 1)
+                        t_nd += w * ((!bi && bj) ? 2.5f : 1.f) * mass_j;                // cu:362
                         if (ds <= d.h_lt) {                                             // support of dW, cu:35-43
                             const float tt = d.hf - ds;
                             const float g = __fdividef(d.dw_c * tt * tt, ds);
@@ -180,18 +181,19 @@ k_pair_unidyn(UniArgs a)
                                 const float mu = __fdividef(dd, ds * ds + d.eps);
                                 const float hm = d.hf * mu;
                                 const float bf = (!bi && bj) ? 1.f + (1.f + 3.f * fluid_i * fluid_i) * alpha_sb : 1.f;
-                                s = __fdividef(((solid_i * 9.f + 1.f) * (float)d.alpha_fluid) * (float)d.sound * (hm + d.visc_q * hm * hm),
+                                // (cu:307 multiplies the linear term by `SPptr[i].mass` with the raw loop index: the home particle's mass is meant)
+                                s = __fdividef(((solid_i * 9.f + 1.f) * (float)d.alpha_fluid) * (float)d.sound * (mass_i * hm + d.visc_q * hm * hm),
                                                (densi + densj) * 0.5f) * bf;
                             }
                             const float pp = vj.w + pod2i + s;                          // cu:310-312
-                            t_x += pp * dkx;
-                            t_y += pp * dky;
-                            t_z += pp * dkz;
+                            t_x += pp * dkx * mass_j;                                   // cu:358-360
+                            t_y += pp * dky * mass_j;
+                            t_z += pp * dkz * mass_j;
                             if (!bi && !bj) {
                                 const float inv = __fdividef(1.f, densj);
-                                t_dx += inv * dkx;                                      // cu:364-366
-                                t_dy += inv * dky;
-                                t_dz += inv * dkz;
+                                t_dx += inv * mass_j * dkx;                             // cu:364-366
+                                t_dy += inv * mass_j * dky;
+                                t_dz += inv * mass_j * dkz;
                                 t_df += -0.5f * inv * (fluid_i + fluid_j) * (dkx * vabx + dky * vaby + dkz * vabz);   // cu:401
                             }
                         }
@@ -395,7 +397,7 @@ __global__ void k_split_table(int numcells, const int *__restrict__ start, const
     split[c] = (s0 >= 0 && end[c] - s0 + 1 > 6) ? c : -1;
 }
 
-cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work, const float4 *carry,
+cudaError_t fsg_launch_unidyn(fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work, const float4 *carry,
                               int *launches, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
@@ -437,6 +439,8 @@ cudaError_t fsg_launch_unidyn(const fsg_ctx *c, int64_t n, const int *binlist, c
         else k_pair_unidyn<false><<<(unsigned)blocks, UP_WARPS * 32, UP_SMEM, s>>>(a);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+        // particle merging / splitting (fsg_unidyn_adapt.cu): on the sorted state, between the pair sums and the update
+        if (c->cfg.unidyn_adapt) { e = fsg_unidyn_adapt_pre(c, n, s); if (e != cudaSuccess) return e; }
     }
     k_update_unidyn<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->dev, (int)n, c->keysA, c->A, c->B, c->keysB, c->sums, c->sums2, carry,
                                                               c->vizb, c->cfg.world > 1 ? c->counters + 6 : nullptr,
@@ -476,7 +480,7 @@ __global__ void k_unpack_aos_unidyn(const unsigned char *__restrict__ aos, int64
     st.velp[i] = make_float4(uldf(r, VEL), uldf(r, VEL + 4), uldf(r, VEL + 8), uldf(r, PRESS));
     st.accf[i] = make_float4(uldf(r, ACC), uldf(r, ACC + 4), uldf(r, ACC + 8), __int_as_float(bnd ? 1 : 0));
     st.dpi[i] = make_float4(uldf(r, DELP_X), uldf(r, DELP_Y), uldf(r, DELP_Z), __int_as_float(*reinterpret_cast<const int *>(r + INDEX)));
-    st.mix[i] = make_float4(solid, uldf(r, FLUID), 0.f, 0.f);
+    st.mix[i] = make_float4(solid, uldf(r, FLUID), uldf(r, MASS) - 1.f, 0.f);          // z = mass - 1 (fsg_unidyn_adapt.cu)
     carry[i] = make_float4(uldf(r, NEWDENS), uldf(r, NDELP_X), uldf(r, NDELP_Y), uldf(r, NDELP_Z));
     if (st.stress) {
         for (int k = 0; k < 9; k++) {
@@ -502,7 +506,7 @@ __global__ void k_pack_aos_unidyn(unsigned char *__restrict__ aos, int64_t n, Fs
     *reinterpret_cast<int *>(r + INDEX) = __float_as_int(dpi.w);
     *reinterpret_cast<int *>(r + CELL) = keys[i];
     *reinterpret_cast<int *>(r + SUBINDEX) = uni_subindex(d, pd.x, pd.y, pd.z);
-    ustf(r, MASS, 1.f);
+    ustf(r, MASS, 1.f + mx.z);
     ustf(r, DENS, fabsf(pd.w));
     ustf(r, PRESS, vp.w);
     ustf(r, DELP_X, dpi.x); ustf(r, DELP_Y, dpi.y); ustf(r, DELP_Z, dpi.z);

@@ -18,7 +18,7 @@ from ._lib import FsgConfig, FsgError, FsgSoa, FsgStats
 
 _F3 = ("pos", "vel", "acc", "delpress", "newdelpress")
 _F1 = ("dens", "press", "newdens")
-_FU = ("solid", "fluid")      # unidyn model only
+_FU = ("solid", "fluid", "mass")      # unidyn model only (mass != 1 needs fsg_config.unidyn_adapt)
 _F9 = ("stress_tensor", "stress_rate")      # unidyn, granular state [n, 9]
 
 
@@ -187,6 +187,12 @@ class FluidSolver:
         out = np.empty(self.numcells, np.int32)
         self._check(self._lib.fsg_get_split(self._ctx, out.ctypes.data), "fsg_get_split")
         return out
+
+    def adapt_counts(self) -> dict:
+        """unidyn_adapt contexts: (pairs merged, particles split, children created) of the last step and since the upload."""
+        last, total = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+        self._check(self._lib.fsg_unidyn_adapt_counts(self._ctx, C.byref(last), C.byref(total)), "fsg_unidyn_adapt_counts")
+        return {"last": tuple(int(v) for v in last), "total": tuple(int(v) for v in total)}
 
     def stats(self) -> dict:
         st = FsgStats()

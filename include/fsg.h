@@ -87,7 +87,11 @@ typedef struct fsg_config {
     int32_t unidyn_open_box; /* unidyn model.  0 (default): Particle::update keeps the reference's literal unit-box floor and walls
                                (z < -0.89, |x|,|y|,|z| > 0.98, FluidGPU-unidyn.cuh:332,404-411); 1: they are switched off, for domains
                                other than [-1,1]^3 (the reference has to be rebuilt for that: oracle/Makefile, ref_harness_unidyn_g128) */
-    int32_t reserved[1];
+    int32_t unidyn_adapt;    /* unidyn model, single-device contexts, pure-fluid scenes.  1: the particle merging / splitting blocks of
+                               FluidGPU-unidyn.cu:260-285 + solver-unidyn.cu:495-542 run every step (race-free reading); uploads may
+                               then carry mass != 1 and the particle count can grow up to `capacity`.  0 (default): mass must be 1 */
+    double  unidyn_merge_distance;  /* the literal -10.00 of FluidGPU-unidyn.cu:261 (default: never merges, like the reference) */
+    double  unidyn_split_mass_min;  /* the literal 3 of FluidGPU-unidyn.cu:278 (default: a merged particle of mass 2.75 never splits, like the reference) */
 } fsg_config;
 
 /* Host-side structure-of-arrays view used by fsg_upload_soa / fsg_download_soa: the live fields
@@ -112,6 +116,7 @@ typedef struct fsg_soa {
     /* unidyn, granular state of mixed-phase scenes (FluidGPU-unidyn.cuh stress_tensor[3][3], stress_rate[3][3]); NULL on upload: zeros */
     float  *stress_tensor; /* [n][9] row major */
     float  *stress_rate;   /* [n][9] */
+    float  *mass;          /* [n] unidyn, Particle::mass (FluidGPU-unidyn.cuh:150); NULL on upload: 1.  Anything but 1 needs unidyn_adapt */
 } fsg_soa;
 
 typedef struct fsg_ctx fsg_ctx;
@@ -277,6 +282,9 @@ FSG_API int  fsg_stage_mykernel(fsg_ctx *ctx, void *d_particles, const int32_t *
 FSG_API int  fsg_stage_mykernel2(fsg_ctx *ctx, void *d_particles, int32_t *d_cells, int32_t *d_start, int32_t *d_end,
                          int64_t n, float *spts, float *a3, float *b3);
 
+
+/* unidyn_adapt contexts: pairs merged / particles split / children created — in the last step and since the upload */
+FSG_API int  fsg_unidyn_adapt_counts(fsg_ctx *ctx, int64_t last[3], int64_t total[3]);
 
 /* unidyn model (context created with FSG_MODEL_UNIDYN): the launches of the single-device loop solver-unidyn.cu:341-548
  * on the reference's own buffers (340-byte unidyn Particle records).  Same scope as the context API: every non-boundary

@@ -99,6 +99,7 @@ typedef struct fsgo_ustate {
     /* mixed-phase / granular scenes (may be NULL for pure-fluid scenes): FluidGPU-unidyn.cuh stress_tensor[3][3], stress_rate[3][3] */
     float *stress_tensor; /* [n][9] row major */
     float *stress_rate;   /* [n][9] */
+    float *mass;          /* [n] Particle::mass (FluidGPU-unidyn.cuh:150); NULL = 1 for every particle */
 } fsgo_ustate;
 
 /* One pass of the solver-unidyn.cu:313-573 loop body on one device: sort (:331) -> count_after_merge (:341)
@@ -110,6 +111,22 @@ typedef struct fsgo_ustate {
  * Returns 0; -1 allocation failure; -2 scene outside the restated scope (see fsg_oracle_unidyn.c). */
 int fsgo_unidyn_step(const fsgo_params *p, fsgo_ustate *s, int t, int *cells_sorted, int *start, int *end, int *split,
                      float *spts, float *a3, float *b3, long long *stats);
+
+/* Particle merging / splitting made live (FluidGPU-unidyn.cu:260-285 == :680-700, host half solver-unidyn.cu:495-542).
+ * In the reference the merge test is `ds <= (-10.00) && ds > 0` (never true), a merge would set mass 2.75 while a split needs
+ * mass > 3, and the host loop that creates the second particle is commented out: with the reference's literals nothing happens.
+ * Here the two thresholds are parameters (the literals are the defaults) and the blocks get a race-free reading, see
+ * fsg_oracle_unidyn.c.  PARITY UNPINNED against the reference (it has no live behaviour to compare with); pinned oracle <-> CUDA. */
+typedef struct fsgo_adapt {
+    double merge_distance;   /* :261  literal -10.00 */
+    double split_mass_min;   /* :278  literal 3 */
+    int    capacity;         /* slots the state arrays (and mass) hold: children are appended behind s->n while there is room */
+    int    next_index;       /* Particle::index given to the next child (in/out) */
+    int    merged, split, added;   /* out: pairs merged, particles split, children created in this step */
+} fsgo_adapt;
+/* fsgo_unidyn_step with the merge / split blocks (pure-fluid scenes, s->mass required).  s->n grows by ad->added. */
+int fsgo_unidyn_step_adapt(const fsgo_params *p, fsgo_ustate *s, fsgo_adapt *ad, int t, int *cells_sorted, int *start, int *end, int *split,
+                           float *spts, float *a3, float *b3, long long *stats);
 
 #ifdef __cplusplus
 }

@@ -207,10 +207,12 @@ static inline void upair_body(const fsgo_params *P, const fsgo_ustate *s, int i,
         int bi = s->boundary[i] != 0, bj = s->boundary[j] != 0;
         float di = s->dens[i], dj = s->dens[j];
         float solid_i = s->solid[i], fluid_i = s->fluid[i];
-        const float mass = 1.0f;
+        /* Particle::mass of the candidate (cu:358-366); cu:307 reads `SPptr[i].mass` with the raw loop index i — the mass of whatever
+           record sits at that sorted slot number, an indexing slip: the home particle's own mass is used here */
+        const float mass = s->mass ? s->mass[j] : 1.0f, mass_i = s->mass ? s->mass[i] : 1.0f;
         /* cu:307 */
         float sv = (((solid_i * 9 + 1) * P->alpha_fluid) * P->sound *
-                    (powf(mass, 1) * cutoff * (d / (d2 + 0.01 * powf(cutoff, 2))) +
+                    (powf(mass_i, 1) * cutoff * (d / (d2 + 0.01 * powf(cutoff, 2))) +
                      50 * 1.0 / P->sound * powf(cutoff * (d / (d2 + 0.01 * powf(cutoff, 2))), 2)) /
                     ((di + dj) / 2.0)) *
                    (d < 0) * (1 + (!bi) * (bj) * ((1 + 3 * fluid_i * fluid_i) * P->alpha_boundary));
@@ -287,8 +289,125 @@ static void permute_f(float *a, const int *perm, int n, int w, float *tmp)
     memcpy(a, tmp, sizeof(float) * (size_t)n * w);
 }
 
+static int ustep(const fsgo_params *P, fsgo_ustate *s, fsgo_adapt *ad, int t, int *cells_sorted, int *start_out, int *end_out,
+                 int *split_out, float *spts, float *a3, float *b3, long long *stats);
+
 int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sorted, int *start_out, int *end_out,
                      int *split_out, float *spts, float *a3, float *b3, long long *stats)
+{
+    return ustep(P, s, NULL, t, cells_sorted, start_out, end_out, split_out, spts, a3, b3, stats);
+}
+
+int fsgo_unidyn_step_adapt(const fsgo_params *P, fsgo_ustate *s, fsgo_adapt *ad, int t, int *cells_sorted, int *start_out, int *end_out,
+                           int *split_out, float *spts, float *a3, float *b3, long long *stats)
+{
+    if (!ad || !s->mass) return -2;
+    return ustep(P, s, ad, t, cells_sorted, start_out, end_out, split_out, spts, a3, b3, stats);
+}
+
+/* ---- particle merging / splitting (FluidGPU-unidyn.cu:260-285, solver-unidyn.cu:495-542): the race-free reading ----
+ * The reference's blocks sit inside the pair loop of mykernel: thread (bin, neighbour j) walks the bin's particles ii and, for a pair
+ * closer than the merge distance, rewrites BOTH particles while every other thread of the launch is reading them — and tests
+ * `diffusion*`, which that same launch is still accumulating.  Reading implemented here (and in fsg_unidyn_adapt.cu):
+ *   1. the pair sums of the step are taken over the unmodified state;
+ *   2. merge candidates are the pairs the reference tests (:261): 0 < ds <= merge_distance, both masses in (0, 2), neither a boundary
+ *      particle, |diffusion|^2 < 20 for both — with the COMPLETED diffusion sums of this step; a particle merges with its nearest
+ *      candidate (ties: the smaller Particle::index) and only if that choice is mutual; the particle with the smaller index survives:
+ *      mass 2.75, velocity and position the pair's mean (:262-270); the other gets mass 0, boundary = true, position 90.99 (:263-271);
+ *   3. a particle with mass > split_mass_min inside the grid, not a boundary particle, with |diffusion|^2 > 35000 or dens < 9400 (:278)
+ *      gets mass 1, split = true and y += 0.015 (:279-282);
+ *   4. mykernel2 / Particle::update as always (the absorbed particle is a boundary particle far outside the grid: it is parked);
+ *   5. the host loop of solver-unidyn.cu:499-531 (commented out there): for the split particles in DESCENDING slot order a child is
+ *      appended at (x, y - 0.03, z) of the parent's updated position with the parent's velocity, mass 1, boundary = false (:503-520),
+ *      every other field the class default (the reference would reuse whatever dead record sits in that slot), while capacity lasts. */
+static float u_diff2(const upair_acc *a) { return powf(a->dx, 2) + powf(a->dy, 2) + powf(a->dz, 2); }
+
+static void uadapt_merge_split(const fsgo_params *P, fsgo_ustate *s, fsgo_adapt *ad, const int *start, const int *end, int nlive,
+                               const upair_acc *acc, unsigned char *splitflag)
+{
+    const int G = P->grid, numcells = G * G * G;
+    int *nn = (int *)malloc(sizeof(int) * (size_t)(nlive > 0 ? nlive : 1));
+    ad->merged = ad->split = 0;
+    if (!nn) return;
+    for (int i = 0; i < nlive; i++) {
+        nn[i] = -1;
+        if (s->boundary[i] || !(s->mass[i] > 0 && s->mass[i] < 2) || !(u_diff2(&acc[i]) < 20)) continue;
+        float best = 0;
+        const int b = s->cell[i];
+        for (int a = -1; a <= 1; a++)
+            for (int bb = -1; bb <= 1; bb++)
+                for (int c = -1; c <= 1; c++) {
+                    const int cb = b + a * G * G + bb * G + c;                    /* cu:130-132 */
+                    if (cb < 0 || cb >= numcells || start[cb] < 0 || end[cb] < 0) continue;
+                    for (int j = start[cb]; j <= end[cb] && j < nlive; j++) {
+                        if (j == i || s->boundary[j] || !(s->mass[j] > 0 && s->mass[j] < 2) || !(u_diff2(&acc[j]) < 20)) continue;
+                        const float *pi = s->pos + 3 * (size_t)i, *pj = s->pos + 3 * (size_t)j;
+                        float ds = sqrt(powf(pi[0] - pj[0], 2) + powf(pi[1] - pj[1], 2) + powf(pi[2] - pj[2], 2));   /* cuh:211-213 */
+                        if (!(ds <= ad->merge_distance && ds > 0)) continue;      /* :261 */
+                        if (nn[i] < 0 || ds < best || (ds == best && s->index[j] < s->index[nn[i]])) { nn[i] = j; best = ds; }
+                    }
+                }
+    }
+    for (int i = 0; i < nlive; i++) {
+        const int j = nn[i];
+        if (j < 0 || nn[j] != i || !(s->index[i] < s->index[j])) continue;       /* the survivor does the work */
+        float *vi = s->vel + 3 * (size_t)i, *vj = s->vel + 3 * (size_t)j, *xi = s->pos + 3 * (size_t)i, *xj = s->pos + 3 * (size_t)j;
+        s->mass[i] = 2.75;                                                         /* :262 */
+        s->mass[j] = 0;                                                            /* :263 */
+        s->boundary[j] = 1;                                                        /* :265 */
+        for (int c = 0; c < 3; c++) vi[c] = (vi[c] + vj[c]) / 2.0;                 /* :266-268 */
+        for (int c = 0; c < 3; c++) xi[c] = (xi[c] + xj[c]) / 2.0;                 /* :269-271 */
+        xj[0] = xj[1] = xj[2] = 90.99;                                             /* :272 */
+        ad->merged++;
+    }
+    for (int i = 0; i < nlive; i++) {
+        splitflag[i] = 0;
+        if (s->mass[i] > ad->split_mass_min && s->cell[i] < numcells && !s->boundary[i] &&
+            (u_diff2(&acc[i]) > 35000 || (s->dens[i] < 9400))) {                   /* :278 */
+            s->mass[i] = 1;                                                        /* :279 */
+            splitflag[i] = 1;                                                      /* :281 */
+            s->pos[3 * (size_t)i + 1] += 0.015;                                    /* :282 */
+            ad->split++;
+        }
+    }
+    free(nn);
+}
+
+/* solver-unidyn.cu:499-531, after the update */
+static void uadapt_children(const fsgo_params *P, fsgo_ustate *s, fsgo_adapt *ad, int nscan, const unsigned char *splitflag)
+{
+    const int G = P->grid, numcells = G * G * G;
+    ad->added = 0;
+    for (int j = nscan - 1; j >= 0; j--) {                                         /* :499 */
+        if (!splitflag[j] || s->boundary[j]) continue;                             /* :500 */
+        if (s->n >= ad->capacity) continue;                                        /* :512 (room left) */
+        const int k = s->n;
+        const float x = s->pos[3 * (size_t)j], y = s->pos[3 * (size_t)j + 1] - 0.03, z = s->pos[3 * (size_t)j + 2];   /* :501-503 */
+        s->pos[3 * (size_t)k] = x; s->pos[3 * (size_t)k + 1] = y; s->pos[3 * (size_t)k + 2] = z;
+        for (int c = 0; c < 3; c++) s->vel[3 * (size_t)k + c] = s->vel[3 * (size_t)j + c];                          /* :504-506, :516-518 */
+        s->mass[k] = 1;                                                            /* :519 */
+        s->boundary[k] = 0;                                                        /* :520 */
+        /* class defaults for the rest (FluidGPU-unidyn.cuh:132-187) */
+        s->acc[3 * (size_t)k] = s->acc[3 * (size_t)k + 1] = 0; s->acc[3 * (size_t)k + 2] = (float)P->gravity;
+        s->dens[k] = 9550; s->press[k] = 0;
+        for (int c = 0; c < 3; c++) s->delpress[3 * (size_t)k + c] = s->newdelpress[3 * (size_t)k + c] = 0;
+        s->newdens[k] = 0;
+        s->solid[k] = 0; s->fluid[k] = 1;
+        s->subindex[k] = 0;
+        s->index[k] = ad->next_index++;
+        {                                                                          /* :522 */
+            float fx = x - P->origin, fy = y - P->origin, fz = z - P->origin;
+            double qx = fx / P->cellsize, qy = fy / P->cellsize, qz = fz / P->cellsize;
+            long long l = (long long)(int)qx * G * G + (long long)(int)qy * G + (int)qz;
+            s->cell[k] = (!(fabs(qx) < 1e6 && fabs(qy) < 1e6 && fabs(qz) < 1e6) || l < 0 || l >= numcells) ? numcells : (int)l;
+        }
+        s->n++;
+        ad->added++;
+    }
+}
+
+static int ustep(const fsgo_params *P, fsgo_ustate *s, fsgo_adapt *ad, int t, int *cells_sorted, int *start_out, int *end_out,
+                 int *split_out, float *spts, float *a3, float *b3, long long *stats)
 {
     (void)t;
     const int n = s->n, G = P->grid, numcells = G * G * G;
@@ -298,6 +417,9 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
     for (int i = 0; i < n; i++)
         if (!s->boundary[i] && s->solid[i] != 0.0f) mixed = 1;
     if (mixed && (!s->stress_tensor || !s->stress_rate)) return -2;
+    if (mixed && ad) return -2;                     /* merging / splitting: pure-fluid scenes */
+    unsigned char *splitflag = ad ? (unsigned char *)calloc((size_t)(n > 0 ? n : 1), 1) : NULL;
+    if (ad && !splitflag) return -1;
 
     int *perm = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
     float *tmp = (float *)malloc(sizeof(float) * 3 * (size_t)(n > 0 ? n : 1));
@@ -333,6 +455,7 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
     permute_f(s->newdelpress, perm, n, 3, tmp);
     permute_f(s->solid, perm, n, 1, tmp);
     permute_f(s->fluid, perm, n, 1, tmp);
+    if (s->mass) permute_f(s->mass, perm, n, 1, tmp);
     if (s->stress_tensor && s->stress_rate) {
         float *t9 = (float *)malloc(sizeof(float) * 9 * (size_t)(n > 0 ? n : 1));
         if (!t9) goto done;
@@ -463,6 +586,9 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
         for (int i = 0; i < nlive; i++) ustress_update(s, acc, i);
     }
 
+    /* ---- particle merging / splitting, between the pair sums and the update (see above) ---- */
+    if (ad) uadapt_merge_split(P, s, ad, start, end, nlive, acc, splitflag);
+
     /* ---- mykernel2 (cu:451-497) + Particle::update(t) (cuh:296-423) + cell_calc (cu:544-551) ---- */
     {
         const double DT = P->dt;
@@ -476,7 +602,7 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
             const float sa0 = mixed ? acc[i].stress_accel[0] : 0.0f, sa1 = mixed ? acc[i].stress_accel[1] : 0.0f, sa2 = mixed ? acc[i].stress_accel[2] : 0.0f;
             const float ma0 = mixed ? acc[i].mix[0] : 0.0f, ma1 = mixed ? acc[i].mix[1] : 0.0f, ma2 = mixed ? acc[i].mix[2] : 0.0f;
             if (spts) { spts[3 * (size_t)i] = x[0]; spts[3 * (size_t)i + 1] = x[1]; spts[3 * (size_t)i + 2] = x[2]; }   /* cu:462-464 */
-            if (a3) a3[i] = 1.0f;                                                                                       /* mass, :465 */
+            if (a3) a3[i] = s->mass ? s->mass[i] : 1.0f;                                                                /* mass, :465 */
             if (b3) b3[i] = powf(diffx, 2) + powf(diffy, 2) + powf(diffz, 2);                                          /* :466 */
             int bnd = s->boundary[i] != 0;
             float solid = s->solid[i], fluid = s->fluid[i];
@@ -543,13 +669,15 @@ int fsgo_unidyn_step(const fsgo_params *P, fsgo_ustate *s, int t, int *cells_sor
         if (spts || a3 || b3)
             for (int i = nlive; i < n; i++) {
                 if (spts) { spts[3 * (size_t)i] = s->pos[3 * (size_t)i]; spts[3 * (size_t)i + 1] = s->pos[3 * (size_t)i + 1]; spts[3 * (size_t)i + 2] = s->pos[3 * (size_t)i + 2]; }
-                if (a3) a3[i] = 1.0f;
+                if (a3) a3[i] = s->mass ? s->mass[i] : 1.0f;
                 if (b3) b3[i] = 0.0f;
             }
     }
+    if (ad) uadapt_children(P, s, ad, nlive, splitflag);
     if (stats) memcpy(stats, st, sizeof(st));
     rc = 0;
 done:
+    free(splitflag);
     free(perm); free(tmp); free(start); free(end); free(split); free(cnt); free(acc); free(accb); free(occ);
     return rc;
 }

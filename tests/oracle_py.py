@@ -26,7 +26,12 @@ class State(C.Structure):
 class UState(C.Structure):
     _fields_ = [("n", C.c_int)] + [(k, C.c_void_p) for k in ("pos", "vel", "acc", "dens", "press", "delpress", "newdens",
                                                               "newdelpress", "index", "cell", "boundary", "solid", "fluid", "subindex",
-                                                              "stress_tensor", "stress_rate")]
+                                                              "stress_tensor", "stress_rate", "mass")]
+
+
+class Adapt(C.Structure):
+    _fields_ = [("merge_distance", C.c_double), ("split_mass_min", C.c_double), ("capacity", C.c_int), ("next_index", C.c_int),
+                ("merged", C.c_int), ("split", C.c_int), ("added", C.c_int)]
 
 
 _lib = None
@@ -56,6 +61,8 @@ def load():
         lib.fsgo_params_unidyn.argtypes = [C.POINTER(Params)]
         lib.fsgo_unidyn_step.restype = C.c_int
         lib.fsgo_unidyn_step.argtypes = [C.POINTER(Params), C.POINTER(UState), C.c_int] + [C.c_void_p] * 8
+        lib.fsgo_unidyn_step_adapt.restype = C.c_int
+        lib.fsgo_unidyn_step_adapt.argtypes = [C.POINTER(Params), C.POINTER(UState), C.POINTER(Adapt), C.c_int] + [C.c_void_p] * 8
         _lib = lib
     return _lib
 
@@ -84,9 +91,10 @@ def unidyn_params(**kw) -> Params:
 
 
 class OracleSimUnidyn:
-    """Runs fsgo_unidyn_step on a copy of a state dict that also holds solid / fluid."""
+    """Runs fsgo_unidyn_step on a copy of a state dict that also holds solid / fluid.  adapt = (merge_distance, split_mass_min,
+    capacity): fsgo_unidyn_step_adapt — particle merging / splitting, the state also carries `mass` and may grow up to `capacity`."""
 
-    def __init__(self, params: Params, state: dict):
+    def __init__(self, params: Params, state: dict, adapt=None):
         self.lib = load()
         self.p = params
         self.s = {k: np.array(v, copy=True) for k, v in state.items()}
@@ -96,6 +104,15 @@ class OracleSimUnidyn:
         self.s.setdefault("subindex", np.zeros(n, np.int32))
         self.s.setdefault("stress_tensor", np.zeros((n, 9), np.float32))
         self.s.setdefault("stress_rate", np.zeros((n, 9), np.float32))
+        self.adapt = None
+        if adapt is not None:
+            self.s.setdefault("mass", np.ones(n, np.float32))
+            self.adapt = Adapt(merge_distance=adapt[0], split_mass_min=adapt[1], capacity=int(adapt[2]), next_index=n)
+            cap = int(adapt[2])
+            for k, v in list(self.s.items()):          # room for the children behind the n particles
+                pad = np.zeros((cap - n,) + v.shape[1:], v.dtype)
+                self.s[k] = np.ascontiguousarray(np.concatenate([v, pad]))
+            n = cap
         nc = params.grid ** 3
         self.cells_sorted = np.zeros(n, np.int32)
         self.start, self.end, self.split = np.zeros(nc, np.int32), np.zeros(nc, np.int32), np.zeros(nc, np.int32)
@@ -107,18 +124,24 @@ class OracleSimUnidyn:
         st = UState()
         st.n = self.n
         for k in ("pos", "vel", "acc", "dens", "press", "delpress", "newdens", "newdelpress", "index", "cell", "boundary", "solid",
-                  "fluid", "subindex", "stress_tensor", "stress_rate"):
+                  "fluid", "subindex", "stress_tensor", "stress_rate") + (("mass",) if self.adapt is not None else ()):
             setattr(st, k, self.s[k].ctypes.data)
+        out = (self.cells_sorted.ctypes.data, self.start.ctypes.data, self.end.ctypes.data, self.split.ctypes.data, self.spts.ctypes.data,
+               self.a3.ctypes.data, self.b3.ctypes.data, self.stats.ctypes.data)
+        self.events = []
         for _ in range(nsteps):
-            rc = self.lib.fsgo_unidyn_step(C.byref(self.p), C.byref(st), self.t, self.cells_sorted.ctypes.data, self.start.ctypes.data,
-                                           self.end.ctypes.data, self.split.ctypes.data, self.spts.ctypes.data, self.a3.ctypes.data,
-                                           self.b3.ctypes.data, self.stats.ctypes.data)
+            if self.adapt is not None:
+                rc = self.lib.fsgo_unidyn_step_adapt(C.byref(self.p), C.byref(st), C.byref(self.adapt), self.t, *out)
+                self.events.append((self.adapt.merged, self.adapt.split, self.adapt.added))
+            else:
+                rc = self.lib.fsgo_unidyn_step(C.byref(self.p), C.byref(st), self.t, *out)
             assert rc == 0, rc
+            self.n = st.n
             self.t += 1
         return self
 
     def state(self) -> dict:
-        return {k: v.copy() for k, v in self.s.items()}
+        return {k: v[:self.n].copy() for k, v in self.s.items()}
 
 
 class OracleSim:

@@ -142,3 +142,42 @@ def test_unidyn_oracle_against_reference_gpu_golden(fsg, oracle, name, steps):
         for fld in ("pos", "vel", "acc", "dens", "press", "delpress", "fluid", "solid"):
             err = oracle_py.rel_l2(got[fld].reshape(n, -1)[o], ref[fld].reshape(n, -1)[r])
             assert err <= 1e-5, (name, k, fld, err)
+
+
+def test_unidyn_oracle_merge_split_semantics():
+    """fsgo_unidyn_step_adapt (particle merging / splitting, FluidGPU-unidyn.cu:260-285 + solver-unidyn.cu:495-542, race-free reading):
+    with the reference's literals it is exactly fsgo_unidyn_step; with a live merge distance every merge removes one particle from the
+    grid (mass 0, boundary, parked at 90.99) and leaves one of mass 2.75 at the pair's midpoint; a heavy particle in thin surroundings
+    splits into two of mass 1, the child 0.015 + ... - 0.03 below / behind the parent in y, with the next free Particle::index, while
+    the capacity lasts."""
+    import fluidsolvergpu_b200 as fsg
+    i = np.arange(8 * 8 * 6)
+    block = np.stack([-0.2 + 0.05 * (i % 8), -0.2 + 0.05 * ((i // 8) % 8), -0.3 + 0.05 * (i // 64)], 1)
+    lone = np.array([[0.5, 0.5, 0.5], [-0.6, 0.5, 0.4], [0.5, -0.6, 0.3]])
+    pos = np.concatenate([block, lone]).astype(np.float32)
+    n = pos.shape[0]
+    st = fsg.scenes.default_state(pos, np.zeros_like(pos), np.zeros(n, np.uint8))
+    st["solid"], st["fluid"] = np.zeros(n, np.float32), np.ones(n, np.float32)
+    st["mass"] = np.r_[np.ones(block.shape[0]), np.full(3, 2.75)].astype(np.float32)
+    p = oracle_py.unidyn_params()
+    plain = oracle_py.OracleSimUnidyn(p, {k: v for k, v in st.items() if k != "mass"}).step(3).state()
+    noop = oracle_py.OracleSimUnidyn(p, dict(st, mass=np.ones(n, np.float32)), adapt=(-10.0, 3.0, n + 8))
+    noop.step(3)
+    assert noop.events[-1] == (0, 0, 0) and all(np.array_equal(plain[k], noop.state()[k]) for k in plain)
+    sim = oracle_py.OracleSimUnidyn(p, st, adapt=(0.0505, 2.0, n + 2))
+    merged = split = added = 0
+    for k in range(4):
+        before = sim.state()
+        sim.step(1)
+        m, s_, a = sim.events[-1]
+        after = sim.state()
+        merged, split, added = merged + m, split + s_, added + a
+        assert after["pos"].shape[0] == before["pos"].shape[0] + a <= n + 2
+        gone = (after["mass"] == 0)
+        assert gone.sum() == merged and np.all(after["boundary"][gone] == 1) and np.all(after["cell"][gone] == p.grid ** 3)
+        assert np.allclose(after["pos"][gone], 90.99)
+    assert merged > 10 and split == 3 and added == 2                       # three heavy lone particles split, two children fit
+    fin = sim.state()
+    kids = fin["index"] >= n
+    assert kids.sum() == 2 and set(fin["index"][kids]) == {n, n + 1} and np.all(fin["mass"][kids] == 1)
+    assert set(np.unique(fin["mass"])) <= {0.0, 1.0, 2.75}

@@ -616,6 +616,76 @@ def test_unidyn_random_scenes(fsg, seed, n, bf):
             unidyn_resync_step(fsg, s)
 
 
+def _adapt_scene(fsg):
+    """An exact lattice block (spacing 0.05: interior particles have |diffusion|^2 ~ 0, the only ones the reference's merge test
+    admits, FluidGPU-unidyn.cu:261; a merge distance just above the spacing makes nearest neighbours candidates) and, above it, a
+    few isolated particles that already carry the merged mass 2.75: after the first step their density is below 9400 and they
+    split (:278) as soon as the split threshold is below 2.75."""
+    i = np.arange(16 * 16 * 10)
+    block = np.stack([-0.4 + 0.05 * (i % 16), -0.4 + 0.05 * ((i // 16) % 16), -0.5 + 0.05 * (i // 256)], 1)
+    k = np.arange(48)
+    lone = np.stack([-0.6 + 0.3 * (k % 4), -0.6 + 0.3 * ((k // 4) % 4), 0.25 + 0.22 * (k // 16)], 1)
+    pos = np.concatenate([block, lone]).astype(np.float32)
+    rng = np.random.default_rng(11)
+    out = fsg.scenes.default_state(pos, rng.uniform(-0.02, 0.02, pos.shape).astype(np.float32), np.zeros(pos.shape[0], np.uint8))
+    out["solid"] = np.zeros(pos.shape[0], np.float32)
+    out["fluid"] = np.ones(pos.shape[0], np.float32)
+    out["mass"] = np.r_[np.ones(block.shape[0]), np.full(lone.shape[0], 2.75)].astype(np.float32)
+    return out
+
+
+def test_unidyn_particle_merging_and_splitting(fsg):
+    """the merge / split blocks of FluidGPU-unidyn.cu:260-285 and the host loop of solver-unidyn.cu:495-542 made
+    live (fsg_config.unidyn_adapt, race-free reading — DESIGN.md §5; parity UNPINNED against the reference, which never merges).
+    (a) With the reference's literals (merge distance -10, split above mass 3) the pass is a no-op: same bits as without it.
+    (b) With a positive merge distance and a split threshold below 2.75: every step from identical bits against the oracle — which
+    pairs merge, who splits, the children appended (count, order, Particle::index), masses and integers exact, fields <= 1e-5;
+    particles are created and the capacity is respected."""
+    state = _adapt_scene(fsg)
+    n = state["pos"].shape[0]
+    plain = dict(state, mass=np.ones(n, np.float32))
+    with fsg.FluidSolver(fsg.FluidSolver.unidyn_config(capacity=n)) as a, \
+            fsg.FluidSolver(fsg.FluidSolver.unidyn_config(capacity=n + 64, unidyn_adapt=1)) as b:
+        a.upload(plain)
+        b.upload(plain)
+        a.step(3)
+        b.step(3)
+        ga, gb = a.download(), b.download()
+        assert b.adapt_counts()["total"] == (0, 0, 0) and gb["pos"].shape[0] == n
+        for f in ga:
+            assert np.array_equal(ga[f], gb[f]), f
+        with pytest.raises(fsg.FsgError, match="mass"):                  # merged particles need the pass
+            a.upload(state)
+    md, smin, cap = 0.0505, 2.0, n + 40
+    cfg = fsg.FluidSolver.unidyn_config(capacity=cap, unidyn_adapt=1, unidyn_merge_distance=md, unidyn_split_mass_min=smin)
+    p = oracle_py.unidyn_params(grid=cfg.grid, origin=cfg.origin, cellsize=cfg.cellsize, h=cfg.h, dt=cfg.dt, alpha_fluid=cfg.alpha_fluid,
+                                alpha_boundary=cfg.alpha_boundary, sound=cfg.sound, gravity=cfg.gravity)
+    seen = np.zeros(3, np.int64)
+    with fsg.FluidSolver(cfg) as s:
+        s.upload(state)
+        for k in range(5):
+            cur = s.download()
+            sim = oracle_py.OracleSimUnidyn(p, {q: v for q, v in cur.items() if q != "cell"}, adapt=(md, smin, cap))
+            s.step(1)
+            sim.step(1)
+            got, ref = s.download(), sim.state()
+            ev = s.adapt_counts()["last"]
+            assert ev == sim.events[-1], (k, ev, sim.events[-1])
+            seen += np.array(ev)
+            assert got["pos"].shape[0] == sim.n <= cap
+            for f in ("index", "cell", "boundary", "mass"):
+                assert np.array_equal(got[f], ref[f]), (k, f)
+            spts, a3, b3 = s.export_viz()
+            m = cur["pos"].shape[0]                                      # (children show up in the export of the NEXT step)
+            assert np.array_equal(a3[:m], sim.a3[:m])
+            errs = {f: rel_l2(got[f], ref[f]) for f in UFIELDS}
+            assert all(e <= TOL for e in errs.values()), (k, errs)
+        # a merged record survives the 340-byte round trip
+        rec = s.download_aos()
+        assert np.array_equal(rec[:, 72:76].copy().view(np.float32)[:, 0], s.download()["mass"])
+    assert seen[0] > 20 and seen[1] > 40 and seen[2] == 40, seen          # 48 lone heavy particles split, 40 children fit
+
+
 @pytest.mark.parametrize("mode", ["messages", "peer"])
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("fast", [False, True])
