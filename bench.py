@@ -766,7 +766,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--grid", type=int, default=512)
     ap.add_argument("--impl", default="fsg", choices=["fsg", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=9)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle-sampled parity check (N=1) / the slab-vs-single check (N>1)")
@@ -774,7 +774,7 @@ def main():
     ap.add_argument("--no-frames", action="store_true", help="skip the frame-output leg (N=1)")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref) beside libfsg")
     ap.add_argument("--grid1024-steps", type=int, default=5, help="steps of the short 1024^3 leg (0 = off)")
-    ap.add_argument("--e2e-contexts", type=int, default=3,
+    ap.add_argument("--e2e-contexts", type=int, default=4,
                     help="N=1: contexts the end-to-end leg pipelines independent batches over (1 = strictly serial upload/step/download)")
     ap.add_argument("--pair-mode", type=int, default=0, choices=[0, 1],
                     help="0: symmetric pair kernel (default); 1: deterministic gather kernel (fsg_config.pair_mode)")
