@@ -801,19 +801,11 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
         if (prof) prof_mark(c);
         // value half + findneighbours (solver.cu:181-182); with a deferred update also mykernel2's update of the PREVIOUS step
         const bool defer = defer_enabled(c);
-        // sorted-ghost slabs: k_reorder also writes the face layers of the state it produces into the neighbours' ghost messages
-        FsgReorderGhost rg, *gh = nullptr;
-        if (c->slab2) {
-            memset(&rg, 0, sizeof rg);
-            int rc = fsg_slab2_ghost_prepare(c, &rg);
-            if (rc != FSG_OK) return rc;
-            if (c->ghost_fused) gh = &rg;
-        }
         if (c->deferred) {
             CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->A, c->B, c->carry_pending ? c->carryA : nullptr, nullptr, c->sums,
                                      defer ? c->keysB : nullptr, c->start, c->end, c->binlist[nxt], c->counters + nxt, c->binlist[nxt],
                                      c->counters + 10, c->counters + 3, c->counters + 5, c->cfg.world > 1 ? c->counters + 16 : nullptr,
-                                     c->counters + 14, c->stream, gh));
+                                     c->counters + 14, c->stream));
             FsgState t = c->A; c->A = c->B; c->B = t;      // A: the sorted pre-update state of THIS step; B: scratch until materialised
             c->carry_pending = false;
             c->deferred = false;
@@ -821,7 +813,7 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
             CU(c, fsg_launch_reorder(c->dev, n, c->perm, c->keysA, c->B, c->A, c->carry_live ? c->carryB : nullptr, c->carryA, nullptr,
                                      defer ? c->keysB : nullptr, c->start, c->end, c->binlist[nxt], c->counters + nxt,
                                      c->binlistB ? c->binlistB : c->binlist[nxt], c->counters + 10, c->counters + 3, c->counters + 5,
-                                     c->cfg.world > 1 ? c->counters + 16 : nullptr, c->counters + 14, c->stream, gh));
+                                     c->cfg.world > 1 ? c->counters + 16 : nullptr, c->counters + 14, c->stream));
         c->n_sorted = n;
         c->launches++;
         // sorted-ghost slab pipeline: the face layers of the sorted state go to the neighbours' ghost zones, theirs come in

@@ -6,7 +6,6 @@
 //   k_pair_update  : gather-form pair sums over the 27-bin neighbourhood, fused with
 //                    Particle::update and re-binning (the reference's mykernel + mykernel2).
 #include "fsg_device.cuh"
-#include <string.h>
 
 // ------------------------------------------------------------------------------------------------
 // small utilities
@@ -118,21 +117,16 @@ cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const i
 // which saves the separate update pass (read 80 B + write 72 B per particle) and one trip of the state through HBM.
 // keys_next != nullptr: the bin id each particle will have after ITS next update goes to keys_next[k] (predicted_key) — the next
 // step's sort input, produced before this step's pair kernel runs.
-// GH (sorted-ghost slab pipeline, fsg_slab2.cu): the particles of the two face layers are ALSO written straight into the neighbours'
-// ghost messages as they come out of the gather (remote stores over NVLink from the kernel that produces them: no separate send
-// kernel, the transfer rides under the rest of the reorder); the last block to finish writes the counts and, after a system-wide
-// fence, the stamps the neighbours wait for.
-template <bool UPD, bool GH>
+template <bool UPD>
 __global__ void __launch_bounds__(256)
 k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restrict__ keysA, FsgState src,
           FsgState dst, const float4 *__restrict__ carry_src, float4 *__restrict__ carry_dst, const float4 *__restrict__ sums_src,
           int *__restrict__ keys_next, int *start, int *end,
-          int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag, FsgReorderGhost gh)
+          int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag)
 {
     const int numcells = d.numcells;
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool head = false, headB = false;
-    bool wrote_remote = false;
     if (k < n) {
         int sidx = perm[k];
         float4 a = src.posd[sidx], b = src.velp[sidx], c = src.accf[sidx], e = src.dpi[sidx];
@@ -158,15 +152,6 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
             for (int q = 0; q < 18; q++) dst.stress[(size_t)k * 18 + q] = src.stress[(size_t)sidx * 18 + q];
         }
         if (keys_next) keys_next[k] = key < numcells ? predicted_key(d, a, b) : key;
-        if (GH) {
-            const int64_t l_end = gh.bounds[0], r_beg = gh.bounds[1], live = gh.bounds[2];
-            if (gh.peer_left && k < l_end) {
-                if (k < gh.cap_g) { const S2Gh M = s2_gh(gh.peer_left, gh.cap_g); M.posd[k] = a; M.velp[k] = b; M.keys[k] = key; wrote_remote = true; }
-            } else if (gh.peer_right && k >= r_beg && k < live) {
-                const int64_t t = k - r_beg;
-                if (t < gh.cap_g) { const S2Gh M = s2_gh(gh.peer_right, gh.cap_g); M.posd[t] = a; M.velp[t] = b; M.keys[t] = key; wrote_remote = true; }
-            }
-        }
         int next = k + 1 < n ? keysA[k + 1] : d.dead;
         if (k + 1 < n && next < key) atomicOr(order_flag, 1);          // the key sort's result, verified where it is consumed
         if (key < numcells) {
@@ -200,7 +185,6 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(FULL, head), mB = __ballot_sync(FULL, headB);
     if (lane == 0) { s_cnt[0][warp] = __popc(m); s_cnt[1][warp] = __popc(mB); }
-    if (GH && wrote_remote) __threadfence_system();        // this thread's remote stores are visible before the block reports in
     __syncthreads();
     if (threadIdx.x < 2) {
         const int L = threadIdx.x;
@@ -212,47 +196,20 @@ k_reorder(FsgDev d, int64_t n, const int *__restrict__ perm, const int *__restri
     __syncthreads();
     if (head) binlist[s_base[0] + s_cnt[0][warp] + __popc(m & ((1u << lane) - 1))] = keysA[k];
     if (headB) binlistB[s_base[1] + s_cnt[1][warp] + __popc(mB & ((1u << lane) - 1))] = keysA[k];
-    if (GH && threadIdx.x == 0) {
-        const int before = atomicAdd(gh.done, 1);
-        if (before == (int)gridDim.x - 1) {                 // every block's face particles are in the neighbours' memory
-            *gh.done = 0;
-            const long long l_end = gh.bounds[0], r_beg = gh.bounds[1], live = gh.bounds[2];
-            const long long gl = l_end, gr = live - r_beg;
-            if ((gh.peer_left && gl > gh.cap_g) || (gh.peer_right && gr > gh.cap_g)) atomicOr(gh.overflow, 1);
-            __threadfence_system();
-            if (gh.peer_left) {
-                const S2Gh M = s2_gh(gh.peer_left, gh.cap_g);
-                M.hdr[0] = gl < gh.cap_g ? gl : gh.cap_g;
-                gh.diag[1] = M.hdr[0];
-            }
-            if (gh.peer_right) {
-                const S2Gh M = s2_gh(gh.peer_right, gh.cap_g);
-                M.hdr[0] = gr < gh.cap_g ? gr : gh.cap_g;
-                gh.diag[3] = M.hdr[0];
-            }
-            __threadfence_system();
-            if (gh.peer_left) *(volatile long long *)s2_gh(gh.peer_left, gh.cap_g).tail = gh.seq;
-            if (gh.peer_right) *(volatile long long *)s2_gh(gh.peer_right, gh.cap_g).tail = gh.seq;
-            __threadfence_system();
-        }
-    }
 }
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, const float4 *sums_src, int *keys_next, int *start,
                                int *end, int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag,
-                               cudaStream_t s, const FsgReorderGhost *gh)
+                               cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    FsgReorderGhost g;
-    memset(&g, 0, sizeof g);
-    if (gh) g = *gh;
-#define FSG_REORDER(UPD, GH, SUMS)                                                                                                          \
-    k_reorder<UPD, GH><<<blocks, 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst, SUMS, keys_next, start, end, binlist, nocc, \
-                                              binlistB, noccB, nlive, nkeep, ranges, order_flag, g)
-    if (sums_src) { if (gh) FSG_REORDER(true, true, sums_src); else FSG_REORDER(true, false, sums_src); }
-    else { if (gh) FSG_REORDER(false, true, nullptr); else FSG_REORDER(false, false, nullptr); }
-#undef FSG_REORDER
+    if (sums_src)
+        k_reorder<true><<<blocks, 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst, sums_src, keys_next, start, end, binlist, nocc,
+                                               binlistB, noccB, nlive, nkeep, ranges, order_flag);
+    else
+        k_reorder<false><<<blocks, 256, 0, s>>>(d, n, perm, keysA, src, dst, carry_src, carry_dst, nullptr, keys_next, start, end, binlist, nocc,
+                                                binlistB, noccB, nlive, nkeep, ranges, order_flag);
     return cudaGetLastError();
 }
 

@@ -92,7 +92,7 @@ struct fsg_ctx {
                         // [14] the sorted key array was found out of order by k_reorder (never expected; reported by fsg_get_stats / downloads),
                         // [16..19] slab contexts: sorted-slot bounds found by k_reorder — first slot of layer rl, of layer rr (the pack's
                         // two-layer regions), of layer x0 + 1, of layer x1 - 1 (the face layers the sorted-ghost pipeline sends),
-                        // [20..21] blocks of k_s2_ghost_send / k_reorder<.., GH> that have finished, [24..26] face-layer bounds of the sorted keys (k_s2_bounds)
+                        // [20..21] blocks of k_slab2_ghost_send that have finished (left, right)
     unsigned long long *dstats;   // [0] tested, [1] in range, [2] dropped
     int *slab_cnt;      // slab pack: per-warp counts of the 4 message categories, then their exclusive scan
     void *scan_tmp;
@@ -112,7 +112,7 @@ struct fsg_ctx {
     // layers of the SORTED state are copied into the neighbours' ghost zones after the reorder.
     bool slab2;
     bool slab2_split;   // in-process slab groups: fsg_step stops after the ghost send, fsg_slab_step_finish does the rest
-    bool step_pending, pending_prof, ghost_prof, ghost_fused;
+    bool step_pending, pending_prof, ghost_prof;
     int pending_nxt;
     bool slab2_mid;     // between fsg_slab_pack_send and fsg_step: migrants have left, B cannot be materialised
     int64_t n_own;
@@ -183,49 +183,17 @@ size_t fsg_scan_temp_bytes(int64_t n);
 cudaError_t fsg_scan_exclusive(void *tmp, size_t tmp_bytes, const int *in, int *out, int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_reset_tables(const int *binlist, const int *nocc, const int *keysA, int *start, int *end,
                                     int64_t n, cudaStream_t s);
-struct FsgReorderGhost;
 cudaError_t fsg_launch_reorder(const FsgDev &d, int64_t n, const int *perm, const int *keysA, FsgState src,
                                FsgState dst, const float4 *carry_src, float4 *carry_dst, const float4 *sums_src, int *keys_next, int *start,
                                int *end, int *binlist, int *nocc, int *binlistB, int *noccB, int *nlive, int *nkeep, int *ranges, int *order_flag,
-                               cudaStream_t s, const FsgReorderGhost *gh = nullptr);
-
-// ---- sorted-ghost slab pipeline (fsg_slab2.cu): the ghost message a neighbour's face layer is written into, and the handle k_reorder
-// gets to write it straight from the gather (compute + transfer in one kernel) ----
-//   [header 64 B: int64 g][posd cap_g][velp cap_g][keys cap_g (int), padded to 64 B][tail 64 B: int64 stamp]
-struct S2Gh {
-    long long *hdr, *tail;
-    float4 *posd, *velp;
-    int *keys;
-};
-__host__ __device__ inline size_t s2_gh_keys_bytes(int64_t cap_g) { return ((size_t)cap_g * sizeof(int) + 63) & ~(size_t)63; }
-__host__ __device__ inline size_t s2_gh_bytes(int64_t cap_g) { return 64 + (size_t)cap_g * 2 * sizeof(float4) + s2_gh_keys_bytes(cap_g) + 64; }
-__host__ __device__ inline S2Gh s2_gh(void *base, int64_t cap_g)
-{
-    S2Gh r;
-    r.hdr = (long long *)base;
-    float4 *p = (float4 *)((char *)base + 64);
-    r.posd = p; r.velp = p + cap_g;
-    r.keys = (int *)(p + 2 * cap_g);
-    r.tail = (long long *)((char *)r.keys + s2_gh_keys_bytes(cap_g));
-    return r;
-}
-
-struct FsgReorderGhost {
-    void *peer_left, *peer_right;     // the neighbours' ghost messages (mapped peer memory), nullptr where there is no neighbour
-    const int *bounds;                // [0] first sorted slot beyond layer x0, [1] first slot of layer x1 - 1, [2] n_live (k_s2_bounds)
-    long long cap_g, seq;
-    int *done;                        // blocks that have finished (reset by the last one)
-    int *overflow;
-    long long *diag;
-};
+                               cudaStream_t s);
 int fsg_slab_sticky_error(fsg_ctx *c); // fsg_slab.cu: FSG_E_STATE once a device-side wait for a neighbour has timed out
 int fsg_slab_send_next(fsg_ctx *c);   // fsg_slab.cu: pack + copies of the next step's messages on c->comm (overlap mode)
 // fsg_slab2.cu — the sorted-ghost slab pipeline
 int fsg_slab2_engage(fsg_ctx *c, int64_t cap_m, int64_t cap_g, size_t *bytes);   // decides the mode at fsg_slab_alloc_messages; message buffer size
 int fsg_slab2_pack_send(fsg_ctx *c);         // migrants (pre-update state + pending sums) -> the neighbours' inboxes
 int fsg_slab2_unpack_recv(fsg_ctx *c);       // waits for the neighbours' migrants, appends them behind the slots in use
-int fsg_slab2_ghost_prepare(fsg_ctx *c, FsgReorderGhost *g);   // before the reorder: the handle k_reorder<.., GH> writes the face layers through
-int fsg_slab2_ghost_send(fsg_ctx *c);            // after the reorder: stand-alone send kernel when the fused form is off
+int fsg_slab2_ghost_send(fsg_ctx *c);            // after the reorder: the sorted face layers -> the neighbours' ghost messages
 int fsg_slab2_ghost_recv(fsg_ctx *c, int nxt);   // wait for the neighbours' ghosts, install them + their bins
 int fsg_slab2_reset_ghost_tables(fsg_ctx *c);        // start / end = -1 for the ghost bins of the last step
 cudaError_t fsg_launch_pair_update(const fsg_ctx *c, int64_t n, const int *binlist, const int *nocc, int *work,

@@ -31,7 +31,14 @@ struct S2Mig {
     long long *hdr, *tail;
     float4 *posd, *velp, *accf, *dpi, *acc;
 };
+struct S2Gh {
+    long long *hdr, *tail;
+    float4 *posd, *velp;
+    int *keys;
+};
 __host__ __device__ inline size_t s2_mig_bytes(int64_t cap_m) { return 64 + (size_t)cap_m * 5 * sizeof(float4) + 64; }
+__host__ __device__ inline size_t s2_gh_keys_bytes(int64_t cap_g) { return ((size_t)cap_g * sizeof(int) + 63) & ~(size_t)63; }
+__host__ __device__ inline size_t s2_gh_bytes(int64_t cap_g) { return 64 + (size_t)cap_g * 2 * sizeof(float4) + s2_gh_keys_bytes(cap_g) + 64; }
 __host__ __device__ inline S2Mig s2_mig(void *base, int64_t cap_m)
 {
     S2Mig r;
@@ -41,6 +48,17 @@ __host__ __device__ inline S2Mig s2_mig(void *base, int64_t cap_m)
     r.tail = (long long *)(p + 5 * cap_m);
     return r;
 }
+__host__ __device__ inline S2Gh s2_gh(void *base, int64_t cap_g)
+{
+    S2Gh r;
+    r.hdr = (long long *)base;
+    float4 *p = (float4 *)((char *)base + 64);
+    r.posd = p; r.velp = p + cap_g;
+    r.keys = (int *)(p + 2 * cap_g);
+    r.tail = (long long *)((char *)r.keys + s2_gh_keys_bytes(cap_g));
+    return r;
+}
+
 // bit 0: leaves to the left, bit 1: leaves to the right
 __device__ __forceinline__ int s2_category(const FsgDev &d, int key)
 {
@@ -250,7 +268,6 @@ k_s2_reset_ghost(const void *from_left, const void *from_right, int64_t cap_g, i
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static void *s2_gh_part(const fsg_ctx *c, void *buf) { return buf ? (char *)buf + c->mig_bytes : nullptr; }
 int fsg_slab2_engage(fsg_ctx *c, int64_t cap_m, int64_t cap_g, size_t *bytes)
 {
     const fsg_config &f = c->cfg;
@@ -271,6 +288,7 @@ int fsg_slab2_engage(fsg_ctx *c, int64_t cap_m, int64_t cap_g, size_t *bytes)
     return FSG_OK;
 }
 
+static void *s2_gh_part(const fsg_ctx *c, void *buf) { return buf ? (char *)buf + c->mig_bytes : nullptr; }
 
 int fsg_slab2_pack_send(fsg_ctx *c)
 {
@@ -369,20 +387,8 @@ static cudaEvent_t s2_event(fsg_ctx *c)
     return e;
 }
 
-// bounds of the face layers in the SORTED key array, before the reorder runs: [0] first slot beyond layer x0, [1] first slot of layer
-// x1 - 1, [2] n_live (first slot that holds no particle of the grid).  Three binary searches.
-__global__ void k_s2_bounds(const int *__restrict__ keysA, int n, int kl1, int kr1, int numcells, int *__restrict__ bounds)
-{
-    if (threadIdx.x >= 3) return;
-    const int want = threadIdx.x == 0 ? kl1 : threadIdx.x == 1 ? kr1 : numcells;
-    int a = 0, b = n;
-    while (a < b) { const int mid = (a + b) >> 1; if (keysA[mid] < want) a = mid + 1; else b = mid; }
-    bounds[threadIdx.x] = a;
-}
-
-// Before the reorder: the handle with which k_reorder<.., GH> writes the face layers of the state it produces straight into the
-// neighbours' ghost messages (fused gather + transfer; k_s2_ghost_send above is the stand-alone form, FSG_SLAB2_FUSED=0).
-int fsg_slab2_ghost_prepare(fsg_ctx *c, FsgReorderGhost *g)
+// first half: the face layers of the sorted state -> the neighbours' ghost messages
+int fsg_slab2_ghost_send(fsg_ctx *c)
 {
     if (!c->inbox[0]) { c->err = "fsg_step: the sorted-ghost pipeline needs its messages (fsg_slab_alloc_messages)"; return FSG_E_STATE; }
     const long long seq = ++c->seq_ghost;
@@ -392,35 +398,10 @@ int fsg_slab2_ghost_prepare(fsg_ctx *c, FsgReorderGhost *g)
         c->err = "fsg_step: the neighbours' inboxes are not mapped (fsg_slab_open_peer)";
         return FSG_E_STATE;
     }
-    if (int rc = fsg_slab_ensure_counts(c, 1)) return rc;
-    static int fused = -1;
-    if (fused < 0) { const char *e = getenv("FSG_SLAB2_FUSED"); fused = e ? atoi(e) != 0 : 1; }
-    c->ghost_fused = fused != 0;
-    if (!c->ghost_fused) return FSG_OK;
-    k_s2_bounds<<<1, 32, 0, c->stream>>>(c->keysA, (int)c->n, (c->dev.x0 + 1) * c->dev.G2, (c->dev.x1 - 1) * c->dev.G2, c->dev.numcells, c->counters + 24);
-    CUS(c, cudaGetLastError());
-    c->launches++;
-    g->peer_left = left ? s2_gh_part(c, c->peer_inbox[par]) : nullptr;
-    g->peer_right = right ? s2_gh_part(c, c->peer_inbox[2 + par]) : nullptr;
-    g->bounds = c->counters + 24;
-    g->cap_g = c->msg_cap_g;
-    g->seq = seq;
-    g->done = c->counters + 20;
-    g->overflow = c->counters + 9;
-    g->diag = fsg_slab_diag(c);
-    return FSG_OK;
-}
-
-// first half, stand-alone form: the face layers of the sorted state -> the neighbours' ghost messages (after the reorder)
-int fsg_slab2_ghost_send(fsg_ctx *c)
-{
     const bool prof = c->profiling && c->ev_ghost.size() < 2 * 4096;
     c->ghost_prof = prof;
     if (prof) s2_event(c);
-    if (c->ghost_fused) return FSG_OK;                  // k_reorder has already written them
-    const long long seq = c->seq_ghost;
-    const int par = (int)(seq & 1);
-    const bool left = c->cfg.rank > 0, right = c->cfg.rank < c->cfg.world - 1;
+    if (int rc = fsg_slab_ensure_counts(c, 1)) return rc;
     // remote stores: enough blocks to keep the link busy, few enough to start at once
     const unsigned gb = (unsigned)(c->sm_count > 0 ? c->sm_count : 1);
     k_s2_ghost_send<<<dim3(gb, 2), 256, 0, c->stream>>>(c->A, c->keysA, c->counters + 16, c->counters + 3,
