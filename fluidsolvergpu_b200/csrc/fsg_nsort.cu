@@ -338,13 +338,25 @@ k_ns_place_stayers(const int *__restrict__ knew, const int *__restrict__ prev, i
     if (in_smem)
         for (int i = threadIdx.x; i < cnt; i += NS_THREADS) { s_mk[i] = mk[lo + i]; s_ms[i] = ms[lo + i]; }
     __syncthreads();
+    // all of this thread's loads first (8 slots x new key, previous key, group prefix, group mask): the placing loop below has
+    // searches and early exits that would otherwise keep one slot's loads from overlapping the next one's
+    int kn[NS_TILE / NS_THREADS], kp[NS_TILE / NS_THREADS], go[NS_TILE / NS_THREADS];
+    unsigned gm[NS_TILE / NS_THREADS];
 #pragma unroll
     for (int r = 0; r < NS_TILE / NS_THREADS; r++) {
         const int64_t k = base + r * NS_THREADS + threadIdx.x;
-        if (k >= n) continue;
-        const int key = knew[k];
-        if (key != prev[k]) continue;                                   // movers place themselves
-        const int before = grp_off[k >> 5] + __popc(grp_mask[k >> 5] & ((1u << (k & 31)) - 1u));
+        const bool in = k < n;
+        kn[r] = in ? knew[k] : 0;
+        kp[r] = in ? prev[k] : 1;                                       // (out of range: looks like a mover, is skipped)
+        go[r] = in ? grp_off[k >> 5] : 0;
+        gm[r] = in ? grp_mask[k >> 5] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < NS_TILE / NS_THREADS; r++) {
+        const int64_t k = base + r * NS_THREADS + threadIdx.x;
+        const int key = kn[r];
+        if (key != kp[r]) continue;                                     // movers place themselves
+        const int before = go[r] + __popc(gm[r] & ((1u << (k & 31)) - 1u));
         int rank;
         if (in_smem) {
             int a = 0, b = cnt;
