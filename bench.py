@@ -397,8 +397,17 @@ def short_leg(fsg, torch, dist, G, rank, world, local, args, steps=5, warmup=3):
             dist.all_reduce(own)
             owned = int(own[0])
         ms /= steps
-        return {"grid": G, "particles": n_total, "particles_conserved": owned == n_total, "steps": steps, "warmup": warmup, "ms_per_step": ms,
-                "value": G ** 3 / (ms * 1e-3), "unit": "cell-updates/s", "particle_steps_per_s": n_total / (ms * 1e-3)}
+        out = {"grid": G, "particles": n_total, "particles_conserved": owned == n_total, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+               "value": G ** 3 / (ms * 1e-3), "unit": "cell-updates/s", "particle_steps_per_s": n_total / (ms * 1e-3)}
+        # the oracle-sampled parity check at THIS grid too (N = 1; two whole-state downloads: ~70 GB of host memory at 1024^3)
+        if world == 1 and not args.no_parity:
+            try:
+                import psutil
+                room = psutil.virtual_memory().available >= 160 * n_total
+            except Exception:
+                room = False
+            out["parity_check"] = parity_sample(solver, cfg, args.parity_bins) if room else {"skipped": "not enough host memory for two whole-state downloads"}
+        return out
     finally:
         solver.close()
 
