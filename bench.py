@@ -281,8 +281,19 @@ def reference_gpu_leg(fsg, torch, steps=100):
     # the SAME model on both sides: libfsg's unidyn path on that scene (unit-box floor / walls off, as in the rebuilt reference)
     ucfg = fsg.FluidSolver.unidyn_config(capacity=n3, grid=128, origin=cfg.origin, unidyn_open_box=1)
     ou = ours(ucfg, s3, 10)
+    # ... and its mixed-phase / granular path (two-pass kernels): the same particles stratified into sand over a mixture band over water
+    z = s3["pos"][:, 2]
+    zq = np.quantile(z, [0.45, 0.55])
+    rng = np.random.default_rng(SEED)
+    s3m = dict(s3)
+    s3m["solid"] = np.where(z > zq[1], 1.0, np.where(z > zq[0], rng.uniform(0.05, 0.95, n3), 0.0)).astype(np.float32)
+    s3m["fluid"] = (1.0 - s3m["solid"]).astype(np.float32)
+    try:
+        om = ours(ucfg, s3m, 5)
+    except Exception as e:                      # noqa: BLE001
+        om = None
     res["plume128"] = {"scene": f"synthetic plume 128^3 bins, {n3} particles (the largest grid the reference's launch shapes address)", "steps": 10,
-                       "ref_ms": r.get("ms_per_step"), "fsg_ms": o, "fsg_unidyn_ms": ou, "ref_detail": r,
+                       "ref_ms": r.get("ms_per_step"), "fsg_ms": o, "fsg_unidyn_ms": ou, "fsg_unidyn_mixed_phase_ms": om, "ref_detail": r,
                        "speedup_same_model": (r["ms_per_step"] / ou) if r.get("ms_per_step") else None,
                        "note": "reference = its unidyn kernels rebuilt with build-time constants for a 128^3 grid (oracle/Makefile); throughput comparison, "
                                "different update physics (leapfrog vs Euler), same pair sums"}
