@@ -13,29 +13,40 @@
 //
 // Same neighbourhood rules as the pure-fluid kernel: 27 bins by linear offset, the first 1024 neighbour particles, the 8-bin
 // octant neighbourhood for home bins with more than 6 particles.  Gather form, one warp per home bin, no atomics: deterministic.
-// These scenes are small (the reference's are 14 k particles); the kernels follow the reference's expression order and promote
-// where it does rather than chase throughput.
+// The frame is the pure-fluid kernel's (fsg_unidyn.cu): the neighbourhood is staged in tiles of UM_TILE candidates with asynchronous
+// 16-byte copies (22 bytes each, 4 warps x 5 blocks per SM), a home particle sweeps only the candidate ranges it may see (its
+// octant's four columns x two z-adjacent bins in a split bin), in-range candidates are queued, the next home particle is requested
+// while this one is processed, and the 25 (pass A) / 5 (pass B) sums of a home particle are reduced over the warp by recursive
+// halving — 31 shuffles instead of 125, lane k ends up holding sum k and stores it.  The pair bodies follow the reference's
+// expression order and promote where it does.
 #include "fsg_unidyn.cuh"
 
-#define UM_WARPS 2
+#define UM_WARPS 4
+#define UM_TILE 512
 #define UM_MIXPRESSURE 1e-12
 #define UM_MIXBROWNIAN 5e-9
 
 struct UmWarpSmem {
-    float4 sp[UNI_TILE];                // x, y, z, +-dens
-    int sj[UNI_TILE];                   // sorted slot of the candidate
-    unsigned short q[UNI_TILE];
-    unsigned char tag[UNI_TILE];
+    float4 sp[UM_TILE];                 // x, y, z, +-dens
+    int sj[UM_TILE];                    // sorted slot of the candidate
+    unsigned short q[UM_TILE];
 };
 #define UM_SMEM (sizeof(UmWarpSmem) * UM_WARPS)
 
-template <int NV>
-__device__ __forceinline__ void um_reduce(float (&v)[NV])
+// v[0 .. 31] summed over the 32 lanes: afterwards v[0] of lane k is the total of value k.  Five halving rounds (16 + 8 + 4 + 2 + 1 = 31
+// shuffles): a lane keeps the half of the values that matches its lane bit and hands the other half to its partner.
+__device__ __forceinline__ float um_reduce_halving(float (&v)[32], int lane)
 {
 #pragma unroll
-    for (int k = 0; k < NV; k++)
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool hi = lane & w;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+        for (int k = 0; k < w; k++) {
+            const float keep = hi ? v[k + w] : v[k], send = hi ? v[k] : v[k + w];
+            v[k] = keep + __shfl_xor_sync(FULL, send, w);
+        }
+    }
+    return v[0];
 }
 
 template <int PASS>
@@ -77,52 +88,82 @@ k_pair_unidyn_mixed(UniArgs a)
         const int hs = __shfl_sync(FULL, st, 13), hn = __shfl_sync(FULL, p, 13);
         const bool split = hn > 6;                  // cu:181
 
+        for (int ig = 0; ig < hn; ig += 32) {
+        const int gcount = min(32, hn - ig);
+#pragma unroll 1
+        for (int t0 = 0; t0 < C; t0 += UM_TILE) {
+        const int t1 = min(t0 + UM_TILE, C);
+        // ---- stage candidates [t0, t1) of the concatenated neighbourhood ----
         __syncwarp();
 #pragma unroll 1
         for (int t = 0; t < 27; t++) {
-            int pt = __shfl_sync(FULL, p, t);
+            const int pt = __shfl_sync(FULL, p, t);
             if (pt == 0) continue;
-            int ex = __shfl_sync(FULL, excl, t), stt = __shfl_sync(FULL, st, t);
-            int hi = min(ex + pt, C);
-            for (int k = ex + lane; k < hi; k += 32) {
-                int j = stt + (k - ex);
-                S.sp[k] = a.A.posd[j];
-                S.sj[k] = j;
-                S.tag[k] = (unsigned char)t;
+            const int ex = __shfl_sync(FULL, excl, t), stt = __shfl_sync(FULL, st, t);
+            const int lo = max(ex, t0), hi = min(ex + pt, t1);
+            for (int k = lo + lane; k < hi; k += 32) {
+                const int j = stt + (k - ex);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&S.sp[k - t0])),
+                             "l"(a.A.posd + j) : "memory");
+                S.sj[k - t0] = j;
             }
         }
+        int my_oct = 0;                              // octants of this group's home particles (cu:182-184), one per lane
+        if (split && lane < gcount) { const float4 ph = a.A.posd[hs + ig + lane]; my_oct = uni_subindex(d, ph.x, ph.y, ph.z); }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
 
+        float4 n_pi = a.A.posd[hs + ig], n_vi = a.A.velp[hs + ig], n_mi = a.A.mix[hs + ig];
 #pragma unroll 1
-        for (int il = 0; il < hn; il++) {
-            const int i = hs + il;
-            const float4 pi = a.A.posd[i], vi = a.A.velp[i], mi = a.A.mix[i];
+        for (int il = 0; il < gcount; il++) {
+            const int i = hs + ig + il;
+            const float4 pi = n_pi, vi = n_vi, mi = n_mi;
+            if (il + 1 < gcount) { n_pi = a.A.posd[i + 1]; n_vi = a.A.velp[i + 1]; n_mi = a.A.mix[i + 1]; }
             const float densi = fabsf(pi.w);
             const bool bi = pi.w < 0.f;
             const float solid_i = mi.x, fluid_i = mi.y, press_i = vi.w;
-            const unsigned allow = split ? uni_octant_mask(uni_subindex(d, pi.x, pi.y, pi.z)) : 0x7ffffffu;
+            // candidate ranges this particle sees: [0, C) or, in a split bin, 4 columns x 2 z-adjacent bins of its octant (cu:579-583)
+            int nr = 1, zlo = 0, ax = 0, ay = 0;
+            if (split) {
+                const int oct = __shfl_sync(FULL, my_oct, il);
+                ax = (oct & 1) ? 1 : -1; ay = (oct & 2) ? 1 : -1;
+                zlo = (oct & 4) ? 0 : 1;
+                nr = 4;
+            }
             int qn = 0;
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                int c = c0 + lane;
-                bool in = false;
-                if (c < C) {
-                    const bool ok = (allow >> S.tag[c]) & 1u;
-                    float4 pj = S.sp[c];
-                    float d2 = dist2(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-                    in = ok && (d2 <= d.d2_max) && (d2 > 0.f);       // cu:287
-                    if (PASS == 1) in = in && sqrtf(d2) <= d.h_lt;   // every pass-B term carries dW, whose support is h (cu:35-43)
+#pragma unroll 1
+            for (int r = 0; r < nr; r++) {
+                int lo = 0, hi = C;
+                if (split) {
+                    const int a_ = (r & 1) ? ax : 0, b_ = (r & 2) ? ay : 0;
+                    const int tl = (a_ + 1) * 9 + (b_ + 1) * 3 + zlo;
+                    lo = __shfl_sync(FULL, excl, tl);
+                    hi = __shfl_sync(FULL, excl, tl + 1) + __shfl_sync(FULL, p, tl + 1);
+                    hi = min(hi, C);
                 }
-                unsigned mk = __ballot_sync(FULL, in);
-                if (in) S.q[qn + __popc(mk & lt_mask)] = (unsigned short)c;
-                qn += __popc(mk);
+                lo = max(lo, t0);
+                hi = min(hi, t1);
+                for (int c0 = lo; c0 < hi; c0 += 32) {
+                    const int c = c0 + lane;
+                    bool in = false;
+                    if (c < hi) {
+                        const float4 pj = S.sp[c - t0];
+                        const float d2 = dist2(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+                        in = (d2 <= d.d2_max) && (d2 > 0.f);             // cu:287
+                        if (PASS == 1) in = in && sqrtf(d2) <= d.h_lt;   // every pass-B term carries dW, whose support is h (cu:35-43)
+                    }
+                    const unsigned mk = __ballot_sync(FULL, in);
+                    if (in) S.q[qn + __popc(mk & lt_mask)] = (unsigned short)(c - t0);
+                    qn += __popc(mk);
+                }
             }
             __syncwarp();
 
             if (PASS == 0) {
                 // acc: 0 newdens, 1-3 newdelpress, 4-6 diffusion, 7-9 solid drift, 10-12 fluid drift, 13-21 vel_grad, 22-24 stress_accel
-                float acc[25];
+                float acc[32];
 #pragma unroll
-                for (int k = 0; k < 25; k++) acc[k] = 0.f;
+                for (int k = 0; k < 32; k++) acc[k] = 0.f;
                 const float4 dpi = a.A.dpi[i];                                          // delpress of the home particle (:342-348)
                 float sti[9];
 #pragma unroll
@@ -206,17 +247,20 @@ k_pair_unidyn_mixed(UniArgs a)
                         }
                     }
                 }
-                um_reduce<25>(acc);
-                if (lane == 0) {
-                    a.sums[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                    a.sums2[i] = make_float4(acc[4], acc[5], acc[6], 0.f);
-                    float *o = a.mixA + (size_t)i * UNI_MIXA;
-#pragma unroll
-                    for (int k = 0; k < UNI_MIXA; k++) o[k] = acc[7 + k];
+                const float tot = um_reduce_halving(acc, lane);          // lane k: sum number k
+                {
+                    // 0-3 -> sums, 4-6 -> sums2.xyz, 7-24 -> mixA[0..17]; lane 25 clears sums2.w (delfluid comes from pass B)
+                    float *dst = lane < 4 ? reinterpret_cast<float *>(a.sums + i) + lane
+                                 : lane < 7 ? reinterpret_cast<float *>(a.sums2 + i) + (lane - 4)
+                                 : lane < 25 ? a.mixA + (size_t)i * UNI_MIXA + (lane - 7) : reinterpret_cast<float *>(a.sums2 + i) + 3;
+                    if (lane < 25) *dst = t0 == 0 ? tot : *dst + tot;
+                    else if (lane == 25 && t0 == 0) *dst = 0.f;
                 }
             } else {
                 // pass B, cu:383-401: 0-2 mixture_accel, 3 delsolid, 4 delfluid
-                float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                float acc[32];
+#pragma unroll
+                for (int k = 0; k < 32; k++) acc[k] = 0.f;
                 const float *di = a.mixA + (size_t)i * UNI_MIXA;
                 const float sdi[3] = {di[0], di[1], di[2]}, fdi[3] = {di[3], di[4], di[5]};
                 for (int q = lane; q < qn; q += 32) {
@@ -249,15 +293,16 @@ k_pair_unidyn_mixed(UniArgs a)
                                       (double)((-(fluid_i * fdi[0] + fluid_j * fdj[0]) * dkx - (fluid_i * fdi[1] + fluid_j * fdj[1]) * dky -
                                                 (fluid_i * fdi[2] + fluid_j * fdj[2]) * dkz) / densj));                   // cu:401
                 }
-                um_reduce<5>(acc);
-                if (lane == 0) {
-                    float *o = a.mixB + (size_t)i * UNI_MIXB;
-#pragma unroll
-                    for (int k = 0; k < 5; k++) o[k] = acc[k];
+                const float tot = um_reduce_halving(acc, lane);
+                if (lane < 5) {
+                    float *dst = a.mixB + (size_t)i * UNI_MIXB + lane;
+                    *dst = t0 == 0 ? tot : *dst + tot;
                 }
             }
             __syncwarp();
         }
+        }       // tiles
+        }       // groups of 32 home particles
         __syncwarp();
     }
 }
@@ -271,7 +316,7 @@ cudaError_t fsg_launch_unidyn_mixed(const UniArgs &a, int pass, int sm_count, cu
         cudaFuncSetAttribute(k_pair_unidyn_mixed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM);
     }
     int64_t blocks = ((int64_t)a.n + UM_WARPS - 1) / UM_WARPS;
-    const int64_t maxb = (int64_t)sm_count * 4;
+    const int64_t maxb = (int64_t)sm_count * 5;           // 5 x 45 KB of shared memory per SM
     if (blocks > maxb) blocks = maxb;
     if (pass == 0) k_pair_unidyn_mixed<0><<<(unsigned)blocks, UM_WARPS * 32, UM_SMEM, s>>>(a);
     else k_pair_unidyn_mixed<1><<<(unsigned)blocks, UM_WARPS * 32, UM_SMEM, s>>>(a);
