@@ -43,7 +43,7 @@ ALG_BYTES_PAIR = 132      # pair sums + EOS/integrate/re-bin as ONE phase (surve
 ALG_BYTES_PAIR_DEFERRED = 48
 ALG_BYTES_STREAM_DEFERRED = 188   # key sort (8 + 8 + 16) + reorder with update (8 keys/perm, 64 + 16 in, 64 + 4 out)
 # measured DRAM bytes per particle of the pair kernel (ncu --set full at 256^3): [symmetric k_pair_v3, gather k_pair_v2]
-NCU_PAIR_DRAM_BYTES_PER_PARTICLE = [(62.5, "profiles/r2_ncu_pair_v3.txt"), (47.2, "profiles/r1_ncu_pair_v2_final.txt")]
+NCU_PAIR_DRAM_BYTES_PER_PARTICLE = [(65.2, "profiles/r2_ncu_pair_v3_512.txt"), (47.2, "profiles/r1_ncu_pair_v2_final.txt")]
 FLOP_IN_RANGE, FLOP_REJECTED = 50, 12   # SURVEY.md §8d algorithmic flop per in-range / rejected candidate
 SPACING, JITTER, SEED = 0.05, 0.005, 20261018
 CPU_SAMPLE_GRID = 128     # bounded sample for the CPU legs: the same plume at 128^3 bins (1.07 M particles)
@@ -533,7 +533,7 @@ def fsg_arm(args):
                                                    " + k_update (EOS/integrate/re-bin)"), "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": ncu_b[0] * n_local + (0.0 if deferred else 152.0 * n_local), "peak_source": peak_src,
-                "traffic_note": f"pair kernel: dram__bytes_read+write = {ncu_b[0]} B/particle under ncu --set full at 256^3 ({ncu_b[1]}), "
+                "traffic_note": f"pair kernel: dram__bytes_read+write = {ncu_b[0]} B/particle under ncu --set full ({ncu_b[1]}), "
                                 "scaled by the particle count" + ("" if deferred else "; k_update: its 152 B/particle of streaming reads + writes"),
                 "kernel_ms": pair_ms, "share_of_step": pair_ms / ms_step,
                 "algorithmic_bytes_per_launch": alg_pair * n_local,
