@@ -778,12 +778,7 @@ extern "C" int fsg_step(fsg_ctx *c, int nsteps)
             if (c->slab2) { int rc = fsg_slab2_reset_ghost_tables(c); if (rc != FSG_OK) return rc; }
         }
         const int nxt = c->cur ^ 1;
-        CU(c, cudaMemsetAsync(c->counters + nxt, 0, sizeof(int), c->stream));
-        CU(c, cudaMemsetAsync(c->counters + 2, 0, 2 * sizeof(int), c->stream));
-        CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(int), c->stream));
-        CU(c, cudaMemsetAsync(c->counters + 10, 0, 2 * sizeof(int), c->stream));
-        if (c->cfg.world > 1) CU(c, fsg_launch_fill(c->counters + 16, (int)n, 4, c->stream));
-        if (c->cfg.collect_stats) CU(c, cudaMemsetAsync(c->dstats, 0, 4 * sizeof(unsigned long long), c->stream));
+        CU(c, fsg_launch_step_counters(c->counters, nxt, (int)n, c->cfg.world > 1, c->cfg.collect_stats ? c->dstats : nullptr, c->stream));
         if (prof) prof_mark(c);
         // thrust::sort_by_key, key half (solver.cu:181)
         if (c->keys_prev_valid && nearly_sorted_enabled(c)) {

@@ -26,6 +26,25 @@ cudaError_t fsg_launch_iota(int *p, int64_t n, cudaStream_t s)
     k_iota<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n);
     return cudaGetLastError();
 }
+// the per-step resets of the device-side counters in ONE launch (they were five memsets and a fill: on small scenes the step is
+// bound by its launch count): nocc of the next list, work counter + n_live, n_keep, the boundary list's pair, the slab bounds
+// (preset to n), the pair statistics
+__global__ void k_step_counters(int *counters, int nxt, int n, bool slab, unsigned long long *dstats)
+{
+    const int t = threadIdx.x;
+    if (t == 0) counters[nxt] = 0;
+    if (t == 1) { counters[2] = 0; counters[3] = 0; }
+    if (t == 2) counters[5] = 0;
+    if (t == 3) { counters[10] = 0; counters[11] = 0; }
+    if (slab && t >= 4 && t < 8) counters[16 + (t - 4)] = n;
+    if (dstats && t >= 8 && t < 12) dstats[t - 8] = 0ull;
+}
+cudaError_t fsg_launch_step_counters(int *counters, int nxt, int n, bool slab, unsigned long long *dstats, cudaStream_t s)
+{
+    k_step_counters<<<1, 32, 0, s>>>(counters, nxt, n, slab, dstats);
+    return cudaGetLastError();
+}
+
 cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;

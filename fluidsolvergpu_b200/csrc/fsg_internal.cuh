@@ -175,6 +175,7 @@ cudaError_t fsg_nsort(void *ws, const int *keys_new, const int *keys_prev, int *
 // fsg_base_kernels.cu
 cudaError_t fsg_launch_iota(int *p, int64_t n, cudaStream_t s);
 cudaError_t fsg_launch_fill(int *p, int v, int64_t n, cudaStream_t s);
+cudaError_t fsg_launch_step_counters(int *counters, int nxt, int n, bool slab, unsigned long long *dstats, cudaStream_t s);
 cudaError_t fsg_launch_keys(const FsgDev &d, const float4 *posd, int *keys, int64_t n, int *any_boundary, bool slab_filter,
                             const int *slot_state, cudaStream_t s);
 cudaError_t fsg_launch_reset_tables_keys(const FsgDev &d, const int *keysA, int *start, int *end, int64_t n, cudaStream_t s);
